@@ -1,0 +1,208 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz by running the REFERENCE's own Cython build (oracle/_ref,
+built by oracle/build_ref.py from /root/reference) on seeded inputs.  Run in the build
+container only (``/root/reference`` does not exist on the GPU box); the .npz outputs are
+committed.  Everything is fp64.  Usage:  python tests/golden/make_golden.py
+"""
+import os
+import pickle
+import sys
+from itertools import islice
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import build_ref, ref_loader  # noqa: E402
+
+build_ref.build()
+ref = ref_loader.load()
+ActivePMF = ref.active_pmf.ActivePMF
+BayesianPMF = ref.bayes_pmf.BayesianPMF
+PMF = ref.pmf_cy.ProbabilisticMatrixFactorization
+normal_gradient = ref.normal_exps_cy.normal_gradient
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrs.items()})
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def all_cells(n, m):
+    ii, jj = np.meshgrid(np.arange(n), np.arange(m), indexing="ij")
+    return ii.ravel(), jj.ravel()
+
+
+def approx_outputs(a, cells):
+    ii, jj = cells
+    pv = np.array([a.pred_variance((i, j)) for i, j in zip(ii, jj)])
+    pm = np.array([a.approx_pred_mean_var(i, j)[0] for i, j in zip(ii, jj)])
+    ph = np.array([a.prob_ge_half((i, j)) for i, j in zip(ii, jj)])
+    p35 = np.array([a.prob_ge_3_5((i, j)) for i, j in zip(ii, jj)])
+    pr = np.array([a.pred((i, j)) for i, j in zip(ii, jj)])
+    gm, gc = normal_gradient(a)
+    return dict(cand_i=ii, cand_j=jj, pred=pr, pred_mean=pm, pred_variance=pv,
+                prob_ge_half=ph, prob_ge_3_5=p35, kl=a.kl_divergence(),
+                grad_mean=gm, grad_cov=gc, approx_entropy=a._approx_entropy())
+
+
+# ---- case 1: the SURVEY.md 8c known-answer input (10x10, d=2, 18 ratings) ------------
+def case_known_answer():
+    with open("/root/reference/results/criteria/10x10_r1_u10_v10_1/data.pkl", "rb") as f:
+        R = np.asarray(pickle.load(f)["_ratings"], dtype=float)
+    n = m = 10
+    d = 2
+    users = (np.arange(n * d).reshape(n, d) + 1) / 7
+    items = (np.arange(m * d).reshape(m, d)[::-1] + 2) / 3
+    a = ActivePMF(R, d)
+    a.users, a.items = users.copy(), items.copy()
+    k = (n + m) * d
+    mean = np.hstack((users.ravel(), items.ravel()))
+    B = np.cos(np.arange(k * k).reshape(k, k) * 0.37)
+    cov = B @ B.T / k + np.eye(k)
+    a.mean, a.cov = mean.copy(), cov.copy()
+    gu, gv = a.gradient()
+    out = dict(ratings=R, users=users, items=items, mean=mean, cov=cov,
+               ll=a.log_likelihood(), full_ll=a.full_ll(), grad_u=gu, grad_v=gv)
+    out.update(approx_outputs(a, all_cells(n, m)))
+    # Bayesian pieces on the same input
+    b = BayesianPMF(R, 2, subtract_mean=False)
+    b.users, b.items = users.copy(), items.copy()
+    sel = R[:, 0] == 0
+    np.random.seed(0)
+    out["sample_feature0"] = b.sample_feature(0, True, np.zeros(2), np.eye(2), items,
+                                              R[sel, 1].astype(int), R[sel, 2])
+    np.random.seed(0)
+    mu, alpha = b.sample_hyperparam(users, True)
+    out["hyper_mu"], out["hyper_alpha"] = mu, alpha
+    np.random.seed(0)
+    s = list(islice(b.samples(num_gibbs=2), 3))
+    out["samples_u"] = np.array([x[0] for x in s])
+    out["samples_v"] = np.array([x[1] for x in s])
+    out["bayes_pred_variance"] = b.pred_variance(s)
+    out["bayes_predict"] = b.predict(s)
+    out["bayes_prob_ge_half"] = b.prob_ge_cutoff(s, 0.5)
+    save("known_answer_10x10_d2", **out)
+
+
+def random_problem(seed, n, m, d, nnz, values=None, scale=1.0):
+    rng = np.random.RandomState(seed)
+    cells = rng.permutation(n * m)[:nnz]
+    # every row and column rated at least once
+    ii, jj = list(cells // m), list(cells % m)
+    for i in range(n):
+        if i not in ii:
+            ii.append(i); jj.append(rng.randint(m))
+    for j in range(m):
+        if j not in jj:
+            jj.append(j); ii.append(rng.randint(n))
+    seen, keep = set(), []
+    for t, ij in enumerate(zip(ii, jj)):
+        if ij not in seen:
+            seen.add(ij); keep.append(t)
+    ii, jj = np.array(ii)[keep], np.array(jj)[keep]
+    tu, tv = rng.normal(0, scale, (n, d)), rng.normal(0, scale, (m, d))
+    r = np.einsum("nd,nd->n", tu[ii], tv[jj]) + rng.normal(0, .25, len(ii))
+    if values is not None:
+        vals = np.array(sorted(values), dtype=float)
+        r = vals[np.abs(r[:, None] - vals[None, :]).argmin(1)]
+    R = np.column_stack((ii, jj, r)).astype(float)
+    users, items = rng.uniform(0, 1, (n, d)), rng.uniform(0, 1, (m, d))
+    return rng, R, users, items
+
+
+# ---- case 2: latent_d = 5 (exercises the d > 2 quirks of normal_gradient) ------------
+def case_d5():
+    n, m, d = 12, 20, 5
+    rng, R, users, items = random_problem(11, n, m, d, 80)
+    a = ActivePMF(R, d)
+    a.users, a.items = users.copy(), items.copy()
+    a.sigma_sq, a.sigma_u_sq, a.sigma_v_sq = 0.7, 6.0, 11.0
+    k = (n + m) * d
+    mean = np.hstack((users.ravel(), items.ravel())) + rng.normal(0, .05, k)
+    S = rng.normal(0, 1, (k, k))
+    cov = ref.active_pmf.project_psd(S @ S.T / k * .3 + rng.normal(0, .01, (k, k)), 1e-5)
+    a.mean, a.cov = mean.copy(), cov.copy()
+    gu, gv = a.gradient()
+    out = dict(ratings=R, users=users, items=items, mean=mean, cov=cov,
+               sigma_sq=a.sigma_sq, sigma_u_sq=a.sigma_u_sq, sigma_v_sq=a.sigma_v_sq,
+               ll=a.log_likelihood(), full_ll=a.full_ll(), grad_u=gu, grad_v=gv)
+    out.update(approx_outputs(a, all_cells(n, m)))
+    save("random_12x20_d5", **out)
+
+
+# ---- case 3: MAP fit trajectory + subtract_mean --------------------------------------
+def case_fit():
+    n, m, d = 30, 40, 4
+    rng, R, users, items = random_problem(5, n, m, d, 300, scale=.8)
+    out = dict(ratings=R, users0=users, items0=items)
+    for sm in (False, True):
+        p = PMF(R, d, sm)
+        p.users, p.items = users.copy(), items.copy()
+        tag = "_sm" if sm else ""
+        gu, gv = p.gradient()
+        out["ll0" + tag], out["grad_u0" + tag], out["grad_v0" + tag] = p.log_likelihood(), gu, gv
+        lls = list(p.fit_lls())
+        out["lls" + tag] = np.array(lls)
+        out["users_fit" + tag], out["items_fit" + tag] = p.users, p.items
+        out["mean_rating"] = p.mean_rating
+        real = rng.normal(0, 1, (n, m))
+        out["real"] = real
+        out["rmse" + tag] = p.rmse(real)
+        p.update_sigma(); p.update_sigma_uv()
+        out["sigmas" + tag] = np.array([p.sigma_sq, p.sigma_u_sq, p.sigma_v_sq])
+    save("fit_30x40_d4", **out)
+
+
+# ---- case 4: variational fit + lookahead criteria on a toy problem -------------------
+def case_lookahead():
+    n, m, d = 6, 7, 2
+    rng, R, users, items = random_problem(3, n, m, d, 14, values=(0., 1.), scale=.7)
+    a = ActivePMF(R, d, rating_values={0, 1}, discrete_expectations=True)
+    a.users, a.items = users.copy(), items.copy()
+    a.fit()
+    np.random.seed(4)
+    a.initialize_approx()
+    cov0 = a.cov.copy()
+    mean0 = a.mean.copy()
+    kls = list(a.fit_normal_kls())
+    out = dict(ratings=R, users=a.users, items=a.items, mean0=mean0, cov0=cov0,
+               kls=np.array(kls), mean=a.mean, cov=a.cov)
+    cand = sorted(a.unrated)
+    ii, jj = np.array(cand).T
+    out["cand_i"], out["cand_j"] = ii, jj
+    out["pred_variance"] = np.array([a.pred_variance(c) for c in cand])
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["uv_entropy"] = np.array([a.exp_approx_entropy(c) for c in cand])
+        out["uv_entropy_approx"] = np.array([a.exp_approx_entropy_byapprox(c) for c in cand])
+        out["total_variance"] = np.array([a.exp_total_variance(c) for c in cand])
+    save("lookahead_6x7_d2", **out)
+
+
+# ---- case 5: Gibbs chain with subtract_mean, d = 3 -----------------------------------
+def case_gibbs():
+    n, m, d = 15, 12, 3
+    rng, R, users, items = random_problem(9, n, m, d, 70, values=(1., 2., 3., 4., 5.), scale=1.2)
+    b = BayesianPMF(R, d)                       # subtract_mean=True default
+    b.users, b.items = users.copy(), items.copy()
+    np.random.seed(21)
+    s = list(islice(b.samples(num_gibbs=2), 6))
+    ii, jj = all_cells(n, m)
+    out = dict(ratings=R, users=users, items=items, seed=21, mean_rating=b.mean_rating,
+               samples_u=np.array([x[0] for x in s]), samples_v=np.array([x[1] for x in s]),
+               cand_i=ii, cand_j=jj,
+               bayes_predict=b.predict(s)[ii, jj],
+               bayes_pred_variance=b.pred_variance(s)[ii, jj],
+               bayes_prob_ge_3_5=b.prob_ge_cutoff(s, 3.5)[ii, jj],
+               bayes_total_variance=b.total_variance(s))
+    save("gibbs_15x12_d3", **out)
+
+
+if __name__ == "__main__":
+    case_known_answer()
+    case_d5()
+    case_fit()
+    case_lookahead()
+    case_gibbs()

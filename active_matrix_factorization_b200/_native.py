@@ -1,0 +1,126 @@
+"""ctypes binding of libamf_b200.so (the C ABI in include/amf_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is missing or no
+sm_100-class device is visible, importing callers get a loud RuntimeError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libamf_b200.so")
+
+F32, F64 = 0, 1
+CRIT_PRED, CRIT_APPROX_MEAN, CRIT_PRED_VARIANCE, CRIT_PROB_GE = 0, 1, 2, 3
+
+
+class PmfParams(C.Structure):
+    _fields_ = [("sigma_sq", C.c_double), ("sigma_u_sq", C.c_double),
+                ("sigma_v_sq", C.c_double), ("mean_offset", C.c_double)]
+
+
+class NormalView(C.Structure):
+    _fields_ = [("mean_u", C.c_void_p), ("mean_u_stride", C.c_int64),
+                ("mean_v", C.c_void_p), ("mean_v_stride", C.c_int64),
+                ("cov_uu", C.c_void_p), ("uu_stride", C.c_int64), ("uu_ld", C.c_int64),
+                ("cov_vv", C.c_void_p), ("vv_stride", C.c_int64), ("vv_ld", C.c_int64),
+                ("cov_uv", C.c_void_p), ("uv_stride_i", C.c_int64),
+                ("uv_stride_j", C.c_int64), ("uv_ld", C.c_int64)]
+
+
+class Best(C.Structure):
+    _fields_ = [("value", C.c_double), ("index", C.c_int64)]
+
+
+_P = C.c_void_p
+_I32, _I64, _F64 = C.c_int32, C.c_int64, C.c_double
+_INT = C.c_int
+
+# name -> argtypes; every symbol declared in include/amf_b200.h appears here
+PROTOTYPES = {
+    "amf_version": [],
+    "amf_device_info": [C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)],
+    "amf_ratings_create": [C.POINTER(_P), _I32, _I32, _I64, _P, _P, _P, _INT, _P],
+    "amf_ratings_create_host": [C.POINTER(_P), _I32, _I32, _I64, _P, _P, _P, _INT],
+    "amf_ratings_destroy": [_P],
+    "amf_ratings_nnz": [_P],
+    "amf_ratings_layout": [_P, _INT, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
+    "amf_ratings_mean": [_P, C.POINTER(_F64), _P],
+    "amf_pmf_loss_grad": [_P, _INT, _INT, _INT, _P, _P, C.POINTER(PmfParams), _P, _P, _P, _P],
+    "amf_axpy": [_INT, _I64, _P, _P, _F64, _P, _P],
+    "amf_pmf_grad_coo": [_INT, _I64, _P, _P, _P, _INT, _INT, _P, _P, C.POINTER(PmfParams),
+                         _P, _P, _P, _P],
+    "amf_momentum_step": [_INT, _I64, _P, _P, _F64, _F64, _P, _P],
+    "amf_pmf_prior": [_INT, _I64, _P, _F64, _P, _P, _P],
+    "amf_pmf_loss_grad_host": [_P, _INT, _INT, _P, _P, C.POINTER(PmfParams), _P, _P, _P],
+    "amf_score_candidates": [_INT, _INT, _I64, _P, _P, _INT, _INT, _P, _P,
+                             C.POINTER(NormalView), _F64, _P, _INT, _I64, _P, _P],
+    "amf_gibbs_half_sweep": [_P, _INT, _INT, _INT, _P, _P, _P, _F64, _F64, _P, _P, _P],
+    "amf_gibbs_status": [_P, C.POINTER(_INT), _P],
+    "amf_bayes_sample_stats": [_INT, _I64, _P, _P, _INT, _I32, _I32, _INT, _P, _P, _F64, _F64,
+                               _P, _P, _P, _INT, _INT, _I64, _P, _P],
+    "amf_score_pred_host": [_INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT,
+                            C.POINTER(Best)],
+}
+
+_lib = None
+
+
+def library_path():
+    return LIB_PATH
+
+
+def load():
+    """Loads the shared library (no device needed) and applies the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libamf_b200.so is not built (%s). Run `python -m active_matrix_factorization_b200.build`. "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.amf_last_error.restype = C.c_char_p
+    lib.amf_last_error.argtypes = []
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = _I64 if name == "amf_ratings_nnz" else _INT
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libamf_b200: " + load().amf_last_error().decode("utf-8", "replace"))
+
+
+_device_checked = False
+
+
+def require_device():
+    """Fails loudly unless a CUDA device is usable.  Called by every compute path."""
+    global _device_checked
+    lib = load()
+    if _device_checked:
+        return lib
+    n, arch, sms = _INT(), _INT(), _INT()
+    check(lib.amf_device_info(C.byref(n), C.byref(arch), C.byref(sms)))
+    if arch.value < 100:
+        raise RuntimeError("libamf_b200 targets sm_100a; found sm_%d" % arch.value)
+    _device_checked = True
+    return lib
+
+
+def dtype_code(np_dtype):
+    np_dtype = np.dtype(np_dtype)
+    if np_dtype == np.float32:
+        return F32
+    if np_dtype == np.float64:
+        return F64
+    raise TypeError("unsupported dtype %r" % (np_dtype,))
+
+
+def host_ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,159 @@
+// Shared internals of libamf_b200 (sm_100a).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/amf_b200.h"
+
+namespace amf {
+
+void set_error(const char* fmt, ...);
+
+#define AMF_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t err__ = (call);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      amf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                       \
+                     cudaGetErrorString(err__));                                         \
+      return AMF_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define AMF_REQUIRE(cond, ...)                                                           \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      amf::set_error(__VA_ARGS__);                                                       \
+      return AMF_ERR_INVALID;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define AMF_LAUNCH_CHECK() AMF_CUDA(cudaGetLastError())
+
+int num_sms();
+
+// ---- 16-byte vectors of the compute type ---------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  using type = float4;
+  static constexpr int N = 4;
+};
+template <> struct Vec<double> {
+  using type = double2;
+  static constexpr int N = 2;
+};
+
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ double2 vzero(double2) { return make_double2(0., 0.); }
+__device__ __forceinline__ float vdot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ double vdot(const double2& a, const double2& b) {
+  return fma(a.x, b.x, a.y * b.y);
+}
+__device__ __forceinline__ void vfma(float4& acc, float s, const float4& b) {
+  acc.x = fmaf(s, b.x, acc.x); acc.y = fmaf(s, b.y, acc.y);
+  acc.z = fmaf(s, b.z, acc.z); acc.w = fmaf(s, b.w, acc.w);
+}
+__device__ __forceinline__ void vfma(double2& acc, double s, const double2& b) {
+  acc.x = fma(s, b.x, acc.x); acc.y = fma(s, b.y, acc.y);
+}
+// vector reduction into global memory (no return value): RED.E.ADD.F32x4 on sm_100a
+__device__ __forceinline__ void vred_add(float* p, const float4& v) {
+  atomicAdd(reinterpret_cast<float4*>(p), v);
+}
+__device__ __forceinline__ void vred_add(double* p, const double2& v) {
+  atomicAdd(p, v.x);
+  atomicAdd(p + 1, v.y);
+}
+// streaming (read-once) loads that do not pollute L1
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of a double, result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double smem_part[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem_part[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem_part[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// ---- arg-best of (value, index): better value wins, lower index on ties, NaN never wins ------
+struct Best {
+  double v;
+  long long i;
+};
+template <bool MAX>
+__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
+  if (i < 0) return false;
+  if (v != v) return false;
+  if (bi < 0) return true;
+  if (MAX ? (v > bv) : (v < bv)) return true;
+  return v == bv && i < bi;
+}
+template <bool MAX>
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (better<MAX>(ov, oi, b.v, b.i)) { b.v = ov; b.i = oi; }
+  }
+  return b;
+}
+// result valid in thread 0
+template <bool MAX>
+__device__ __forceinline__ Best block_best(Best b) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  b = warp_best<MAX>(b);
+  if (lane == 0) { sv[w] = b.v; si[w] = b.i; }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (threadIdx.x < nw) { b.v = sv[threadIdx.x]; b.i = si[threadIdx.x]; }
+  else { b.v = 0; b.i = -1; }
+  if (w == 0) b = warp_best<MAX>(b);
+  __syncthreads();
+  return b;
+}
+
+// final reduction of per-block partial winners (launch with one block)
+int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
+                      cudaStream_t s);
+
+}  // namespace amf
+
+struct amf_ratings {
+  int32_t n_users, n_items;
+  int64_t nnz;
+  int dtype;
+  // side 0: user-major (rows = users, idx = item); side 1: item-major
+  int64_t* ptr[2];      // [rows+1]
+  int32_t* idx[2];      // [nnz]
+  void* val[2];         // [nnz] of dtype
+  int32_t* sub_row[2];  // row containing entry s*AMF_SUB, one per sub-chunk of AMF_SUB entries
+  int64_t n_sub;
+  // staging for *_host entry points (grown on demand)
+  void* stage[8];
+  size_t stage_bytes[8];
+  double* sums_d;
+  int device;
+};
+
+#define AMF_SUB 32

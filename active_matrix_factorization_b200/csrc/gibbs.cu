@@ -1,0 +1,282 @@
+// Bayesian PMF: batched row/column conditionals of the Gibbs sampler and streaming sample
+// statistics over posterior samples.
+//
+//   amf_gibbs_half_sweep : bayes_pmf.py:189-216 sample_feature for every row of one side
+//                          (the loops at :286-292 / :294-300), one CTA per row.
+//   amf_bayes_sample_stats : bayes_pmf.py:433-455 predict / pred_variance and :528-538
+//                          prob_ge_cutoff without materialising S dense N x M matrices.
+//
+// The reference draws z ~ N(0, I_d) per row from numpy's global stream, in row order; the host
+// passes those draws in (z_d) so a seeded chain reproduces the reference's samples.  As in the
+// reference the sample is  chol(inv(Lambda)) z + mean  (lower factor of the COVARIANCE), not the
+// cheaper  Lambda = R R', x = mean + R^-T z, which has the same law but different values.
+#include "common.cuh"
+
+namespace amf {
+
+constexpr int GIBBS_THREADS = 128;
+constexpr int GIBBS_TILE = 32;   // rated rows staged per tile
+constexpr int GIBBS_MAXD = 64;
+constexpr int GIBBS_MAXACC = (GIBBS_MAXD * GIBBS_MAXD + GIBBS_THREADS - 1) / GIBBS_THREADS;
+
+// in-place lower Cholesky of the d x d matrix A (leading dimension lda) in shared memory.
+// Returns false (to all threads) if a pivot is not positive.
+__device__ bool chol_lower(double* A, int d, int lda, int* flag) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) *flag = 1;
+  __syncthreads();
+  for (int j = 0; j < d; ++j) {
+    if (tid == 0) {
+      double pv = A[j * lda + j];
+      if (!(pv > 0.0)) *flag = 0;
+      A[j * lda + j] = sqrt(pv);
+    }
+    __syncthreads();
+    const double inv = 1.0 / A[j * lda + j];
+    for (int i = j + 1 + tid; i < d; i += nt) A[i * lda + j] *= inv;
+    __syncthreads();
+    const int rem = d - j - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int i = j + 1 + t / rem, k = j + 1 + t % rem;
+      if (k <= i) A[i * lda + k] -= A[i * lda + j] * A[k * lda + j];
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < d * d; t += nt) {
+    const int i = t / d, k = t % d;
+    if (k > i) A[i * lda + k] = 0.0;
+  }
+  __syncthreads();
+  return *flag != 0;
+}
+
+// Linv = inverse of the lower-triangular L (both d x d in shared memory, distinct buffers)
+__device__ void tri_inverse_lower(const double* L, double* Linv, int d, int lda) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int c = tid; c < d; c += nt) {          // column c of the inverse: L x = e_c
+    for (int i = 0; i < d; ++i) {
+      if (i < c) { Linv[i * lda + c] = 0.0; continue; }
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= L[i * lda + k] * Linv[k * lda + c];
+      Linv[i * lda + c] = s / L[i * lda + i];
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GIBBS_THREADS)
+gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                  const T* __restrict__ val, int rows, int d, const T* __restrict__ other,
+                  const T* __restrict__ alpha, const T* __restrict__ mu, double beta,
+                  double mean_offset, const T* __restrict__ z, T* __restrict__ out,
+                  int* __restrict__ fail) {
+  extern __shared__ double smem[];
+  const int lda = d + 1;
+  double* A = smem;                 // d x lda : Lambda -> chol -> ...
+  double* Bm = A + d * lda;         // d x lda : scratch
+  double* rhs = Bm + d * lda;       // d
+  double* mean = rhs + d;           // d
+  double* tile_r = mean + d;        // GIBBS_TILE
+  T* tile = reinterpret_cast<T*>(tile_r + GIBBS_TILE);   // GIBBS_TILE x (d+1)
+  __shared__ int flag;
+  const int tid = threadIdx.x;
+  const int ldt = d + 1;
+
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int64_t p0 = ptr[row], p1 = ptr[row + 1];
+    // ---- Gram matrix F'F and F'(r - offset), accumulated per thread over (k,l) pairs ------
+    T acc[GIBBS_MAXACC];
+#pragma unroll
+    for (int a = 0; a < GIBBS_MAXACC; ++a) acc[a] = 0;
+    T racc = 0;                                  // thread k < d accumulates rhs[k]
+    for (int64_t base = p0; base < p1; base += GIBBS_TILE) {
+      const int cnt = (int)min((int64_t)GIBBS_TILE, p1 - base);
+      for (int t = tid; t < cnt * d; t += GIBBS_THREADS) {
+        const int e = t / d, k = t % d;
+        tile[e * ldt + k] = other[(int64_t)idx[base + e] * d + k];
+      }
+      for (int t = tid; t < cnt; t += GIBBS_THREADS) tile_r[t] = (double)val[base + t] - mean_offset;
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < GIBBS_MAXACC; ++a) {
+        const int pr = tid + a * GIBBS_THREADS;
+        if (pr < d * d) {
+          const int k = pr / d, l = pr % d;
+          T s = acc[a];
+          for (int e = 0; e < cnt; ++e) s = fma(tile[e * ldt + k], tile[e * ldt + l], s);
+          acc[a] = s;
+        }
+      }
+      if (tid < d) {
+        T s = racc;
+        for (int e = 0; e < cnt; ++e) s = fma(tile[e * ldt + tid], (T)tile_r[e], s);
+        racc = s;
+      }
+      __syncthreads();
+    }
+    // ---- Lambda = alpha + beta F'F ; rhs = beta F'r + alpha mu ---------------------------
+#pragma unroll
+    for (int a = 0; a < GIBBS_MAXACC; ++a) {
+      const int pr = tid + a * GIBBS_THREADS;
+      if (pr < d * d) {
+        const int k = pr / d, l = pr % d;
+        A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)acc[a];
+      }
+    }
+    if (tid < d) {
+      double s = beta * (double)racc;
+      for (int l = 0; l < d; ++l) s += (double)alpha[tid * d + l] * (double)mu[l];
+      rhs[tid] = s;
+    }
+    __syncthreads();
+    // ---- cov = Lambda^-1 via Cholesky: Lambda = R R', cov = R^-T R^-1 ---------------------
+    bool ok = chol_lower(A, d, lda, &flag);
+    tri_inverse_lower(A, Bm, d, lda);            // Bm = R^-1
+    for (int t = tid; t < d * d; t += GIBBS_THREADS) {
+      const int k = t / d, l = t % d;
+      double s = 0;
+      for (int q = max(k, l); q < d; ++q) s += Bm[q * lda + k] * Bm[q * lda + l];
+      A[k * lda + l] = s;                        // cov
+    }
+    __syncthreads();
+    if (tid < d) {
+      double s = 0;
+      for (int l = 0; l < d; ++l) s += A[tid * lda + l] * rhs[l];
+      mean[tid] = s;
+    }
+    __syncthreads();
+    ok = chol_lower(A, d, lda, &flag) && ok;     // A = lower chol of cov
+    if (tid < d) {
+      double s = mean[tid];
+      for (int l = 0; l <= tid; ++l) s += A[tid * lda + l] * (double)z[(int64_t)row * d + l];
+      out[(int64_t)row * d + tid] = (T)s;
+    }
+    if (!ok && tid == 0) atomicExch(fail, 1);
+    __syncthreads();
+  }
+}
+
+// mean / population variance / exceedance frequency of U_s[i].V_s[j] + offset over S samples
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(128)
+sample_stats_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj, int64_t ncand,
+                    int S, int64_t n, int64_t m, int d, const T* __restrict__ Us,
+                    const T* __restrict__ Vs, T offset, T cutoff, T* __restrict__ mean_out,
+                    T* __restrict__ var_out, T* __restrict__ prob_out, int select,
+                    int64_t index_base, Best* __restrict__ part) {
+  Best best{0.0, -1};
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncand;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = ci[c], j = cj[c];
+    double sum = 0, wmean = 0, m2 = 0;
+    int cnt_ge = 0;
+    for (int s = 0; s < S; ++s) {
+      const T* u = Us + ((int64_t)s * n + i) * d;
+      const T* v = Vs + ((int64_t)s * m + j) * d;
+      T dot = 0;
+      for (int k = 0; k < d; ++k) dot = fma(u[k], v[k], dot);
+      const T pred = dot + offset;
+      cnt_ge += (pred >= cutoff);
+      sum += (double)pred;
+      const double delta = (double)pred - wmean;
+      wmean += delta / (double)(s + 1);
+      m2 += delta * ((double)pred - wmean);
+    }
+    const double mean = sum / (double)S, var = m2 / (double)S, prob = (double)cnt_ge / (double)S;
+    if (mean_out) mean_out[c] = (T)mean;
+    if (var_out) var_out[c] = (T)var;
+    if (prob_out) prob_out[c] = (T)prob;
+    const double sel = select == 0 ? mean : (select == 1 ? var : prob);
+    if (better<MAX>(sel, c + index_base, best.v, best.i)) { best.v = sel; best.i = c + index_base; }
+  }
+  best = block_best<MAX>(best);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
+int acquire_partials(Best** out);
+int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
+                      cudaStream_t s);
+
+template <typename T>
+static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, const T* alpha,
+                        const T* mu, double beta, double mean_offset, const T* z, T* out,
+                        cudaStream_t s) {
+  const int rows = side == 0 ? h->n_users : h->n_items;
+  const size_t smem = sizeof(double) * (2 * d * (d + 1) + 2 * d + GIBBS_TILE) +
+                      sizeof(T) * GIBBS_TILE * (d + 1);
+  AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  int* fail = reinterpret_cast<int*>(h->sums_d + 6);
+  AMF_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
+  const int grid = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  gibbs_rows_kernel<T><<<grid, GIBBS_THREADS, smem, s>>>(h->ptr[side], h->idx[side],
+                                                         (const T*)h->val[side], rows, d, other,
+                                                         alpha, mu, beta, mean_offset, z, out, fail);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+}  // namespace amf
+
+using namespace amf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int amf_gibbs_half_sweep(const amf_ratings_t* h, int side, int dtype, int d, const void* other_d,
+                         const void* alpha_d, const void* mu_d, double beta, double mean_offset,
+                         const void* z_d, void* out_d, void* stream) {
+  AMF_REQUIRE(h && other_d && alpha_d && mu_d && z_d && out_d, "amf_gibbs_half_sweep: NULL argument");
+  AMF_REQUIRE(side == 0 || side == 1, "amf_gibbs_half_sweep: side must be 0 or 1");
+  AMF_REQUIRE(dtype == h->dtype, "amf_gibbs_half_sweep: dtype does not match the rating list");
+  AMF_REQUIRE(d >= 1 && d <= GIBBS_MAXD, "amf_gibbs_half_sweep: latent_d=%d unsupported (max %d)", d,
+              GIBBS_MAXD);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == AMF_F32)
+    return gibbs_launch<float>(h, side, d, (const float*)other_d, (const float*)alpha_d,
+                               (const float*)mu_d, beta, mean_offset, (const float*)z_d,
+                               (float*)out_d, s);
+  return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
+                              (const double*)mu_d, beta, mean_offset, (const double*)z_d,
+                              (double*)out_d, s);
+}
+
+int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream) {
+  AMF_REQUIRE(h && failed, "amf_gibbs_status: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  AMF_CUDA(cudaMemcpyAsync(failed, reinterpret_cast<int*>(h->sums_d + 6), sizeof(int),
+                           cudaMemcpyDeviceToHost, s));
+  AMF_CUDA(cudaStreamSynchronize(s));
+  return AMF_OK;
+}
+
+int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
+                           int S, int32_t n, int32_t m, int d, const void* Us_d, const void* Vs_d,
+                           double mean_offset, double cutoff, void* mean_d, void* var_d,
+                           void* prob_d, int select, int maximize, int64_t index_base,
+                           amf_best_t* best_d, void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_bayes_sample_stats: bad dtype");
+  AMF_REQUIRE(S >= 1 && d >= 1 && ncand >= 0, "amf_bayes_sample_stats: bad sizes");
+  AMF_REQUIRE(select >= 0 && select <= 2, "amf_bayes_sample_stats: bad select");
+  cudaStream_t s = (cudaStream_t)stream;
+  Best* part = nullptr;
+  int rc = acquire_partials(&part);
+  if (rc != AMF_OK) return rc;
+  const int64_t blocks = (ncand + 127) / 128;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? (blocks > 0 ? blocks : 1)
+                                                          : (int64_t)num_sms() * 16);
+#define STATS(T, MAXV)                                                                          \
+  sample_stats_kernel<T, MAXV><<<grid, 128, 0, s>>>(ci_d, cj_d, ncand, S, n, m, d,              \
+      (const T*)Us_d, (const T*)Vs_d, (T)mean_offset, (T)cutoff, (T*)mean_d, (T*)var_d,         \
+      (T*)prob_d, select, index_base, part)
+  if (dtype == AMF_F32) { if (maximize) STATS(float, true); else STATS(float, false); }
+  else { if (maximize) STATS(double, true); else STATS(double, false); }
+#undef STATS
+  AMF_LAUNCH_CHECK();
+  if (best_d) return launch_best_final(part, grid, maximize != 0, best_d, s);
+  return AMF_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,462 @@
+// Fused PMF objective + gradient (pmf_cy.pyx:170-193 log_likelihood, :204-223 gradient).
+//
+// The reference walks the (nnz,3) rating list once per call in Python.  Here one "side pass"
+// streams one sorted copy of the list (8 B/entry: other index + rating), keeps the row being
+// reduced (U_i and its gradient accumulator) in registers, gathers the other side's factor row
+// (one 128 B line at d=32 fp32) and reduces
+//     e = r - U_i.V_j - mean,   sum e^2,   dU_i += (e / sigma^2) V_j.
+// The same kernel run on the item-major copy with the roles of U and V swapped gives dV, so no
+// transposed scatter is needed and results do not depend on atomics ordering except for rows
+// that straddle a 32-entry sub-chunk boundary (their partial sums are combined with RED.ADD).
+//
+// Thread mapping: LPR lanes cooperate on one rating, each owning VPL 16-byte vectors of the
+// factor row (d=32 fp32 -> LPR=8, VPL=1: one float4 per lane, a warp gathers 4 full lines per
+// load instruction).  Work is split by entries, not rows: a lane group owns sub-chunks of
+// AMF_SUB=32 consecutive entries and finds its starting row in the precomputed sub_row table.
+#include "common.cuh"
+
+namespace amf {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+prior_kernel(const T* __restrict__ X, int64_t count, T neg_inv_sigma, T* __restrict__ dX,
+             double* __restrict__ norm2) {
+  using V = typename Vec<T>::type;
+  constexpr int N = Vec<T>::N;
+  const int64_t nvec = count / N;
+  double acc = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nvec;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    V x = reinterpret_cast<const V*>(X)[t];
+    T s = vdot(x, x);
+    acc += (double)s;
+    if (dX) {
+      V g = vzero(x);
+      vfma(g, neg_inv_sigma, x);
+      reinterpret_cast<V*>(dX)[t] = g;
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0 && norm2) atomicAdd(norm2, acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpy_kernel(const T* __restrict__ X, const T* __restrict__ G, T lr, int64_t count,
+            T* __restrict__ Xn) {
+  using V = typename Vec<T>::type;
+  constexpr int N = Vec<T>::N;
+  const int64_t nvec = count / N;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nvec;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    V x = reinterpret_cast<const V*>(X)[t];
+    V g = reinterpret_cast<const V*>(G)[t];
+    vfma(x, lr, g);
+    reinterpret_cast<V*>(Xn)[t] = x;
+  }
+}
+
+// momentum SGD update of fit_minibatches (pmf_cy.pyx:338-344):
+//   inc = momentum * inc + scale * G ;  X += inc
+template <typename T>
+__global__ void __launch_bounds__(256)
+momentum_kernel(T* __restrict__ inc, const T* __restrict__ G, T momentum, T scale, int64_t count,
+                T* __restrict__ X) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    T v = fma(scale, G[t], momentum * inc[t]);
+    inc[t] = v;
+    X[t] += v;
+  }
+}
+
+template <typename T, int LPR, int VPL, bool GRAD>
+__global__ void __launch_bounds__(256)
+side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                 const T* __restrict__ val, const int32_t* __restrict__ sub_row,
+                 const T* __restrict__ Self, const T* __restrict__ Other, int ld, int nvec,
+                 T inv_sigma, T mean_offset, T* __restrict__ dSelf,
+                 double* __restrict__ sq_err, int64_t nnz, int64_t n_sub) {
+  using V = typename Vec<T>::type;
+  constexpr int N = Vec<T>::N;
+  constexpr int G = 32 / LPR;  // ratings in flight per warp
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  bool have[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) have[v] = (l + v * LPR) < nvec;
+
+  double local_sq = 0;
+  for (int64_t base = warp * G; base < n_sub; base += nwarps * G) {
+    T sub_sq = 0;
+    const int64_t sub = base + g;
+    const bool live = sub < n_sub;
+    const int64_t p0 = sub * AMF_SUB;
+    const int64_t p1 = live ? min(p0 + (int64_t)AMF_SUB, nnz) : p0;
+    int32_t row = live ? sub_row[sub] : 0;
+    int64_t row_end = live ? ptr[row + 1] : 0;
+    V self[VPL], acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      acc[v] = vzero(V());
+      self[v] = (live && have[v])
+                    ? reinterpret_cast<const V*>(Self + (int64_t)row * ld)[l + v * LPR]
+                    : vzero(V());
+    }
+#pragma unroll 4
+    for (int t = 0; t < AMF_SUB; ++t) {
+      const int64_t p = p0 + t;
+      const bool valid = p < p1;
+      if (valid && p >= row_end) {
+        // leave the finished row: publish its partial gradient, move to the row holding p
+        if (GRAD) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            if (have[v]) vred_add(dSelf + (int64_t)row * ld + (l + v * LPR) * N, acc[v]);
+        }
+        do { ++row; row_end = ptr[row + 1]; } while (p >= row_end);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          acc[v] = vzero(V());
+          if (have[v]) self[v] = reinterpret_cast<const V*>(Self + (int64_t)row * ld)[l + v * LPR];
+        }
+      }
+      int32_t j = 0;
+      T r = 0;
+      if (valid) { j = ld_stream(idx + p); r = ld_stream(val + p); }
+      V o[VPL];
+      T dot = 0;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        o[v] = (valid && have[v]) ? reinterpret_cast<const V*>(Other + (int64_t)j * ld)[l + v * LPR]
+                                  : vzero(V());
+        dot += vdot(self[v], o[v]);
+      }
+#pragma unroll
+      for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      const T e = valid ? (r - dot - mean_offset) : T(0);
+      if (l == 0) sub_sq = fma(e, e, sub_sq);
+      if (GRAD) {
+        const T w = e * inv_sigma;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) vfma(acc[v], w, o[v]);
+      }
+    }
+    if (GRAD && live && p1 > p0) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        if (have[v]) vred_add(dSelf + (int64_t)row * ld + (l + v * LPR) * N, acc[v]);
+    }
+    local_sq += (double)sub_sq;
+  }
+  if (sq_err) {
+    double s = block_sum(local_sq);
+    if (threadIdx.x == 0) atomicAdd(sq_err, s);
+  }
+}
+
+// COO mini-batch variant with atomics into both sides (gradient(ratings=batch))
+template <typename T, int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+coo_grad_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj,
+                const T* __restrict__ val, int64_t nnz, const T* __restrict__ U,
+                const T* __restrict__ Vm, int ld, int nvec, T inv_sigma, T mean_offset,
+                T* __restrict__ dU, T* __restrict__ dV, double* __restrict__ sq_err) {
+  using V = typename Vec<T>::type;
+  constexpr int N = Vec<T>::N;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  T local_sq = 0;
+  for (int64_t base = warp * G; base < nnz; base += nwarps * G) {
+    const int64_t p = base + g;
+    const bool valid = p < nnz;
+    const int32_t i = valid ? ci[p] : 0, j = valid ? cj[p] : 0;
+    const T r = valid ? val[p] : T(0);
+    V a[VPL], b[VPL];
+    T dot = 0;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const bool h = valid && (l + v * LPR) < nvec;
+      a[v] = h ? reinterpret_cast<const V*>(U + (int64_t)i * ld)[l + v * LPR] : vzero(V());
+      b[v] = h ? reinterpret_cast<const V*>(Vm + (int64_t)j * ld)[l + v * LPR] : vzero(V());
+      dot += vdot(a[v], b[v]);
+    }
+#pragma unroll
+    for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    const T e = valid ? (r - dot - mean_offset) : T(0);
+    if (l == 0) local_sq = fma(e, e, local_sq);
+    const T w = e * inv_sigma;
+    if (valid && dU) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        if ((l + v * LPR) < nvec) {
+          V gu = vzero(V()), gv = vzero(V());
+          vfma(gu, w, b[v]);
+          vfma(gv, w, a[v]);
+          vred_add(dU + (int64_t)i * ld + (l + v * LPR) * N, gu);
+          vred_add(dV + (int64_t)j * ld + (l + v * LPR) * N, gv);
+        }
+    }
+  }
+  if (sq_err) {
+    double s = block_sum((double)local_sq);
+    if (threadIdx.x == 0) atomicAdd(sq_err, s);
+  }
+}
+
+static inline int pow2_ceil(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// grid: enough warps to cover the sub-chunks, capped at a multiple of the SM count
+static inline int grid_for(int64_t units_per_block_total, int blocks_per_sm_cap) {
+  int64_t want = units_per_block_total;
+  int64_t cap = (int64_t)num_sms() * blocks_per_sm_cap;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+template <typename T, bool GRAD>
+static int launch_side(const amf_ratings* h, int side, const T* Self, const T* Other, int ld,
+                       T inv_sigma, T mean_offset, T* dSelf, double* sq_err, cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  const int nvec = ld / N;
+  int lpr = pow2_ceil(nvec);
+  int vpl = 1;
+  if (lpr > 32) { vpl = lpr / 32; lpr = 32; }
+  if (vpl > 4) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
+  const int G = 32 / lpr;
+  const int64_t warps_needed = (h->n_sub + G - 1) / G;
+  const int grid = grid_for((warps_needed + 7) / 8, 8);
+#define SIDE(LPR_, VPL_)                                                                      \
+  side_pass_kernel<T, LPR_, VPL_, GRAD><<<grid, 256, 0, s>>>(                                 \
+      h->ptr[side], h->idx[side], (const T*)h->val[side], h->sub_row[side], Self, Other, ld,  \
+      nvec, inv_sigma, mean_offset, dSelf, sq_err, h->nnz, h->n_sub)
+  if (vpl == 1) {
+    switch (lpr) {
+      case 1: SIDE(1, 1); break;
+      case 2: SIDE(2, 1); break;
+      case 4: SIDE(4, 1); break;
+      case 8: SIDE(8, 1); break;
+      case 16: SIDE(16, 1); break;
+      default: SIDE(32, 1); break;
+    }
+  } else if (vpl == 2) {
+    SIDE(32, 2);
+  } else {
+    SIDE(32, 4);
+  }
+#undef SIDE
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+template <typename T>
+static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V,
+                     const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
+  AMF_REQUIRE((dU == nullptr) == (dV == nullptr), "dU and dV must both be given or both NULL");
+  AMF_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+  const int64_t cu = (int64_t)h->n_users * ld, cv = (int64_t)h->n_items * ld;
+  const int gu = grid_for((cu / N + 255) / 256, 8), gv = grid_for((cv / N + 255) / 256, 8);
+  prior_kernel<T><<<gu, 256, 0, s>>>(U, cu, (T)(-1.0 / p->sigma_u_sq), dU, sums + 1);
+  AMF_LAUNCH_CHECK();
+  prior_kernel<T><<<gv, 256, 0, s>>>(V, cv, (T)(-1.0 / p->sigma_v_sq), dV, sums + 2);
+  AMF_LAUNCH_CHECK();
+  if (h->nnz == 0) return AMF_OK;
+  const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
+  int rc;
+  if (dU) {
+    rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
+    if (rc != AMF_OK) return rc;
+    rc = launch_side<T, true>(h, 1, V, U, ld, inv_sigma, mo, dV, nullptr, s);
+  } else {
+    rc = launch_side<T, false>(h, 0, U, V, ld, inv_sigma, mo, nullptr, sums, s);
+  }
+  return rc;
+}
+
+template <typename T>
+static int grad_coo(int64_t nnz, const int32_t* i_d, const int32_t* j_d, const T* r_d, int d,
+                    int ld, const T* U, const T* V, const amf_pmf_params_t* p, T* dU, T* dV,
+                    double* sums, cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
+  if (sums) AMF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double), s));
+  if (nnz == 0) return AMF_OK;
+  const int nvec = ld / N;
+  int lpr = pow2_ceil(nvec), vpl = 1;
+  if (lpr > 32) { vpl = lpr / 32; lpr = 32; }
+  if (vpl > 4) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
+  const int G = 32 / lpr;
+  const int grid = grid_for((((nnz + G - 1) / G) + 7) / 8, 8);
+  const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
+#define COO(LPR_, VPL_)                                                                        \
+  coo_grad_kernel<T, LPR_, VPL_><<<grid, 256, 0, s>>>(i_d, j_d, r_d, nnz, U, V, ld, nvec,      \
+                                                      inv_sigma, mo, dU, dV, sums)
+  if (vpl == 1) {
+    switch (lpr) {
+      case 1: COO(1, 1); break;
+      case 2: COO(2, 1); break;
+      case 4: COO(4, 1); break;
+      case 8: COO(8, 1); break;
+      case 16: COO(16, 1); break;
+      default: COO(32, 1); break;
+    }
+  } else if (vpl == 2) {
+    COO(32, 2);
+  } else {
+    COO(32, 4);
+  }
+#undef COO
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+// (rows, d) tightly packed host matrix <-> zero-padded (rows, ld) device matrix
+static int ensure_stage(amf_ratings* h, int slot, size_t bytes) {
+  if (h->stage_bytes[slot] >= bytes) return AMF_OK;
+  cudaFree(h->stage[slot]);
+  h->stage[slot] = nullptr;
+  h->stage_bytes[slot] = 0;
+  AMF_CUDA(cudaMalloc(&h->stage[slot], bytes));
+  h->stage_bytes[slot] = bytes;
+  return AMF_OK;
+}
+
+}  // namespace amf
+
+using namespace amf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int amf_pmf_loss_grad(const amf_ratings_t* h, int dtype, int d, int ld, const void* U_d,
+                      const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
+                      double* sums_d, void* stream) {
+  AMF_REQUIRE(h && U_d && V_d && p && sums_d, "amf_pmf_loss_grad: NULL argument");
+  AMF_REQUIRE(dtype == h->dtype, "amf_pmf_loss_grad: dtype %d does not match the rating list's %d",
+              dtype, h->dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == AMF_F32)
+    return loss_grad<float>(h, d, ld, (const float*)U_d, (const float*)V_d, p, (float*)dU_d,
+                            (float*)dV_d, sums_d, s);
+  return loss_grad<double>(h, d, ld, (const double*)U_d, (const double*)V_d, p, (double*)dU_d,
+                           (double*)dV_d, sums_d, s);
+}
+
+int amf_axpy(int dtype, int64_t count, const void* X_d, const void* G_d, double lr, void* Xnew_d,
+             void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_axpy: bad dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (count == 0) return AMF_OK;
+  if (dtype == AMF_F32) {
+    AMF_REQUIRE(count % 4 == 0, "amf_axpy: count must be a multiple of 4");
+    axpy_kernel<float><<<grid_for((count / 4 + 255) / 256, 8), 256, 0, s>>>(
+        (const float*)X_d, (const float*)G_d, (float)lr, count, (float*)Xnew_d);
+  } else {
+    AMF_REQUIRE(count % 2 == 0, "amf_axpy: count must be a multiple of 2");
+    axpy_kernel<double><<<grid_for((count / 2 + 255) / 256, 8), 256, 0, s>>>(
+        (const double*)X_d, (const double*)G_d, lr, count, (double*)Xnew_d);
+  }
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+int amf_momentum_step(int dtype, int64_t count, void* inc_d, const void* G_d, double momentum,
+                      double scale, void* X_d, void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_momentum_step: bad dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (count == 0) return AMF_OK;
+  const int grid = grid_for((count + 255) / 256, 8);
+  if (dtype == AMF_F32)
+    momentum_kernel<float><<<grid, 256, 0, s>>>((float*)inc_d, (const float*)G_d, (float)momentum,
+                                                (float)scale, count, (float*)X_d);
+  else
+    momentum_kernel<double><<<grid, 256, 0, s>>>((double*)inc_d, (const double*)G_d, momentum,
+                                                 scale, count, (double*)X_d);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+int amf_pmf_prior(int dtype, int64_t count, const void* X_d, double sigma_x_sq, void* dX_d,
+                  double* norm2_d, void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_pmf_prior: bad dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (count == 0) return AMF_OK;
+  if (dtype == AMF_F32) {
+    AMF_REQUIRE(count % 4 == 0, "amf_pmf_prior: count must be a multiple of 4");
+    prior_kernel<float><<<grid_for((count / 4 + 255) / 256, 8), 256, 0, s>>>(
+        (const float*)X_d, count, (float)(-1.0 / sigma_x_sq), (float*)dX_d, norm2_d);
+  } else {
+    AMF_REQUIRE(count % 2 == 0, "amf_pmf_prior: count must be a multiple of 2");
+    prior_kernel<double><<<grid_for((count / 2 + 255) / 256, 8), 256, 0, s>>>(
+        (const double*)X_d, count, -1.0 / sigma_x_sq, (double*)dX_d, norm2_d);
+  }
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+int amf_pmf_grad_coo(int dtype, int64_t nnz, const int32_t* i_d, const int32_t* j_d,
+                     const void* r_d, int d, int ld, const void* U_d, const void* V_d,
+                     const amf_pmf_params_t* p, void* dU_d, void* dV_d, double* sums_d,
+                     void* stream) {
+  AMF_REQUIRE(U_d && V_d && p, "amf_pmf_grad_coo: NULL argument");
+  AMF_REQUIRE((dU_d == nullptr) == (dV_d == nullptr), "dU and dV must both be given or both NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == AMF_F32)
+    return grad_coo<float>(nnz, i_d, j_d, (const float*)r_d, d, ld, (const float*)U_d,
+                           (const float*)V_d, p, (float*)dU_d, (float*)dV_d, sums_d, s);
+  AMF_REQUIRE(dtype == AMF_F64, "amf_pmf_grad_coo: bad dtype");
+  return grad_coo<double>(nnz, i_d, j_d, (const double*)r_d, d, ld, (const double*)U_d,
+                          (const double*)V_d, p, (double*)dU_d, (double*)dV_d, sums_d, s);
+}
+
+int amf_pmf_loss_grad_host(const amf_ratings_t* hc, int dtype, int d, const void* U_h,
+                           const void* V_h, const amf_pmf_params_t* p, void* dU_h, void* dV_h,
+                           double* sums_h) {
+  AMF_REQUIRE(hc && U_h && V_h && p && sums_h, "amf_pmf_loss_grad_host: NULL argument");
+  AMF_REQUIRE(dtype == hc->dtype, "amf_pmf_loss_grad_host: dtype mismatch");
+  AMF_REQUIRE((dU_h == nullptr) == (dV_h == nullptr), "dU and dV must both be given or both NULL");
+  amf_ratings* h = const_cast<amf_ratings*>(hc);
+  const size_t es = dtype == AMF_F32 ? 4 : 8;
+  const int vecn = dtype == AMF_F32 ? 4 : 2;
+  const int ld = (d + vecn - 1) / vecn * vecn;
+  const size_t bu = (size_t)h->n_users * ld * es, bv = (size_t)h->n_items * ld * es;
+  int rc;
+  if ((rc = ensure_stage(h, 0, bu)) || (rc = ensure_stage(h, 1, bv))) return rc;
+  if (dU_h && ((rc = ensure_stage(h, 2, bu)) || (rc = ensure_stage(h, 3, bv)))) return rc;
+  cudaStream_t s = nullptr;
+  if (ld != d) {
+    AMF_CUDA(cudaMemsetAsync(h->stage[0], 0, bu, s));
+    AMF_CUDA(cudaMemsetAsync(h->stage[1], 0, bv, s));
+  }
+  AMF_CUDA(cudaMemcpy2DAsync(h->stage[0], ld * es, U_h, d * es, d * es, h->n_users,
+                             cudaMemcpyHostToDevice, s));
+  AMF_CUDA(cudaMemcpy2DAsync(h->stage[1], ld * es, V_h, d * es, d * es, h->n_items,
+                             cudaMemcpyHostToDevice, s));
+  rc = amf_pmf_loss_grad(h, dtype, d, ld, h->stage[0], h->stage[1], p,
+                         dU_h ? h->stage[2] : nullptr, dU_h ? h->stage[3] : nullptr, h->sums_d, s);
+  if (rc != AMF_OK) return rc;
+  if (dU_h) {
+    AMF_CUDA(cudaMemcpy2DAsync(dU_h, d * es, h->stage[2], ld * es, d * es, h->n_users,
+                               cudaMemcpyDeviceToHost, s));
+    AMF_CUDA(cudaMemcpy2DAsync(dV_h, d * es, h->stage[3], ld * es, d * es, h->n_items,
+                               cudaMemcpyDeviceToHost, s));
+  }
+  AMF_CUDA(cudaMemcpyAsync(sums_h, h->sums_d, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AMF_CUDA(cudaStreamSynchronize(s));
+  return AMF_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,311 @@
+// Candidate scoring with a fused arg-best (active_pmf.py:739-770 _get_key_vals and the
+// chooser at :737; criteria pred :416-421, approx_pred_mean_var :392-400, pred_variance
+// :502-524 = exp_dotprod_sq (normal_exps_cy.pyx:111-135) - E^2, _prob_ge_cutoff :432-439).
+//
+// The reference maps a Python method over the pool (optionally through multiprocessing.Pool,
+// pickling the model per chunk).  Here the pool is a pair of int32 device arrays; one launch
+// scores every candidate, optionally stores the scores, and reduces (value, index) to the
+// winner with the lowest-index tie-break, so selection costs no second pass.
+#include "common.cuh"
+
+namespace amf {
+
+template <bool MAX>
+__global__ void best_final_kernel(const Best* __restrict__ part, int nparts,
+                                  amf_best_t* __restrict__ out) {
+  Best b{0.0, -1};
+  for (int t = threadIdx.x; t < nparts; t += blockDim.x) {
+    Best o = part[t];
+    if (better<MAX>(o.v, o.i, b.v, b.i)) b = o;
+  }
+  b = block_best<MAX>(b);
+  if (threadIdx.x == 0) { out->value = b.v; out->index = b.i; }
+}
+
+int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
+                      cudaStream_t s) {
+  if (maximize) best_final_kernel<true><<<1, 256, 0, s>>>(part_d, nparts, out_d);
+  else best_final_kernel<false><<<1, 256, 0, s>>>(part_d, nparts, out_d);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+// MAP prediction U_i . V_j : LPR lanes per candidate, one 16-byte vector each (x VPL)
+template <typename T, int LPR, int VPL, bool MAX>
+__global__ void __launch_bounds__(256)
+score_pred_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj, int64_t ncand,
+                  const T* __restrict__ U, const T* __restrict__ Vm, int ld, int nvec,
+                  T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
+  using V = typename Vec<T>::type;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, l = lane % LPR;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Best best{0.0, -1};
+  for (int64_t base = warp * G; base < ncand; base += nwarps * G) {
+    const int64_t c = base + g;
+    const bool valid = c < ncand;
+    const int32_t i = valid ? ld_stream(ci + c) : 0, j = valid ? ld_stream(cj + c) : 0;
+    T dot = 0;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      if (valid && (l + v * LPR) < nvec) {
+        V a = reinterpret_cast<const V*>(U + (int64_t)i * ld)[l + v * LPR];
+        V b = reinterpret_cast<const V*>(Vm + (int64_t)j * ld)[l + v * LPR];
+        dot += vdot(a, b);
+      }
+    }
+#pragma unroll
+    for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (valid && l == 0) {
+      if (scores) __stcs(scores + c, dot);
+      if (better<MAX>((double)dot, c + index_base, best.v, best.i)) {
+        best.v = (double)dot; best.i = c + index_base;
+      }
+    }
+  }
+  best = block_best<MAX>(best);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
+struct NormalView {
+  const void *mean_u, *mean_v, *cov_uu, *cov_vv, *cov_uv;
+  long long mean_u_stride, mean_v_stride, uu_stride, uu_ld, vv_stride, vv_ld, uv_stride_i,
+      uv_stride_j, uv_ld;
+};
+
+// Moments of U_i . V_j under the Gaussian approximation, one thread per candidate.
+//   E   = mu.mv + tr C
+//   Var = <A,B> + <C,C'> + mv'A mv + mu'B mu + 2 mu'C'mv        (== exp_dotprod_sq - E^2)
+template <typename T, int CRIT, bool MAX>
+__global__ void __launch_bounds__(128)
+score_normal_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj, int64_t ncand,
+                    int d, NormalView nv, T cutoff, T* __restrict__ scores, int64_t index_base,
+                    Best* __restrict__ part) {
+  Best best{0.0, -1};
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncand;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = ci[c], j = cj[c];
+    const T* mu = (const T*)nv.mean_u + i * nv.mean_u_stride;
+    const T* mv = (const T*)nv.mean_v + j * nv.mean_v_stride;
+    const T* A = (const T*)nv.cov_uu + i * nv.uu_stride;
+    const T* B = (const T*)nv.cov_vv + j * nv.vv_stride;
+    const T* C = nv.cov_uv ? (const T*)nv.cov_uv + i * nv.uv_stride_i + j * nv.uv_stride_j : nullptr;
+    T e = 0, var = 0;
+    for (int k = 0; k < d; ++k) {
+      const T muk = mu[k], mvk = mv[k];
+      e = fma(muk, mvk, e);
+      if (C) e += C[k * nv.uv_ld + k];
+      if (CRIT != AMF_CRIT_APPROX_MEAN) {
+        T ab = 0, amv = 0, bmu = 0, cc = 0, cmv = 0;
+        for (int l = 0; l < d; ++l) {
+          const T a = A[k * nv.uu_ld + l], b = B[k * nv.vv_ld + l];
+          ab = fma(a, b, ab);
+          amv = fma(a, mv[l], amv);
+          bmu = fma(b, mu[l], bmu);
+          if (C) {
+            const T clk = C[l * nv.uv_ld + k];
+            cc = fma(C[k * nv.uv_ld + l], clk, cc);
+            cmv = fma(clk, mv[l], cmv);
+          }
+        }
+        var += ab + cc + mvk * amv + muk * bmu + 2 * muk * cmv;
+      }
+    }
+    T out;
+    if (CRIT == AMF_CRIT_APPROX_MEAN) out = e;
+    else if (CRIT == AMF_CRIT_PRED_VARIANCE) out = var;
+    else {
+      // scipy.stats.norm.sf(cutoff, loc=e, scale=var): the reference passes the variance as the
+      // scale (active_pmf.py:438-439); scale <= 0 gives nan there too
+      out = var > 0 ? T(0.5) * erfc((cutoff - e) / (var * T(1.4142135623730951))) : T(NAN);
+    }
+    if (scores) scores[c] = out;
+    if (better<MAX>((double)out, c + index_base, best.v, best.i)) {
+      best.v = (double)out; best.i = c + index_base;
+    }
+  }
+  best = block_best<MAX>(best);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
+static inline int pow2c(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <typename T, bool MAX>
+static int score_pred(int64_t ncand, const int32_t* ci, const int32_t* cj, int d, int ld,
+                      const T* U, const T* V, T* scores, int64_t index_base, Best* part, int grid,
+                      cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
+  const int nvec = ld / N;
+  int lpr = pow2c(nvec), vpl = 1;
+  if (lpr > 32) { vpl = lpr / 32; lpr = 32; }
+  if (vpl > 4) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
+#define PRED(LPR_, VPL_)                                                                     \
+  score_pred_kernel<T, LPR_, VPL_, MAX><<<grid, 256, 0, s>>>(ci, cj, ncand, U, V, ld, nvec,  \
+                                                             scores, index_base, part)
+  if (vpl == 1) {
+    switch (lpr) {
+      case 1: PRED(1, 1); break;
+      case 2: PRED(2, 1); break;
+      case 4: PRED(4, 1); break;
+      case 8: PRED(8, 1); break;
+      case 16: PRED(16, 1); break;
+      default: PRED(32, 1); break;
+    }
+  } else if (vpl == 2) {
+    PRED(32, 2);
+  } else {
+    PRED(32, 4);
+  }
+#undef PRED
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+template <typename T, bool MAX>
+static int score_normal(int crit, int64_t ncand, const int32_t* ci, const int32_t* cj, int d,
+                        const NormalView& nv, double cutoff, T* scores, int64_t index_base,
+                        Best* part, int grid, cudaStream_t s) {
+  switch (crit) {
+    case AMF_CRIT_APPROX_MEAN:
+      score_normal_kernel<T, AMF_CRIT_APPROX_MEAN, MAX><<<grid, 128, 0, s>>>(
+          ci, cj, ncand, d, nv, (T)cutoff, scores, index_base, part);
+      break;
+    case AMF_CRIT_PRED_VARIANCE:
+      score_normal_kernel<T, AMF_CRIT_PRED_VARIANCE, MAX><<<grid, 128, 0, s>>>(
+          ci, cj, ncand, d, nv, (T)cutoff, scores, index_base, part);
+      break;
+    default:
+      score_normal_kernel<T, AMF_CRIT_PROB_GE, MAX><<<grid, 128, 0, s>>>(
+          ci, cj, ncand, d, nv, (T)cutoff, scores, index_base, part);
+      break;
+  }
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
+// per-device scratch for the per-block partial winners (one slot per host thread is not needed:
+// the buffer is only touched by kernels ordered on the caller's stream; distinct streams get
+// distinct slices through a small ring)
+static Best* partials(int device, int slot) {
+  static Best* bufs[64][8] = {{nullptr}};
+  if (device >= 64) return nullptr;
+  if (!bufs[device][slot]) {
+    if (cudaMalloc(&bufs[device][slot], sizeof(Best) * 8192) != cudaSuccess) return nullptr;
+  }
+  return bufs[device][slot];
+}
+
+int acquire_partials(Best** out) {
+  static thread_local int rr = 0;
+  int dev = 0;
+  AMF_CUDA(cudaGetDevice(&dev));
+  Best* p = partials(dev, (rr++) & 7);
+  AMF_REQUIRE(p != nullptr, "could not allocate arg-best scratch");
+  *out = p;
+  return AMF_OK;
+}
+
+}  // namespace amf
+
+using namespace amf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t* ci_d,
+                         const int32_t* cj_d, int d, int ld, const void* U_d, const void* V_d,
+                         const amf_normal_view_t* nvp, double cutoff, void* scores_d,
+                         int maximize, int64_t index_base, amf_best_t* best_d, void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_score_candidates: bad dtype %d", dtype);
+  AMF_REQUIRE(criterion >= AMF_CRIT_PRED && criterion <= AMF_CRIT_PROB_GE,
+              "amf_score_candidates: unknown criterion %d", criterion);
+  AMF_REQUIRE(best_d != nullptr, "amf_score_candidates: best_d is NULL");
+  AMF_REQUIRE(ncand >= 0 && d > 0, "amf_score_candidates: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  Best* part = nullptr;
+  int rc = acquire_partials(&part);
+  if (rc != AMF_OK) return rc;
+  int grid;
+  if (criterion == AMF_CRIT_PRED) {
+    AMF_REQUIRE(U_d && V_d, "amf_score_candidates: U/V are NULL");
+    const int64_t blocks = (ncand + 63) / 64;  // >= 2 candidates per lane group before capping
+    grid = (int)(blocks < (int64_t)num_sms() * 8 ? (blocks > 0 ? blocks : 1) : (int64_t)num_sms() * 8);
+  } else {
+    AMF_REQUIRE(nvp && nvp->mean_u && nvp->mean_v && nvp->cov_uu && nvp->cov_vv,
+                "amf_score_candidates: normal view is incomplete");
+    const int64_t blocks = (ncand + 127) / 128;
+    grid = (int)(blocks < (int64_t)num_sms() * 16 ? (blocks > 0 ? blocks : 1) : (int64_t)num_sms() * 16);
+  }
+  NormalView nv{};
+  if (nvp) {
+    nv.mean_u = nvp->mean_u; nv.mean_v = nvp->mean_v; nv.cov_uu = nvp->cov_uu;
+    nv.cov_vv = nvp->cov_vv; nv.cov_uv = nvp->cov_uv;
+    nv.mean_u_stride = nvp->mean_u_stride; nv.mean_v_stride = nvp->mean_v_stride;
+    nv.uu_stride = nvp->uu_stride; nv.uu_ld = nvp->uu_ld;
+    nv.vv_stride = nvp->vv_stride; nv.vv_ld = nvp->vv_ld;
+    nv.uv_stride_i = nvp->uv_stride_i; nv.uv_stride_j = nvp->uv_stride_j; nv.uv_ld = nvp->uv_ld;
+  }
+#define DISPATCH(T)                                                                              \
+  if (criterion == AMF_CRIT_PRED) {                                                              \
+    rc = maximize ? score_pred<T, true>(ncand, ci_d, cj_d, d, ld, (const T*)U_d, (const T*)V_d,  \
+                                        (T*)scores_d, index_base, part, grid, s)                 \
+                  : score_pred<T, false>(ncand, ci_d, cj_d, d, ld, (const T*)U_d, (const T*)V_d, \
+                                         (T*)scores_d, index_base, part, grid, s);               \
+  } else {                                                                                       \
+    rc = maximize ? score_normal<T, true>(criterion, ncand, ci_d, cj_d, d, nv, cutoff,           \
+                                          (T*)scores_d, index_base, part, grid, s)               \
+                  : score_normal<T, false>(criterion, ncand, ci_d, cj_d, d, nv, cutoff,          \
+                                           (T*)scores_d, index_base, part, grid, s);             \
+  }
+  if (dtype == AMF_F32) { DISPATCH(float) } else { DISPATCH(double) }
+#undef DISPATCH
+  if (rc != AMF_OK) return rc;
+  return launch_best_final(part, grid, maximize != 0, best_d, s);
+}
+
+int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,
+                        int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
+                        void* scores_h, int maximize, amf_best_t* best_h) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_score_pred_host: bad dtype");
+  AMF_REQUIRE(best_h && U_h && V_h, "amf_score_pred_host: NULL argument");
+  const size_t es = dtype == AMF_F32 ? 4 : 8;
+  const int vecn = dtype == AMF_F32 ? 4 : 2;
+  const int ld = (d + vecn - 1) / vecn * vecn;
+  void *U_d = nullptr, *V_d = nullptr, *sc_d = nullptr;
+  int32_t *ci_d = nullptr, *cj_d = nullptr;
+  amf_best_t* best_d = nullptr;
+  const size_t nc = ncand > 0 ? (size_t)ncand : 1;
+  AMF_CUDA(cudaMalloc(&U_d, (size_t)n * ld * es));
+  AMF_CUDA(cudaMalloc(&V_d, (size_t)m * ld * es));
+  AMF_CUDA(cudaMalloc(&ci_d, 4 * nc));
+  AMF_CUDA(cudaMalloc(&cj_d, 4 * nc));
+  AMF_CUDA(cudaMalloc(&best_d, sizeof(amf_best_t)));
+  if (scores_h) AMF_CUDA(cudaMalloc(&sc_d, es * nc));
+  cudaStream_t s = nullptr;
+  if (ld != d) {
+    AMF_CUDA(cudaMemsetAsync(U_d, 0, (size_t)n * ld * es, s));
+    AMF_CUDA(cudaMemsetAsync(V_d, 0, (size_t)m * ld * es, s));
+  }
+  AMF_CUDA(cudaMemcpy2DAsync(U_d, ld * es, U_h, d * es, d * es, n, cudaMemcpyHostToDevice, s));
+  AMF_CUDA(cudaMemcpy2DAsync(V_d, ld * es, V_h, d * es, d * es, m, cudaMemcpyHostToDevice, s));
+  if (ncand > 0) {
+    AMF_CUDA(cudaMemcpyAsync(ci_d, ci_h, 4 * ncand, cudaMemcpyHostToDevice, s));
+    AMF_CUDA(cudaMemcpyAsync(cj_d, cj_h, 4 * ncand, cudaMemcpyHostToDevice, s));
+  }
+  int rc = amf_score_candidates(AMF_CRIT_PRED, dtype, ncand, ci_d, cj_d, d, ld, U_d, V_d, nullptr,
+                                0.0, sc_d, maximize, 0, best_d, s);
+  if (rc == AMF_OK) {
+    if (scores_h && ncand > 0)
+      AMF_CUDA(cudaMemcpyAsync(scores_h, sc_d, es * ncand, cudaMemcpyDeviceToHost, s));
+    AMF_CUDA(cudaMemcpyAsync(best_h, best_d, sizeof(amf_best_t), cudaMemcpyDeviceToHost, s));
+    AMF_CUDA(cudaStreamSynchronize(s));
+  }
+  cudaFree(U_d); cudaFree(V_d); cudaFree(ci_d); cudaFree(cj_d); cudaFree(best_d); cudaFree(sc_d);
+  return rc;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

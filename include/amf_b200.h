@@ -1,0 +1,190 @@
+/*
+ * amf_b200.h -- C ABI of the B200-native (sm_100a) accelerator for the python-pmf hot path
+ * of autonlab/active-matrix-factorization.
+ *
+ * The reference has no FFI: its seam is the Python class API backed by Cython
+ * (python-pmf/pmf_cy.pxd:6-36).  Each entry point below names the reference routine whose
+ * inner loop it replaces (paths relative to python-pmf/).  The Python host mirror in
+ * active_matrix_factorization_b200/ binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; amf_last_error() gives the
+ *     message of the calling thread's last failure.  No function falls back to the CPU.
+ *   - pointers named *_d are device pointers on the current CUDA device, *_h host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All work
+ *     is enqueued asynchronously unless the function name ends in _host or says it syncs.
+ *   - dtype: AMF_F32 (fast mode) or AMF_F64 (parity mode, the reference's precision).
+ *   - factor matrices are row-major (rows, ld) with ld >= d, ld*sizeof(T) a multiple of 16
+ *     bytes, and columns d..ld-1 equal to zero.
+ *   - the library keeps no global mutable state besides per-thread error text; handles may be
+ *     used from different host threads as long as one handle is not used concurrently.
+ */
+#ifndef AMF_B200_H
+#define AMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMF_F32 0
+#define AMF_F64 1
+
+#define AMF_OK 0
+#define AMF_ERR_INVALID 1
+#define AMF_ERR_CUDA 2
+#define AMF_ERR_UNSUPPORTED 3
+
+const char* amf_last_error(void);
+int amf_version(void);
+/* number of visible CUDA devices and the compute capability (major*10+minor) of the current one;
+ * fails (AMF_ERR_CUDA) when there is no usable device -- callers must not fall back. */
+int amf_device_info(int* n_devices, int* sm_arch, int* n_sms);
+
+/* ------------------------------------------------------------------------------------------
+ * Rating list (replaces `ratings`, the (nnz,3) float64 array iterated row by row in
+ * pmf_cy.pyx:184-186 and :217-221, and the adjacency dicts of bayes_pmf.py:241-255).
+ * Device-resident, stored twice: user-major (CSR) and item-major (CSC), each entry
+ * {other-side index:int32, rating:T}; order inside a row/column is the input order (stable).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amf_ratings amf_ratings_t;
+
+/* i_d/j_d/r_d: device COO arrays of length nnz (r_d of `dtype`).  Duplicates are kept. */
+int amf_ratings_create(amf_ratings_t** out, int32_t n_users, int32_t n_items, int64_t nnz,
+                       const int32_t* i_d, const int32_t* j_d, const void* r_d, int dtype,
+                       void* stream);
+/* same from host arrays (copies them to the device first) */
+int amf_ratings_create_host(amf_ratings_t** out, int32_t n_users, int32_t n_items, int64_t nnz,
+                            const int32_t* i_h, const int32_t* j_h, const void* r_h, int dtype);
+int amf_ratings_destroy(amf_ratings_t* h);
+int64_t amf_ratings_nnz(const amf_ratings_t* h);
+/* device pointers of the two layouts (for tests / Gibbs):  ptr int64[rows+1], idx int32[nnz],
+ * val T[nnz].  side 0 = user-major, 1 = item-major. */
+int amf_ratings_layout(const amf_ratings_t* h, int side, const int64_t** ptr_d,
+                       const int32_t** idx_d, const void** val_d);
+/* sum and count of ratings -> mean_rating (pmf_cy.pyx:63); synchronises. */
+int amf_ratings_mean(const amf_ratings_t* h, double* mean_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PMF objective and gradient (pmf_cy.pyx:170-193 log_likelihood, :204-223 gradient,
+ * :225-234 update_sigma).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  double sigma_sq, sigma_u_sq, sigma_v_sq; /* pmf_cy.pyx:40-42 */
+  double mean_offset;                      /* mean_rating if subtract_mean else 0 (:165-168) */
+} amf_pmf_params_t;
+
+/* Fused loss + gradient at (U, V):
+ *   sums_d[0] = sum (r - r_hat)^2, sums_d[1] = |U|^2, sums_d[2] = |V|^2   (double[3], device)
+ *   dU = -U/sigma_u_sq + sum_j V_j (r - r_hat)/sigma_sq, dV symmetric     (ascent direction)
+ * dU_d/dV_d may both be NULL: loss only.  log-likelihood =
+ *   -sums[0]/(2 sigma_sq) - sums[1]/(2 sigma_u_sq) - sums[2]/(2 sigma_v_sq). */
+int amf_pmf_loss_grad(const amf_ratings_t* h, int dtype, int d, int ld, const void* U_d,
+                      const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
+                      double* sums_d, void* stream);
+
+/* Line-search trial point of fit_lls (pmf_cy.pyx:271-272): X_new = X + lr * G, elementwise
+ * over `count` elements (the padded (rows, ld) block). */
+int amf_axpy(int dtype, int64_t count, const void* X_d, const void* G_d, double lr,
+             void* Xnew_d, void* stream);
+
+/* Gradient of an explicit COO mini-batch with atomics (gradient(ratings=batch),
+ * pmf_cy.pyx:205,211-212 as used by fit_minibatches :335-336).  dU/dV must already hold the
+ * prior term or zeros; this only adds the data term.  sums_d[0] gets the squared error. */
+int amf_pmf_grad_coo(int dtype, int64_t nnz, const int32_t* i_d, const int32_t* j_d,
+                     const void* r_d, int d, int ld, const void* U_d, const void* V_d,
+                     const amf_pmf_params_t* p, void* dU_d, void* dV_d, double* sums_d,
+                     void* stream);
+/* dX = -X / sigma_x_sq and |X|^2 -> *norm2_d (added) : the prior half of the gradient */
+int amf_pmf_prior(int dtype, int64_t count, const void* X_d, double sigma_x_sq, void* dX_d,
+                  double* norm2_d, void* stream);
+
+/* Momentum SGD update of fit_minibatches (pmf_cy.pyx:338-344), elementwise over `count`:
+ *   inc = momentum * inc + scale * G ;  X += inc */
+int amf_momentum_step(int dtype, int64_t count, void* inc_d, const void* G_d, double momentum,
+                      double scale, void* X_d, void* stream);
+
+/* End-to-end variant with HOST buffers (what ProbabilisticMatrixFactorization.gradient() /
+ * .log_likelihood(users, items) call): copies U, V (n*d and m*d, tightly packed row-major, of
+ * `dtype`) to the device, runs amf_pmf_loss_grad, copies dU, dV (may be NULL) and the three sums
+ * back, and synchronises. */
+int amf_pmf_loss_grad_host(const amf_ratings_t* h, int dtype, int d, const void* U_h,
+                           const void* V_h, const amf_pmf_params_t* p, void* dU_h, void* dV_h,
+                           double* sums_h);
+
+/* ------------------------------------------------------------------------------------------
+ * Candidate scoring with fused arg-best (active_pmf.py:739-770 _get_key_vals + :737 chooser;
+ * criteria :416-421 pred, :432-439 _prob_ge_cutoff, :392-400 approx_pred_mean_var,
+ * :502-524 pred_variance with normal_exps_cy.pyx:111-135 exp_dotprod_sq).
+ * ------------------------------------------------------------------------------------------ */
+#define AMF_CRIT_PRED 0          /* U_i . V_j (MAP)                                         */
+#define AMF_CRIT_APPROX_MEAN 1   /* E[U_i . V_j] under the normal approximation            */
+#define AMF_CRIT_PRED_VARIANCE 2 /* Var[U_i . V_j] under the normal approximation          */
+#define AMF_CRIT_PROB_GE 3       /* norm.sf(cutoff, loc=E, scale=Var)  (reference quirk)    */
+
+/* Strided view of the Gaussian approximation N(mean, cov) over all factors.  Element (k,l) of
+ * the d x d block A_i = Cov(U_i, U_i) is cov_uu[i*uu_stride + k*uu_ld + l]; B_j likewise;
+ * C_ij[k,l] = Cov(U_ki, V_lj) = cov_uv[i*uv_stride_i + j*uv_stride_j + k*uv_ld + l] or
+ * cov_uv == NULL for a block-diagonal posterior.  With the reference's full k x k matrix
+ * (k=(n+m)d, active_pmf.py:136-142): mean_u=mean, mean_v=mean+n*d, cov_uu=cov,
+ * uu_stride=d*k+d, uu_ld=k, cov_vv=cov+n*d*k+n*d, cov_uv=cov+n*d, uv_stride_i=d*k,
+ * uv_stride_j=d, uv_ld=k.  All of `dtype`. */
+typedef struct {
+  const void* mean_u; int64_t mean_u_stride;
+  const void* mean_v; int64_t mean_v_stride;
+  const void* cov_uu; int64_t uu_stride, uu_ld;
+  const void* cov_vv; int64_t vv_stride, vv_ld;
+  const void* cov_uv; int64_t uv_stride_i, uv_stride_j, uv_ld;
+} amf_normal_view_t;
+
+/* Scores ncand candidates (ci_d[c], cj_d[c]).  scores_d (T[ncand]) may be NULL when only the
+ * winner is wanted.  best_d: device record {double value; int64 index} of the max
+ * (maximize != 0) or min, lowest candidate index on ties, index -1 if ncand == 0 or all NaN.
+ * For AMF_CRIT_PRED U_d/V_d/ld are used; for the others `nv`.  index_base is added to the
+ * reported index (shard offset on multi-GPU runs). */
+typedef struct { double value; int64_t index; } amf_best_t;
+int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t* ci_d,
+                         const int32_t* cj_d, int d, int ld, const void* U_d, const void* V_d,
+                         const amf_normal_view_t* nv, double cutoff, void* scores_d,
+                         int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
+
+/* End-to-end host variant of AMF_CRIT_PRED: host candidate arrays and factors in, scores
+ * (may be NULL) and winner out; synchronises. */
+int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,
+                        int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
+                        void* scores_h, int maximize, amf_best_t* best_h);
+
+/* ------------------------------------------------------------------------------------------
+ * Bayesian PMF (bayes_pmf.py:189-216 sample_feature inside the sweeps of :283-300;
+ * :433-455 predict / pred_variance / :528-538 prob_ge_cutoff over a list of samples).
+ * ------------------------------------------------------------------------------------------ */
+/* One half-sweep: for every row n of the side being sampled
+ *   Lambda = alpha + beta F'F,  cov = Lambda^-1,  mean = cov (beta F'(r - mean_offset) + alpha mu),
+ *   out[n] = chol(cov) z[n] + mean            (lower Cholesky factor, like np.linalg.cholesky)
+ * where F = other[idx of row n].  side 0 samples users (other = items), 1 samples items.
+ * z_d: (rows, d) standard normals in the reference's draw order; alpha_d (d,d), mu_d (d).
+ * other_d/out_d are tightly packed (rows, d).  Always computed in fp64 when dtype==AMF_F64. */
+int amf_gibbs_half_sweep(const amf_ratings_t* h, int side, int dtype, int d, const void* other_d,
+                         const void* alpha_d, const void* mu_d, double beta, double mean_offset,
+                         const void* z_d, void* out_d, void* stream);
+
+/* 1 in *failed if any row of the last half-sweep on this handle met a non-positive-definite
+ * precision/covariance (np.linalg.cholesky would have raised LinAlgError); synchronises. */
+int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream);
+
+/* Sample statistics of S posterior samples at ncand cells: Us_d (S, n, d), Vs_d (S, m, d)
+ * tightly packed.  Any of mean_d / var_d / prob_d may be NULL.  var is the population variance
+ * (np.var, bayes_pmf.py:448); prob = fraction of samples with prediction >= cutoff.
+ * best_d (nullable) selects on `select` (0 mean, 1 var, 2 prob). */
+int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
+                           int S, int32_t n, int32_t m, int d, const void* Us_d, const void* Vs_d,
+                           double mean_offset, double cutoff, void* mean_d, void* var_d,
+                           void* prob_d, int select, int maximize, int64_t index_base,
+                           amf_best_t* best_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMF_B200_H */

@@ -136,7 +136,8 @@ def case_d5():
 def case_fit():
     n, m, d = 30, 40, 4
     rng, R, users, items = random_problem(5, n, m, d, 300, scale=.8)
-    out = dict(ratings=R, users0=users, items0=items)
+    real = rng.normal(0, 1, (n, m))
+    out = dict(ratings=R, users0=users, items0=items, real=real)
     for sm in (False, True):
         p = PMF(R, d, sm)
         p.users, p.items = users.copy(), items.copy()
@@ -147,8 +148,6 @@ def case_fit():
         out["lls" + tag] = np.array(lls)
         out["users_fit" + tag], out["items_fit" + tag] = p.users, p.items
         out["mean_rating"] = p.mean_rating
-        real = rng.normal(0, 1, (n, m))
-        out["real"] = real
         out["rmse" + tag] = p.rmse(real)
         p.update_sigma(); p.update_sigma_uv()
         out["sigmas" + tag] = np.array([p.sigma_sq, p.sigma_u_sq, p.sigma_v_sq])
@@ -201,8 +200,7 @@ def case_gibbs():
 
 
 if __name__ == "__main__":
-    case_known_answer()
-    case_d5()
-    case_fit()
-    case_lookahead()
-    case_gibbs()
+    cases = dict(known_answer=case_known_answer, d5=case_d5, fit=case_fit,
+                 lookahead=case_lookahead, gibbs=case_gibbs)
+    for name in (sys.argv[1:] or list(cases)):
+        cases[name]()

@@ -1,0 +1,106 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, and
+the host-side mirror of the reference API behaves like the reference where no compute is
+involved (constructors, bookkeeping, errors, pickling)."""
+import copy
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from active_matrix_factorization_b200 import _native as N
+from active_matrix_factorization_b200 import build as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return N.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "amf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(amf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), "libamf_b200.so does not export %s" % name
+    # and the ctypes prototypes cover the same set
+    assert set(names) == set(N.PROTOTYPES) | {"amf_last_error"}
+
+
+def test_no_device_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        N.require_device()
+
+
+def _toy():
+    rng = np.random.RandomState(0)
+    return np.array([(i, j, float(rng.randint(1, 6))) for i in range(4) for j in range(5)
+                     if (i + j) % 2 == 0])
+
+
+def test_constructor_and_bookkeeping():
+    from active_matrix_factorization_b200.pmf_cy import ProbabilisticMatrixFactorization as PMF
+    R = _toy()
+    np.random.seed(3)
+    p = PMF(R, 3)
+    np.random.seed(3)
+    assert np.array_equal(p.users, np.random.random((4, 3)))       # same RNG draws as the reference
+    assert np.array_equal(p.items, np.random.random((5, 3)))
+    assert (p.num_users, p.num_items, p.latent_d) == (4, 5, 3)
+    assert p.mean_rating == pytest.approx(R[:, 2].mean())
+    assert len(p.rated) == len(R) and len(p.rated) + len(p.unrated) == 20
+    assert (p.sigma_sq, p.sigma_u_sq, p.sigma_v_sq) == (1, 10, 10)
+    assert (p.learning_rate, p.min_learning_rate, p.stop_thresh) == (1e-4, 1e-10, 1e-2)
+    p.add_rating(0, 1, 2.0)
+    assert (0, 1) in p.rated and (0, 1) not in p.unrated and p.ratings.shape == (len(R) + 1, 3)
+    with pytest.raises(ValueError):
+        p.add_rating(0, 1, 3.0)
+    with pytest.raises(TypeError):
+        p.add_ratings([[1, 2]])
+    with pytest.raises(AssertionError):
+        p.add_rating(9, 0, 1.0)
+    with pytest.raises(TypeError):
+        PMF(np.zeros((3, 2)))
+    with pytest.raises(TypeError):
+        PMF(None)
+    p.fit_type = ('nope',)
+    with pytest.raises(ValueError):
+        p.do_fit()
+    q = PMF(R, 2, knowable=[(0, 1), (0, 0)])
+    assert q.unrated == {(0, 1)}
+
+
+def test_state_roundtrip():
+    from active_matrix_factorization_b200.pmf_cy import ProbabilisticMatrixFactorization as PMF
+    p = PMF(_toy(), 2, True)
+    p.sigma_sq = 0.5
+    keys = {'latent_d', 'num_users', 'num_items', 'learning_rate', 'min_learning_rate',
+            'stop_thresh', 'sigma_sq', 'sigma_u_sq', 'sigma_v_sq', 'fit_type', 'sig_u_mean',
+            'sig_u_var', 'sig_v_mean', 'sig_v_var', 'ratings', 'users', 'items', 'subtract_mean',
+            'mean_rating', 'rated', 'unrated'}
+    assert set(p.__getstate__()) == keys                               # pmf_cy.pyx:99-126
+    for q in (copy.deepcopy(p), pickle.loads(pickle.dumps(p))):
+        assert q.sigma_sq == 0.5 and q.subtract_mean and q.latent_d == 2
+        assert np.array_equal(q.users, p.users) and q.users is not p.users
+        assert q.rated == p.rated
+    r = PMF(_toy(), 1)
+    r.__setstate__(p.__getstate__())                                   # add_rmse_boosts.py:39-40
+    assert r.latent_d == 2 and np.array_equal(r.items, p.items)
+
+
+def test_parse_fit_type():
+    from active_matrix_factorization_b200.pmf_cy import parse_fit_type
+    assert parse_fit_type('batch') == ('batch',)
+    assert parse_fit_type('mini-valid,100,30,1.5') == ('mini-valid', 100, 30, 1.5)

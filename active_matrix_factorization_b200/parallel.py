@@ -1,0 +1,158 @@
+"""One process per GPU: sharding of the two data-parallel axes of the path.
+
+* candidate scoring (active_pmf.py:739-770): the pool is split into contiguous shards, one per
+  rank; each rank scores its shard with the fused arg-best kernel, then a 16-byte all-gather of
+  (value, global index) and the same deterministic reduction on every rank (best value, lowest
+  global index on ties).  No score ever crosses NVLink unless the full matrix is requested.
+* PMF loss+gradient (pmf_cy.pyx:170-223): ratings are split by blocks; every rank evaluates
+  the data term on its block, rank 0 alone adds the prior term and the norms, and dU, dV and
+  the three objective sums are all-reduced (NCCL over NVLink; gloo in the CPU tests).
+
+The collectives go through torch.distributed so the same code runs under NCCL and gloo.
+"""
+import math
+
+import torch
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+def shard_bounds(total, world, rank):
+    """Contiguous, balanced [lo, hi) of `total` items for `rank` of `world`."""
+    base, extra = divmod(int(total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def reduce_winners(values, indices, maximize=True):
+    """values (W,) float64, indices (W,) int64 (-1 = shard had no valid candidate).
+    Returns (value, index) of the best; ties go to the lowest index; (nan, -1) if none."""
+    valid = indices >= 0
+    valid &= ~torch.isnan(values)
+    if not bool(valid.any()):
+        return float('nan'), -1
+    fill = -math.inf if maximize else math.inf
+    v = torch.where(valid, values, torch.full_like(values, fill))
+    top = v.max() if maximize else v.min()
+    tie = valid & (v == top)
+    big = torch.iinfo(torch.int64).max
+    idx = torch.where(tie, indices, torch.full_like(indices, big)).min()
+    return float(top), int(idx)
+
+
+def gather_winner(best, world, group=None):
+    """best: tensor of 2 int64 words holding {float64 value, int64 index} (amf_best_t).
+    All-gathers the records and returns the reduced (value, index) -- identical on every rank."""
+    if world == 1:
+        rec = best.view(1, 2)
+    else:
+        rec = torch.empty((world, 2), dtype=torch.int64, device=best.device)
+        dist.all_gather_into_tensor(rec, best.view(1, 2), group=group) if best.is_cuda else \
+            dist.all_gather(list(rec.unbind(0)), best.view(2), group=group)
+    return rec
+
+
+def winner_from_records(rec, maximize=True):
+    vals = rec[:, 0].contiguous().view(torch.float64)
+    return reduce_winners(vals, rec[:, 1].contiguous(), maximize)
+
+
+def prior_once_params(params, rank):
+    """Only rank 0 contributes the prior term -U/sigma_u^2 (and V's); the others pass an
+    infinite prior variance so that the all-reduced gradient counts it once."""
+    if rank == 0:
+        return params
+    return type(params)(params.sigma_sq, math.inf, math.inf, params.mean_offset)
+
+
+def combine_loss_grad(dU, dV, sums, world, rank, group=None):
+    """All-reduce of the per-shard data terms; |U|^2, |V|^2 are counted once (rank 0)."""
+    if world == 1:
+        return
+    if rank != 0:
+        sums[1:].zero_()
+    if dU is not None:
+        dist.all_reduce(dU, group=group)
+        dist.all_reduce(dV, group=group)
+    dist.all_reduce(sums, group=group)
+
+
+class ShardedStep:
+    """The benchmarked step: fused loss+gradient over this rank's rating block, then scoring
+    of this rank's candidate shard with a fused arg-best, each followed by its collective."""
+
+    def __init__(self, rat, d, name, world=1, rank=0):
+        self.rat, self.d, self.name, self.world, self.rank = rat, d, name, world, rank
+        self.index_base = 0
+        self._rec = None
+        # kernels launched by one step: 2 prior + 2 side passes; scoring + winner reduction
+        self.launches_per_step = 6
+
+    def set_candidate_offset(self, ncand_local):
+        """global index = offset of this rank's shard + local index"""
+        if self.world == 1:
+            self.index_base = 0
+            return
+        cnt = torch.tensor([ncand_local], dtype=torch.int64, device='cuda')
+        allc = torch.empty(self.world, dtype=torch.int64, device='cuda')
+        dist.all_gather_into_tensor(allc, cnt)
+        self.index_base = int(allc[:self.rank].sum().item())
+
+    def loss_grad(self, U, V, params, dU, dV, sums):
+        from . import device as D
+        D.loss_grad(self.rat, self.d, U, V, prior_once_params(params, self.rank), dU, dV, sums)
+        combine_loss_grad(dU, dV, sums, self.world, self.rank)
+
+    def select(self, criterion, ci, cj, U, V, view, cutoff, maximize, best):
+        from . import device as D
+        from . import _native as N
+        import ctypes as C
+        if self._rec is None:
+            self.set_candidate_offset(int(ci.numel()))
+            self._rec = True
+        lib = N.require_device()
+        N.check(lib.amf_score_candidates(
+            criterion, D.code(self.name), int(ci.numel()), D.ptr(ci), D.ptr(cj), self.d,
+            U.shape[1] if U is not None else 0, D.ptr(U), D.ptr(V),
+            C.byref(view) if view is not None else None, float(cutoff), None,
+            1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
+        if self.world > 1:
+            rec = gather_winner(best, self.world)
+            vals = rec[:, 0].contiguous().view(torch.float64)
+            idx = rec[:, 1].contiguous()
+            # device-side reduction with the same tie-break; no host sync inside the step
+            valid = (idx >= 0) & ~torch.isnan(vals)
+            fill = -math.inf if maximize else math.inf
+            v = torch.where(valid, vals, torch.full_like(vals, fill))
+            top = v.max() if maximize else v.min()
+            tie = valid & (v == top)
+            win = torch.where(tie, idx, torch.full_like(idx, torch.iinfo(torch.int64).max)).min()
+            best[0] = top.view(torch.int64)
+            best[1] = torch.where(valid.any(), win, torch.full_like(win, -1))
+
+    def kernel_times(self, U, V, params, dU, dV, sums, ci, cj, best, reps=5):
+        """Average device time of the two dominant kernels, timed alone on the current stream
+        with CUDA events (inputs are far larger than L2, so every launch streams from HBM)."""
+        from . import device as D
+        from . import _native as N
+        lib = N.require_device()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            D.loss_grad(self.rat, self.d, U, V, params, dU, dV, sums)
+        e1.record()
+        torch.cuda.synchronize()
+        side = e0.elapsed_time(e1) / reps
+        e0.record()
+        for _ in range(reps):
+            N.check(lib.amf_score_candidates(N.CRIT_PRED, D.code(self.name), int(ci.numel()),
+                                             D.ptr(ci), D.ptr(cj), self.d, U.shape[1], D.ptr(U),
+                                             D.ptr(V), None, 0.0, None, 1, 0, D.ptr(best),
+                                             D.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        return {"side_pass_ms": side, "score_ms": e0.elapsed_time(e1) / reps}

@@ -1,0 +1,451 @@
+#!/usr/bin/env python3
+"""Benchmark of the python-pmf hot path on B200 (BASELINE.json metric):
+candidate entries scored/sec and PMF ratings/sec/iter, vs the reference's CPU path.
+
+One "step" = one active-learning inner step on the C5 workload: one fused PMF
+loss+gradient evaluation over the observed-rating list (pmf_cy.pyx:170-223) followed by one
+scoring pass with fused arg-max over the candidate pool (active_pmf.py:709-770, criterion
+`pred`).  `value` is candidates scored per second over the scoring phase; the gradient phase
+is reported beside it as ratings/sec/iter (`phases`).  `ms_per_step` covers both phases.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidates_scored_per_sec"
+UNIT = "candidates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--users", type=int, default=200_000)
+    ap.add_argument("--items", type=int, default=50_000)
+    ap.add_argument("--latent-d", type=int, default=32)
+    ap.add_argument("--nnz", type=int, default=50_000_000, help="observed ratings per GPU")
+    ap.add_argument("--ncand", type=int, default=100_000_000, help="candidates per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "C5 synthetic %dx%d, rank %d, %d ratings + %d candidates per GPU" % (
+        a.users, a.items, a.latent_d, a.nnz, a.ncand)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic C5 data, generated on the device
+# ------------------------------------------------------------------------------------------
+def make_problem(a, rank, torch):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n, m, d = a.users, a.items, a.latent_d
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    # observed cells: uniform, every row and column hit at least once, duplicates removed
+    i = torch.randint(0, n, (a.nnz,), generator=g, device=dev, dtype=torch.int64)
+    j = torch.randint(0, m, (a.nnz,), generator=g, device=dev, dtype=torch.int64)
+    i = torch.cat([i, torch.arange(n, device=dev), torch.randint(0, n, (m,), generator=g, device=dev)])
+    j = torch.cat([j, torch.randint(0, m, (n,), generator=g, device=dev), torch.arange(m, device=dev)])
+    keys = torch.unique(i * m + j)
+    del i, j
+    perm = torch.randperm(keys.numel(), generator=g, device=dev)
+    keys_shuf = keys[perm]                 # the rating LIST is unordered, like the reference's
+    del perm
+    ri = (keys_shuf // m).to(torch.int32)
+    rj = (keys_shuf % m).to(torch.int32)
+    del keys_shuf
+    g0 = torch.Generator(device=dev)
+    g0.manual_seed(99)                     # the model is the same on every rank
+    scale = 1.0 / np.sqrt(np.sqrt(d))
+    Ut = torch.randn((n, d), generator=g0, device=dev, dtype=tdt) * scale
+    Vt = torch.randn((m, d), generator=g0, device=dev, dtype=tdt) * scale
+    r = (Ut[ri.long()] * Vt[rj.long()]).sum(1) + 0.25 * torch.randn(ri.numel(), generator=g, device=dev, dtype=tdt)
+    U = (Ut + 0.1 * torch.randn((n, d), generator=g0, device=dev, dtype=tdt)).contiguous()
+    V = (Vt + 0.1 * torch.randn((m, d), generator=g0, device=dev, dtype=tdt)).contiguous()
+    del Ut, Vt
+    # candidates: distinct unobserved cells, sorted by (i, j)
+    ck = torch.randint(0, n * m, (int(a.ncand * 1.02) + 1024,), generator=g, device=dev, dtype=torch.int64)
+    ck = torch.unique(ck)
+    pos = torch.searchsorted(keys, ck).clamp_(max=keys.numel() - 1)
+    ck = ck[keys[pos] != ck]
+    del pos, keys
+    if ck.numel() > a.ncand:
+        # drop a random subset but keep the order
+        keep = torch.randperm(ck.numel(), generator=g, device=dev)[:a.ncand].sort().values
+        ck = ck[keep]
+        del keep
+    ci = (ck // m).to(torch.int32)
+    cj = (ck % m).to(torch.int32)
+    del ck
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return dict(ri=ri, rj=rj, r=r.contiguous(), U=U, V=V, ci=ci, cj=cj)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(a, prob_host, sample):
+    """Times the reference's own CPU path (oracle/_ref when built, else the numpy port) on a
+    bounded sample of the same workload.  Returns the cpu_baseline dict."""
+    from oracle import build_ref
+    n, m, d = a.users, a.items, a.latent_d
+    ri, rj, r, U, V, ci, cj = prob_host
+    s_r = min(sample, len(ri))
+    s_c = min(sample, len(ci))
+    R = np.column_stack((ri[:s_r], rj[:s_r], r[:s_r])).astype(float)
+    R[0, 0], R[1, 1] = n - 1, m - 1        # pin the model shape (reference infers it from max id)
+    pool = list(zip(ci[:s_c].tolist(), cj[:s_c].tolist()))
+    out = {"cores": 1, "unit": UNIT}
+    if build_ref.built():
+        from oracle import ref_loader
+        ref = ref_loader.load()
+        apmf = ref.active_pmf.ActivePMF(R, d, knowable=())
+        apmf.users, apmf.items = U.astype(float), V.astype(float)
+        t0 = time.perf_counter()
+        apmf.gradient()
+        apmf.log_likelihood()
+        t_grad = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        vals = apmf._get_key_vals(pool, ref.active_pmf.ActivePMF.pred, 1, None)
+        best = max(zip(pool, vals), key=lambda t: t[1])[0]
+        t_score = time.perf_counter() - t0
+        out["kind"] = "reference"
+        how = "oracle/_ref (reference Cython) ActivePMF.gradient()+log_likelihood() and _get_key_vals(pool, pred, procs=1)"
+    else:
+        from oracle import pmf_oracle as O
+        t0 = time.perf_counter()
+        O.gradient(R, U.astype(float), V.astype(float))
+        O.log_likelihood(R, U.astype(float), V.astype(float))
+        t_grad = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        vals = np.einsum("nd,nd->n", U[ci[:s_c]].astype(float), V[cj[:s_c]].astype(float))
+        best = pool[int(np.argmax(vals))]
+        t_score = time.perf_counter() - t0
+        out["kind"] = "port"
+        how = "oracle/pmf_oracle.py (numpy port) gradient+log_likelihood and vectorised pred"
+    out["value"] = s_c / t_score
+    out["pmf_ratings_per_sec_iter"] = s_r / t_grad
+    out["sample"] = "%d of the ratings and %d of the candidates of rank 0's shard, fp64, %s; " \
+                    "per-item cost is size independent (SURVEY.md 6)" % (s_r, s_c, how)
+    out["seconds"] = {"grad_plus_ll": t_grad, "score": t_score}
+    out["cpu_model"] = cpu_model()
+    out["host_cores"] = os.cpu_count()
+    out["_best"] = best
+    return out
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rng = np.random.RandomState(1234)
+    n, m, d = a.users, a.items, a.latent_d
+    s = a.cpu_sample
+    ri, rj = rng.randint(0, n, s), rng.randint(0, m, s)
+    U = (rng.standard_normal((n, d)) / np.sqrt(np.sqrt(d))).astype(np.float32)
+    V = (rng.standard_normal((m, d)) / np.sqrt(np.sqrt(d))).astype(np.float32)
+    r = (U[ri] * V[rj]).sum(1) + .25 * rng.standard_normal(s)
+    ck = np.unique(rng.randint(0, n * m, s))
+    ci, cj = ck // m, ck % m
+    host = (ri, rj, r, U, V, ci, cj)
+    times = []
+    res = None
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        res = cpu_reference_sample(a, host, s)
+        if it >= a.warmup:
+            times.append((time.perf_counter() - t0, res["seconds"]["score"], res["seconds"]["grad_plus_ll"]))
+    t_score = float(np.mean([t[1] for t in times]))
+    t_grad = float(np.mean([t[2] for t in times]))
+    value = len(ci) / t_score
+    res.pop("_best", None)
+    res["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * float(np.mean([t[0] for t in times])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(a),
+                                        "note": "each step is a bounded sample (%d ratings, %d candidates) "
+                                                "of the workload on the host CPU" % (s, len(ci))},
+        "phases": {"pmf_loss_grad": {"ratings_per_sec_iter": s / t_grad},
+                   "score_pred": {"candidates_per_sec": value}},
+        "cpu_baseline": res,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from active_matrix_factorization_b200 import build as B
+    if rank == 0:
+        B.build()
+    if world > 1:
+        dist.barrier()
+    from active_matrix_factorization_b200 import _native as N
+    from active_matrix_factorization_b200 import device as D
+    from active_matrix_factorization_b200 import parallel as P
+    lib = N.require_device()
+
+    n, m, d = a.users, a.items, a.latent_d
+    name = a.dtype
+    es = 4 if name == "f32" else 8
+    prob = make_problem(a, rank, torch)
+    rat = D.Ratings(n, m, prob["ri"], prob["rj"], prob["r"], name)
+    nnz, ncand = rat.nnz, int(prob["ci"].numel())
+    U, V, ci, cj = prob["U"], prob["V"], prob["ci"], prob["cj"]
+    ld = D.padded_ld(d, name)
+    assert ld == d, "bench uses an unpadded rank"
+    dU, dV = torch.empty_like(U), torch.empty_like(V)
+    sums = torch.zeros(3, dtype=torch.float64, device=U.device)
+    best = torch.zeros(2, dtype=torch.int64, device=U.device)
+    params = D.pmf_params(1.0, 10.0, 10.0, 0.0)
+    step = P.ShardedStep(rat, d, name, world, rank)
+
+    def one_step(ev=None):
+        if ev: ev[0].record()
+        step.loss_grad(U, V, params, dU, dV, sums)
+        if ev: ev[1].record()
+        step.select(N.CRIT_PRED, ci, cj, U, V, None, 0.0, True, best)
+        if ev: ev[2].record()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        one_step()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t_begin.record()
+    for k in range(a.steps):
+        one_step(evs[k])
+    t_end.record()
+    sync()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_begin.elapsed_time(t_end)
+    grad_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    score_ms = total_ms - grad_ms          # scoring + selection (+ its collective) up to step end
+    # isolated timing of the two dominant kernels for the roofline (same stream, CUDA events)
+    kt = step.kernel_times(U, V, params, dU, dV, sums, ci, cj, best, reps=max(5, a.steps // 2))
+    tm = torch.tensor([total_ms, grad_ms, score_ms, kt["side_pass_ms"], kt["score_ms"]],
+                      dtype=torch.float64, device=U.device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, grad_ms, score_ms, side_ms, scorek_ms = tm.tolist()
+
+    # ---- end to end through the host-buffer C ABI (PCIe copies inside the timed region) ------
+    U_h = torch.empty((n, d), dtype=U.dtype).pin_memory(); U_h.copy_(U)
+    V_h = torch.empty((m, d), dtype=V.dtype).pin_memory(); V_h.copy_(V)
+    dU_h = torch.empty((n, d), dtype=U.dtype).pin_memory()
+    dV_h = torch.empty((m, d), dtype=V.dtype).pin_memory()
+    ci_h = torch.empty(ncand, dtype=torch.int32).pin_memory(); ci_h.copy_(ci)
+    cj_h = torch.empty(ncand, dtype=torch.int32).pin_memory(); cj_h.copy_(cj)
+    sums_h = np.zeros(3)
+    best_h = N.Best()
+
+    def e2e_step():
+        t0 = time.perf_counter()
+        N.check(lib.amf_pmf_loss_grad_host(rat.handle, D.code(name), d, C.c_void_p(U_h.data_ptr()),
+                                           C.c_void_p(V_h.data_ptr()), C.byref(params),
+                                           C.c_void_p(dU_h.data_ptr()), C.c_void_p(dV_h.data_ptr()),
+                                           N.host_ptr(sums_h)))
+        t1 = time.perf_counter()
+        N.check(lib.amf_score_pred_host(D.code(name), ncand, C.c_void_p(ci_h.data_ptr()),
+                                        C.c_void_p(cj_h.data_ptr()), n, m, d,
+                                        C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
+                                        None, 1, C.byref(best_h)))
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    e2e_step()
+    sync()
+    e2e = [e2e_step() for _ in range(a.e2e_steps)]
+    e2e_t = torch.tensor([float(np.mean([t[0] for t in e2e])), float(np.mean([t[1] for t in e2e]))],
+                         dtype=torch.float64, device=U.device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_grad_s, e2e_score_s = e2e_t.tolist()
+    # the two paths must agree on the winner
+    bv, bi = np.frombuffer(best.cpu().numpy().tobytes()[:8], dtype=np.float64)[0], int(best[1].item())
+    if world == 1:
+        assert best_h.index == bi, "device-resident and end-to-end paths picked different candidates"
+
+    cnt = torch.tensor([nnz, ncand], dtype=torch.int64, device=U.device)
+    if world > 1:
+        dist.all_reduce(cnt)
+    nnz_all, ncand_all = cnt.tolist()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind = peaks()
+    tables = (n + m) * d * es
+    score_bytes = ncand * 8 + tables
+    grad_bytes = nnz * 12 + 2 * tables
+    score_gbs = score_bytes / (scorek_ms * 1e-3) / 1e9
+    grad_gbs = grad_bytes / (side_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": ncand_all / (score_ms / a.steps * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": name, "data": "synthetic",
+        "config": {"workload": workload_name(a), "criterion": "pred (MAP prediction) with fused arg-max, winner only",
+                   "parallelism": "candidates and ratings sharded per GPU (weak), NCCL all-reduce of dU/dV/sums + all-gather of winners" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (rating list %.0f MB x2 layouts, candidates %.0f MB per GPU)" % (nnz * 8 / 1e6, ncand * 8 / 1e6),
+                   "value_is": "candidates / scoring-phase time; ms_per_step covers gradient + scoring"},
+        "phases": {
+            "pmf_loss_grad": {"ms": grad_ms / a.steps, "ratings_per_sec_iter": nnz_all / (grad_ms / a.steps * 1e-3), "nnz_total": nnz_all},
+            "score_pred": {"ms": score_ms / a.steps, "candidates_per_sec": ncand_all / (score_ms / a.steps * 1e-3), "ncand_total": ncand_all},
+        },
+        "roofline": {"kernel": "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
+                     "peak_source": peak_kind, "unit": "GB/s", "frac": score_gbs / hbm_peak,
+                     "algorithmic_bytes": score_bytes, "kernel_ms": scorek_ms, "traffic": None},
+        "roofline_gradient": {"kernel": "side_pass_kernel x2 + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
+                              "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": grad_gbs / hbm_peak,
+                              "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms, "traffic": None},
+        "e2e": {"value": ncand_all / e2e_score_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(ncand * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
+                "pmf_ratings_per_sec_iter": nnz_all / e2e_grad_s,
+                "note": "amf_pmf_loss_grad_host + amf_score_pred_host with pinned host buffers; rating list resident"},
+        "gpu_launches": a.steps * step.launches_per_step,
+        "clocks": clocks,
+        "selected": {"value": float(bv), "index": bi},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        host = (prob["ri"][:a.cpu_sample].cpu().numpy(), prob["rj"][:a.cpu_sample].cpu().numpy(),
+                prob["r"][:a.cpu_sample].double().cpu().numpy(), U.cpu().numpy(), V.cpu().numpy(),
+                ci[:a.cpu_sample].cpu().numpy(), cj[:a.cpu_sample].cpu().numpy())
+        cb = cpu_reference_sample(a, host, a.cpu_sample)
+        # parity spot check of the sample against the device path
+        cb.pop("_best", None)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

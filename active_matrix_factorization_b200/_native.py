@@ -29,6 +29,16 @@ class NormalView(C.Structure):
                 ("uv_stride_j", C.c_int64), ("uv_ld", C.c_int64)]
 
 
+class NormalFitParams(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("d", C.c_int32),
+                ("sigma_sq", C.c_double), ("sigma_u_sq", C.c_double), ("sigma_v_sq", C.c_double),
+                ("learning_rate", C.c_double), ("min_eig", C.c_double), ("kl_stop", C.c_double),
+                ("min_lr", C.c_double), ("max_steps", C.c_int32)]
+
+
+NORMAL_FIT, NORMAL_KL, NORMAL_GRADIENT, NORMAL_PROJECT = 0, 1, 2, 3
+
+
 class Best(C.Structure):
     _fields_ = [("value", C.c_double), ("index", C.c_int64)]
 
@@ -60,6 +70,9 @@ PROTOTYPES = {
     "amf_gibbs_status": [_P, C.POINTER(_INT), _P],
     "amf_bayes_sample_stats": [_INT, _I64, _P, _P, _INT, _I32, _I32, _INT, _P, _P, _F64, _F64,
                                _P, _P, _P, _INT, _INT, _I64, _P, _P],
+    "amf_normal_workspace_doubles": [_I32, _I32, _INT],
+    "amf_normal_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
+                           _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],
     "amf_score_pred_host": [_INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT,
                             C.POINTER(Best)],
 }
@@ -86,7 +99,7 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = _I64 if name == "amf_ratings_nnz" else _INT
+        fn.restype = _I64 if name in ("amf_ratings_nnz", "amf_normal_workspace_doubles") else _INT
     _lib = lib
     return lib
 

@@ -1,0 +1,1019 @@
+"""Host mirror of the reference's ``active_pmf`` module (python-pmf/active_pmf.py).
+
+Same names and conventions -- ``ActivePMF``, the criterion methods with their
+``do_normal_fit / spawn_processes / nice_name / chooser`` attributes, ``KEY_FUNCS``,
+``pick_query_point / _get_key_vals / get_key_evals``, ``full_test``, ``compare``, ``main`` --
+but the pool of candidates is evaluated in batched GPU launches instead of a Python map over
+``multiprocessing.Pool`` workers:
+
+* cheap criteria (pred, prob-ge-*, pred-variance): one scoring launch with a fused arg-best;
+* lookahead criteria (``_exp_with_rij``, active_pmf.py:635-704): every (candidate, value)
+  pair is an independent variational re-fit; the whole batch runs as ONE launch with one CTA
+  per problem (csrc/normal.cu), replacing deepcopy + host ``fit_normal`` per pair.
+
+There is no CPU path: every numeric method raises if libamf_b200 or the GPU is missing.
+"""
+from copy import deepcopy
+import functools
+import itertools
+import math
+import numbers
+import operator
+import random
+import warnings
+
+import numpy as np
+from scipy import stats
+import scipy.integrate
+
+from . import _native as N
+from . import normal as _normal
+from . import scoring as _scoring
+from .pmf_cy import ProbabilisticMatrixFactorization, parse_fit_type
+from .normal_exps_cy import (quadexpect, exp_a2bc, exp_dotprod_sq,  # noqa: F401 (API parity)
+                             normal_gradient)
+
+
+################################################################################
+### Helpers
+
+def project_psd(mat, min_eig=0):
+    '''
+    Symmetrise `mat` and clamp its spectrum from below at `min_eig`
+    (active_pmf.py:36-50); the eigendecomposition is the parallel Jacobi of csrc/normal.cu.
+    '''
+    return _normal.project_psd_device(np.asarray(mat, dtype=float), float(min_eig))
+
+
+class ActivePMFEvaluator(object):
+    '''Kept for API parity (active_pmf.py:54-67): evaluates one criterion for one pair.'''
+    def __init__(self, apmf, key):
+        self.apmf = apmf
+        self.key_name = key.__name__
+
+    def __call__(self, ij):
+        return getattr(self.apmf, self.key_name)(ij)
+
+
+def strictmap(*args, **kwargs):
+    return list(map(*args, **kwargs))
+
+
+# decorators carrying the criterion metadata the drivers read (active_pmf.py:73-96)
+def do_normal_fit(val):
+    def decorator(f):
+        f.do_normal_fit = val
+        return f
+    return decorator
+
+
+def spawn_processes(val):
+    def decorator(f):
+        f.spawn_processes = val
+        return f
+    return decorator
+
+
+def nice_name(name):
+    def decorator(f):
+        f.nice_name = name
+        return f
+    return decorator
+
+
+def minimize(f):
+    f.chooser = min
+    return f
+
+
+def maximize(f):
+    f.chooser = max
+    return f
+
+
+def _criterion(name, normal_fit, spawn, chooser):
+    def decorator(f):
+        do_normal_fit(normal_fit)(f)
+        spawn_processes(spawn)(f)
+        nice_name(name)(f)
+        (maximize if chooser is max else minimize)(f)
+        return f
+    return decorator
+
+
+################################################################################
+### Main code
+
+class ActivePMF(ProbabilisticMatrixFactorization):
+    verbose_lookahead = False   # the reference prints one line per lookahead (active_pmf.py:702-703)
+
+    def __init__(self, rating_tuples, latent_d=1, rating_values=None,
+                 discrete_expectations=False, refit_lookahead=False, knowable=None,
+                 fit_type=('batch',)):
+        super(ActivePMF, self).__init__(rating_tuples, latent_d=latent_d, subtract_mean=False,
+                                        knowable=knowable, fit_type=fit_type)
+        self.ratings = np.asarray(self.ratings, dtype=float)
+
+        if rating_values is not None:
+            rating_values = set(map(float, rating_values))
+            if not rating_values.issuperset(self.ratings[:, 2]):
+                raise ValueError("got ratings not in rating_values")
+
+        self.rating_values = rating_values
+        self.discrete_expectations = discrete_expectations
+        self.refit_lookahead = refit_lookahead
+
+        self.mean = None
+        self.cov = None
+
+        n, m, d = self.num_users, self.num_items, self.latent_d
+        self.approx_dim = k = (n + m) * d
+        self.num_params = k + k * (k + 1) / 2
+        # positions of U_ki / V_kj in the k-vector (active_pmf.py:141-142)
+        self.u = np.arange(0, n * d).reshape(n, d).T
+        self.v = np.arange(n * d, (n + m) * d).reshape(m, d).T
+
+        self.normal_learning_rate = 1e-4
+        self.min_eig = 1e-5
+
+    def __copy__(self):
+        res = ActivePMF(self.ratings, self.latent_d, self.rating_values, self.discrete_expectations)
+        res.__setstate__(self.__getstate__())
+        return res
+
+    def __deepcopy__(self, memodict):
+        res = ActivePMF(self.ratings, self.latent_d, self.rating_values, self.discrete_expectations)
+        res.__setstate__(deepcopy(self.__getstate__(), memodict))
+        return res
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        state['__dict__'] = {k: v for k, v in self.__dict__.items()
+                             if k not in ('_dev', '_users', '_items', '_ratings')}
+        return state
+
+    rating_values = property(lambda self: self._rating_values)
+    rating_bounds = property(lambda self: self._rating_bounds)
+
+    @rating_values.setter
+    def rating_values(self, vals):
+        if vals:
+            vals = tuple(sorted(vals))
+            self._rating_values = vals
+            edges = np.empty(len(vals) + 2)
+            edges[0], edges[-1] = -np.inf, np.inf
+            edges[1:-1] = vals
+            self._rating_bounds = (edges[1:] + edges[:-1]) / 2
+        else:
+            self._rating_values = None
+            self._rating_bounds = None
+
+    ############################################################################
+    ### Normal approximation
+
+    def _fit_params(self, max_steps=0):
+        return _normal.fit_params(self.num_users, self.num_items, self.latent_d, self.sigma_sq,
+                                  self.sigma_u_sq, self.sigma_v_sq,
+                                  learning_rate=self.normal_learning_rate, min_eig=self.min_eig,
+                                  max_steps=max_steps)
+
+    def initialize_approx(self):
+        '''(active_pmf.py:190-200): mean <- MAP factors, cov <- random PSD matrix'''
+        self.mean = np.hstack((self.users.reshape(-1), self.items.reshape(-1)))
+        s = np.random.normal(0, 2, (self.approx_dim, self.approx_dim))
+        self.cov = project_psd(s, min_eig=self.min_eig)
+
+    def kl_divergence(self, mean=None, cov=None):
+        '''KL(PMF model || approximation), up to an additive constant (active_pmf.py:202-240)'''
+        if mean is None:
+            mean = self.mean
+        if cov is None:
+            cov = self.cov
+        if mean is None or cov is None:
+            raise ValueError("run initialize_approx first")
+        batch = _normal.NormalBatch(self.ratings, self._fit_params(), mean[None], cov[None])
+        return float(batch.kl_divergence()[0])
+
+    def fit_normal(self):
+        for _kl in self.fit_normal_kls():
+            pass
+
+    def fit_normal_kls(self):
+        '''
+        Line-search descent on the KL (active_pmf.py:251-288).  The whole search runs in one
+        kernel launch; the KL after each accepted step is yielded afterwards.
+        '''
+        if self.mean is None or self.cov is None:
+            raise ValueError("run initialize_approx first")
+        batch = _normal.NormalBatch(self.ratings, self._fit_params(), self.mean[None], self.cov[None])
+        trace_len = 1 << 14
+        res = batch.fit(trace_len=trace_len)
+        steps = int(res['steps'][0])
+        if steps > 0:
+            self.mean = batch.means()[0]
+            self.cov = batch.covs()[0]
+        for kl in res['trace'][0][:min(steps, trace_len)]:
+            yield float(kl)
+
+    ############################################################################
+    ### Quantities under the current approximation
+
+    def _require_approx(self):
+        if self.mean is None or self.cov is None:
+            raise ValueError("run initialize_approx first")
+
+    def mean_meandiff(self):
+        p = np.hstack((self.users.reshape(-1), self.items.reshape(-1)))
+        return np.abs(self.mean - p).mean()
+
+    def _all_cells(self):
+        ii, jj = np.meshgrid(np.arange(self.num_users), np.arange(self.num_items), indexing='ij')
+        return ii.reshape(-1), jj.reshape(-1)
+
+    def _normal_scores(self, criterion, ii, jj, cutoff=0., maximize_=True):
+        self._require_approx()
+        return _scoring.score_normal(criterion, self.mean, self.cov, self.num_users,
+                                     self.num_items, self.latent_d, ii, jj, "f64",
+                                     cutoff=cutoff, maximize=maximize_)
+
+    def approx_pred_means_vars(self):
+        '''(active_pmf.py:301-322) mean and variance of every predicted cell'''
+        ii, jj = self._all_cells()
+        shape = (self.num_users, self.num_items)
+        mn, _ = self._normal_scores(N.CRIT_APPROX_MEAN, ii, jj)
+        var, _ = self._normal_scores(N.CRIT_PRED_VARIANCE, ii, jj)
+        return mn.reshape(shape), var.reshape(shape)
+
+    def approx_pred_mean_var(self, i, j):
+        '''(active_pmf.py:392-400)'''
+        mn, _ = self._normal_scores(N.CRIT_APPROX_MEAN, [i], [j])
+        var, _ = self._normal_scores(N.CRIT_PRED_VARIANCE, [i], [j])
+        return float(mn[0]), float(var[0])
+
+    def approx_pred_covs(self):
+        '''(active_pmf.py:324-390) covariance between all pairs of predicted cells'''
+        self._require_approx()
+        return _pred_covs(self.mean, self.cov, self.num_users, self.num_items, self.latent_d)
+
+    ############################################################################
+    ### Criteria -- each is usable on one pair; pools go through _get_key_vals
+
+    @_criterion("Random", False, False, max)
+    def random_weighting(self, ij):
+        return random.random()
+
+    @_criterion("Pred Mag", False, False, max)
+    def pred(self, ij):
+        '''The MAP estimate of R_ij (active_pmf.py:416-421).'''
+        return self._get_key_vals([ij], ActivePMF.pred, 1, None)[0]
+
+    def _prob_ge_cutoff(self, ij, cutoff):
+        '''norm.sf(cutoff, loc=mean, scale=var) -- the reference passes the variance as the
+        scale (active_pmf.py:432-439); reproduced.'''
+        vals, _ = self._normal_scores(N.CRIT_PROB_GE, [ij[0]], [ij[1]], cutoff=cutoff)
+        return float(vals[0])
+
+    @_criterion("Prob >= 3.5", True, False, max)
+    def prob_ge_3_5(self, ij):
+        return self._prob_ge_cutoff(ij, 3.5)
+
+    @_criterion("Prob >= .5", True, False, max)
+    def prob_ge_half(self, ij):
+        return self._prob_ge_cutoff(ij, .5)
+
+    def _onestep_ge_cutoff(self, ij, cutoff, use_map):
+        '''One-step lookahead utility (active_pmf.py:460-474); always discretised.'''
+        return self._lookahead([ij], ('onestep', cutoff), use_map, discretize=True)[0]
+
+    @_criterion("1 step >= 3.5 (MAP)", True, True, max)
+    def onestep_ge_3_5(self, ij):
+        return self._onestep_ge_cutoff(ij, 3.5, True)
+
+    @_criterion("1 step >= 3.5 (Approx)", True, True, max)
+    def onestep_ge_3_5_approx(self, ij):
+        return self._onestep_ge_cutoff(ij, 3.5, False)
+
+    @_criterion("1 step >= .5 (MAP)", True, True, max)
+    def onestep_ge_half(self, ij):
+        return self._onestep_ge_cutoff(ij, .5, True)
+
+    @_criterion("1 step >= .5 (Approx)", True, True, max)
+    def onestep_ge_half_approx(self, ij):
+        return self._onestep_ge_cutoff(ij, .5, False)
+
+    def _last_step_lookahead_helper(self, cutoff, v):
+        '''(active_pmf.py:492-500)'''
+        if not self.unrated:
+            raise ValueError("max() arg is an empty sequence")
+        pool = list(self.unrated)
+        ii, jj = zip(*pool)
+        _, (best, _idx) = self._normal_scores(N.CRIT_PROB_GE, ii, jj, cutoff=cutoff)
+        return int(v >= cutoff) + best
+
+    @_criterion("Pred Variance", True, False, max)
+    def pred_variance(self, ij):
+        '''Variance of the prediction for R_ij under the approximation (active_pmf.py:502-524).'''
+        vals, _ = self._normal_scores(N.CRIT_PRED_VARIANCE, [ij[0]], [ij[1]])
+        return float(vals[0])
+
+    def _approx_entropy(self):
+        '''(active_pmf.py:526-530) log det cov'''
+        sign, logdet = _slogdet(self.cov)
+        assert sign == 1
+        return logdet
+
+    @_criterion("E[U/V Entropy] (MAP)", True, True, min)
+    def exp_approx_entropy(self, ij):
+        return self._lookahead([ij], 'entropy', True)[0]
+
+    @_criterion("E[U/V Entropy] (Approx)", True, True, min)
+    def exp_approx_entropy_byapprox(self, ij):
+        return self._lookahead([ij], 'entropy', False)[0]
+
+    def _pred_entropy_bound(self):
+        '''(active_pmf.py:559-574)'''
+        s, logdet = _slogdet(self.approx_pred_covs())
+        if s != 1:
+            if s == -1 and logdet < -50:
+                return -1000
+            m = "prediction cov has det with sign {}, log {}"
+            raise ValueError(m.format(s, logdet))
+        return logdet
+
+    @_criterion("E[Pred Entropy Bound] (MAP)", True, True, min)
+    def exp_pred_entropy_bound(self, ij):
+        return self._lookahead([ij], 'pred_entropy_bound', True)[0]
+
+    @_criterion("E[Pred Entropy Bound] (Approx)", True, True, min)
+    def exp_pred_entropy_bound_byapprox(self, ij):
+        return self._lookahead([ij], 'pred_entropy_bound', False)[0]
+
+    def _total_variance(self):
+        return self.approx_pred_means_vars()[1].sum()
+
+    @_criterion("E[Pred Total Variance] (MAP)", True, True, min)
+    def exp_total_variance(self, ij):
+        return self._lookahead([ij], 'total_variance', True)[0]
+
+    @_criterion("E[Pred Total Variance] (Approx)", True, True, min)
+    def exp_total_variance_byapprox(self, ij):
+        return self._lookahead([ij], 'total_variance', False)[0]
+
+    # name of the quantity -> the reference's helper, for _exp_with_rij(fn=...) callers
+    _FN_NAMES = {'_approx_entropy': 'entropy', '_total_variance': 'total_variance',
+                 '_pred_entropy_bound': 'pred_entropy_bound'}
+
+    def _exp_with_rij(self, ij, fn, use_map=True, discretize=None, pass_v=False):
+        '''E[fn(apmf with R_ij)] (active_pmf.py:635-704) for one pair.'''
+        name = getattr(fn, '__name__', '')
+        if name in self._FN_NAMES:
+            what = self._FN_NAMES[name]
+        elif name.startswith('_1step_') or pass_v:
+            cutoff = getattr(fn, 'keywords', {}).get('cutoff')
+            what = ('onestep', cutoff)
+        else:
+            what = ('fn', fn, pass_v)   # arbitrary callable: evaluated on a host copy of each re-fit
+        return self._lookahead([ij], what, use_map, discretize=discretize, pass_v=pass_v)[0]
+
+    ############################################################################
+    ### Batched lookahead
+
+    def _rij_distribution(self, pool, use_map):
+        '''mean and variance of the distribution assumed for each R_ij (active_pmf.py:656-666)'''
+        ii, jj = zip(*pool)
+        if use_map:
+            mu, _ = _scoring.score_pred(self.users, self.items, ii, jj, "f64")
+            var = np.full(len(pool), float(self.sigma_sq))
+        else:
+            mu, _ = self._normal_scores(N.CRIT_APPROX_MEAN, ii, jj)
+            var, _ = self._normal_scores(N.CRIT_PRED_VARIANCE, ii, jj)
+        return mu, var
+
+    def _refits(self, pairs_vals, what):
+        '''fn(model + (i, j, v)) for a list of (i, j, v): one variational re-fit each.'''
+        self._require_approx()
+        B = len(pairs_vals)
+        if B == 0:
+            return np.zeros(0)
+        if self.refit_lookahead:
+            return np.array([self._refit_one_host_driven(i, j, v, what) for i, j, v in pairs_vals])
+        ei = np.array([p[0] for p in pairs_vals], dtype=np.int32)
+        ej = np.array([p[1] for p in pairs_vals], dtype=np.int32)
+        er = np.array([p[2] for p in pairs_vals], dtype=np.float64)
+        k = self.approx_dim
+        # bound the device workspace: (5 k^2 + 2k) doubles of scratch + k^2 + k of state each
+        per = 8 * (6 * k * k + 3 * k)
+        chunk = max(1, min(B, int(6e9 // per)))
+        out = np.empty(B)
+        for s in range(0, B, chunk):
+            e = min(B, s + chunk)
+            nb = e - s
+            batch = _normal.NormalBatch(self.ratings, self._fit_params(),
+                                        np.broadcast_to(self.mean, (nb, k)),
+                                        np.broadcast_to(self.cov, (nb, k, k)),
+                                        extra=(ei[s:e], ej[s:e], er[s:e]))
+            res = batch.fit(want_entropy=(what == 'entropy'),
+                            want_totvar=(what == 'total_variance'))
+            if what == 'entropy':
+                out[s:e] = res['entropy']
+            elif what == 'total_variance':
+                out[s:e] = res['total_variance']
+            else:
+                means, covs = batch.means(), batch.covs()
+                for b in range(nb):
+                    out[s + b] = self._criterion_on(means[b], covs[b], what,
+                                                    (int(ei[s + b]), int(ej[s + b])), er[s + b])
+        return out
+
+    def _criterion_on(self, mean, cov, what, ij, v):
+        '''criteria that need more than the fit kernel's own outputs'''
+        n, m, d = self.num_users, self.num_items, self.latent_d
+        if what == 'pred_entropy_bound':
+            s, logdet = _slogdet(_pred_covs(mean, cov, n, m, d))
+            if s != 1:
+                if s == -1 and logdet < -50:
+                    return -1000
+                raise ValueError("prediction cov has det with sign {}, log {}".format(s, logdet))
+            return logdet
+        if isinstance(what, tuple) and what[0] == 'fn':
+            apmf = deepcopy(self)
+            apmf.add_rating(ij[0], ij[1], v)
+            apmf.mean, apmf.cov = mean, cov
+            return what[1](apmf, v=v) if what[2] else what[1](apmf)
+        if isinstance(what, tuple) and what[0] == 'onestep':
+            cutoff = what[1]
+            pool = [c for c in self.unrated if c != ij]
+            if not pool:
+                raise ValueError("max() arg is an empty sequence")
+            ii, jj = zip(*pool)
+            _, (best, _i) = _scoring.score_normal(N.CRIT_PROB_GE, mean, cov, n, m, d, ii, jj,
+                                                  "f64", cutoff=cutoff)
+            return int(v >= cutoff) + best
+        raise ValueError("unknown lookahead quantity %r" % (what,))
+
+    def _refit_one_host_driven(self, i, j, v, what):
+        '''refit_lookahead=True (active_pmf.py:669-676): MAP refit + fresh random covariance per
+        problem, consuming the global RNG in the reference's order.'''
+        apmf = deepcopy(self)
+        apmf.add_rating(i, j, v)
+        apmf.do_fit()
+        apmf.initialize_approx()
+        apmf.fit_normal()
+        if what == 'entropy':
+            return apmf._approx_entropy()
+        if what == 'total_variance':
+            return apmf._total_variance()
+        if what == 'pred_entropy_bound':
+            return apmf._pred_entropy_bound()
+        if what[0] == 'fn':
+            return what[1](apmf, v=v) if what[2] else what[1](apmf)
+        return apmf._last_step_lookahead_helper(what[1], v)
+
+    def _lookahead(self, pool, what, use_map, discretize=None, pass_v=False):
+        '''_exp_with_rij for every pair of `pool`.'''
+        pool = [(int(i), int(j)) for i, j in pool]
+        if discretize is None:
+            discretize = self.discrete_expectations
+        mu, var = self._rij_distribution(pool, use_map)
+        std = np.sqrt(var)
+        points = self.rating_values
+        if discretize and points:
+            vals = np.array(points, dtype=float)
+            trip = [(i, j, v) for (i, j) in pool for v in vals]
+            evals = self._refits(trip, what).reshape(len(pool), len(vals))
+            if discretize == 'simps':
+                pdfs = stats.norm.pdf(vals[None, :], loc=mu[:, None], scale=std[:, None])
+                est = scipy.integrate.simpson(evals * pdfs, x=vals, axis=1)
+                how = "simps'ed"
+            else:
+                cdfs = stats.norm.cdf(self.rating_bounds[None, :], loc=mu[:, None],
+                                      scale=std[:, None])
+                est = (evals * np.diff(cdfs, axis=1)).sum(1)
+                how = "summed"
+        else:
+            if discretize and points is None:
+                warnings.warn("ActivePMF has no rating_values; doing integral")
+            est = np.empty(len(pool))
+            for t, (i, j) in enumerate(pool):
+                left, right = mu[t] - 2 * std[t], mu[t] + 2 * std[t]
+                est[t] = stats.norm.expect(
+                    lambda v: float(self._refits([(i, j, float(v))], what)[0]),
+                    loc=mu[t], scale=std[t], lb=left, ub=right, epsrel=.02)
+            how = "integrated"
+        if self.verbose_lookahead:
+            name = what if isinstance(what, str) else getattr(what, '__name__', str(what))
+            for (i, j), e in zip(pool, est):
+                print("\t{:>20}({},{}) {}: {: 10.2f}".format(name, i, j, how, e))
+        return [float(e) for e in est]
+
+    ############################################################################
+    ### Picking a query point
+
+    def pick_query_point(self, pool=None, key=None, procs=None, worker_pool=None):
+        '''(active_pmf.py:709-737); procs / worker_pool are accepted and ignored.'''
+        if pool is None:
+            pool = self.unrated
+        if key is None:
+            key = ActivePMF.pred_variance
+        chooser = getattr(key, 'chooser', max)
+        if len(pool) == 0:
+            raise ValueError("can't pick a query point from an empty pool")
+        elif len(pool) == 1:
+            return next(iter(pool))
+        pool = list(pool)
+        vals = self._get_key_vals(pool, key, procs, worker_pool)
+        return chooser(zip(pool, vals), key=operator.itemgetter(1))[0]
+
+    def _get_key_vals(self, pool, key, procs=None, worker_pool=None):
+        '''Criterion value for every pair of `pool`, aligned with its iteration order
+        (active_pmf.py:739-770) -- evaluated in batched GPU launches.'''
+        pool = list(pool)
+        if not pool:
+            return []
+        name = getattr(key, '__name__', None)
+        if name == 'random_weighting':
+            return [random.random() for _ in pool]
+        ii, jj = zip(*pool)
+        if name == 'pred':
+            vals, _ = _scoring.score_pred(self.users, self.items, ii, jj, self.dtype_name)
+            return vals.tolist()
+        if name == 'pred_variance':
+            return self._normal_scores(N.CRIT_PRED_VARIANCE, ii, jj)[0].tolist()
+        if name == 'prob_ge_3_5':
+            return self._normal_scores(N.CRIT_PROB_GE, ii, jj, cutoff=3.5)[0].tolist()
+        if name == 'prob_ge_half':
+            return self._normal_scores(N.CRIT_PROB_GE, ii, jj, cutoff=.5)[0].tolist()
+        lookaheads = {
+            'exp_approx_entropy': ('entropy', True),
+            'exp_approx_entropy_byapprox': ('entropy', False),
+            'exp_total_variance': ('total_variance', True),
+            'exp_total_variance_byapprox': ('total_variance', False),
+            'exp_pred_entropy_bound': ('pred_entropy_bound', True),
+            'exp_pred_entropy_bound_byapprox': ('pred_entropy_bound', False),
+        }
+        if name in lookaheads:
+            what, use_map = lookaheads[name]
+            return self._lookahead(pool, what, use_map)
+        onesteps = {'onestep_ge_3_5': (3.5, True), 'onestep_ge_3_5_approx': (3.5, False),
+                    'onestep_ge_half': (.5, True), 'onestep_ge_half_approx': (.5, False)}
+        if name in onesteps:
+            cutoff, use_map = onesteps[name]
+            return self._lookahead(pool, ('onestep', cutoff), use_map, discretize=True)
+        # unknown criterion: evaluate it pair by pair like the reference's serial path
+        return [key(self, ij) for ij in pool]
+
+    def get_key_evals(self, pool=None, key=None, procs=None, worker_pool=None):
+        '''(active_pmf.py:772-787) NaN-filled (N, M) matrix of criterion values'''
+        if pool is None:
+            pool = self.unrated
+        if key is None:
+            key = ActivePMF.pred_variance
+        pool = list(pool)
+        evals = np.empty((self.num_users, self.num_items))
+        evals.fill(np.nan)
+        if pool:
+            evals[tuple(zip(*pool))] = self._get_key_vals(pool, key, procs, worker_pool)
+        return evals
+
+
+def _slogdet(mat):
+    '''np.linalg.slogdet semantics, computed on the device (cuSOLVER LU through torch)'''
+    import torch
+    from . import device as D
+    s, ld = torch.linalg.slogdet(torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float64)).to(D.device()))
+    return float(s.item()), float(ld.item())
+
+
+def _pred_covs(mean, cov, n, m, d):
+    '''(active_pmf.py:324-390) as batched tensor algebra on the device.
+
+    With X = [vec U; vec V] ~ N(mean, cov) every entry is a sum of 4th moments minus a product of
+    2nd moments; by Isserlis  Cov(UiVj, UaVb) = sum_kl  m m C + ... , evaluated here with einsum
+    over the (n,d)/(m,d) blocks of cov.  The diagonal uses the same closed form as pred_variance.
+    '''
+    import torch
+    from . import device as D
+    dev = D.device()
+    mean_t = torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float64)).to(dev)
+    cov_t = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).to(dev)
+    nu = n * d
+    mu = mean_t[:nu].reshape(n, d)
+    mv = mean_t[nu:].reshape(m, d)
+    Suu = cov_t[:nu, :nu].reshape(n, d, n, d)      # [i,k,a,l] = Cov(U_ki, U_la)
+    Svv = cov_t[nu:, nu:].reshape(m, d, m, d)      # [j,k,b,l]
+    Suv = cov_t[:nu, nu:].reshape(n, d, m, d)      # [i,k,b,l] = Cov(U_ki, V_lb)
+    # Cov(sum_k Uki Vkj, sum_l Ula Vlb) over independent-looking index pairs, Isserlis:
+    # E[x1 x2 x3 x4] - E[x1 x2]E[x3 x4] = m1 m3 C24 + m1 m4 C23 + m2 m3 C14 + m2 m4 C13
+    #                                      + C13 C24 + C14 C23     with x1=Uki x2=Vkj x3=Ula x4=Vlb
+    e = torch.einsum
+    t1 = e('ik,al,jkbl->ijab', mu, mu, Svv)                   # m1 m3 C24
+    t2 = e('ik,bl,aljk->ijab', mu, mv, Suv)                   # m1 m4 C23 = Cov(Vkj, Ula)
+    t3 = e('jk,al,ikbl->ijab', mv, mu, Suv)                   # m2 m3 C14 = Cov(Uki, Vlb)
+    t4 = e('jk,bl,ikal->ijab', mv, mv, Suu)                   # m2 m4 C13
+    t5 = e('ikal,jkbl->ijab', Suu, Svv)                       # C13 C24
+    t6 = e('ikbl,aljk->ijab', Suv, Suv)                       # C14 C23
+    out = (t1 + t2 + t3 + t4 + t5 + t6).reshape(n * m, n * m)
+    return out.cpu().numpy()
+
+
+################################################################################
+### Drivers (active_pmf.py:796-1257)
+
+def full_test(apmf, real, picker_key=ActivePMF.pred_variance, fit_normal=True,
+              fit_sigmas=False, processes=None):
+    '''Serial active-learning loop (active_pmf.py:796-850).'''
+    print("Training PMF")
+    if fit_sigmas:
+        apmf.fit_with_sigmas()
+    else:
+        apmf.do_fit()
+    apmf.initialize_approx()
+    if fit_normal:
+        print("Fitting normal")
+        apmf.fit_normal()
+        print("Mean diff of means: %g; mean cov %g" % (apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
+
+    total = apmf.num_users * apmf.num_items
+    rmse = apmf.rmse(real)
+    print("RMSE: {:.5}".format(rmse))
+    yield len(apmf.rated), rmse, None, None
+
+    while apmf.unrated:
+        print()
+        print("Picking a query point...")
+        if len(apmf.unrated) == 1:
+            i, j = next(iter(apmf.unrated))
+            vals = None
+        else:
+            pool = list(apmf.unrated)
+            vals = apmf._get_key_vals(pool, picker_key, processes, None)
+            i, j = picker_key.chooser(zip(pool, vals), key=operator.itemgetter(1))[0]
+
+        apmf.add_rating(i, j, real[i, j])
+        print("Queried (%d, %d); %d/%d known" % (i, j, len(apmf.rated), total))
+
+        print("Training PMF")
+        for _ll in apmf.fit_lls():
+            pass
+        if fit_normal:
+            print("Fitting normal")
+            for kl in apmf.fit_normal_kls():
+                assert kl > -1e5
+            print("Mean diff of means: %g; mean cov %g" % (apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
+
+        rmse = apmf.rmse(real)
+        print("RMSE: {:.5}".format(rmse))
+        yield len(apmf.rated), rmse, (i, j), vals
+
+
+def _in_between_work(apmf, i, j, realval, total, fit_normal, fit_sigmas, name):
+    '''(active_pmf.py:853-868)'''
+    apmf.add_rating(i, j, realval)
+    print("{:<40} Queried ({}, {}); {}/{} known".format(name, i, j, len(apmf.rated), total))
+    if fit_sigmas:
+        apmf.fit_with_sigmas()
+    else:
+        apmf.do_fit()
+    if fit_normal:
+        if apmf.refit_lookahead:
+            apmf.initialize_approx()
+        apmf.fit_normal()
+    return apmf
+
+
+class _InlinePool(object):
+    '''Stand-in for multiprocessing.Pool in the threaded driver: the GPU does the fan-out, so
+    work submitted to the "pool" runs in the calling thread.'''
+    def apply(self, fn, args=(), kwds=None):
+        return fn(*args, **(kwds or {}))
+
+    def map(self, fn, it):
+        return [fn(x) for x in it]
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+def _full_test_threaded(apmf, real, picker_key, fit_normal, fit_sigmas, worker_pool):
+    '''(active_pmf.py:871-898)'''
+    total = real.size
+    name = picker_key.nice_name
+    rmse = apmf.rmse(real)
+    print("{:<40} Initial RMSE: {:.5}".format(name, rmse))
+    yield len(apmf.rated), rmse, None, None
+
+    while apmf.unrated:
+        n = len(apmf.rated) + 1
+        print("{:<40} Picking query point {}...".format(name, n))
+        if len(apmf.unrated) == 1:
+            vals = np.empty((apmf.num_users, apmf.num_items))
+            vals.fill(np.nan)
+            i, j = next(iter(apmf.unrated))
+        else:
+            vals = apmf.get_key_evals(key=picker_key, worker_pool=worker_pool)
+            i, j = picker_key.chooser(apmf.unrated, key=vals.__getitem__)
+
+        apmf = worker_pool.apply(_in_between_work,
+                                 (apmf, i, j, real[i, j], total, fit_normal, fit_sigmas, name))
+        rmse = apmf.rmse(real)
+        print("{:<40} RMSE {}: {:.5}".format(picker_key.nice_name, n, rmse))
+        yield len(apmf.rated), rmse, (i, j), vals
+
+
+KEY_FUNCS = {
+    "random": ActivePMF.random_weighting,
+    "pred-variance": ActivePMF.pred_variance,
+
+    "total-variance": ActivePMF.exp_total_variance,
+    "total-variance-approx": ActivePMF.exp_total_variance_byapprox,
+
+    "uv-entropy": ActivePMF.exp_approx_entropy,
+    "uv-entropy-approx": ActivePMF.exp_approx_entropy_byapprox,
+
+    "pred-entropy-bound": ActivePMF.exp_pred_entropy_bound,
+    "pred-entropy-bound-approx": ActivePMF.exp_pred_entropy_bound_byapprox,
+
+    "pred": ActivePMF.pred,
+    "prob-ge-3.5": ActivePMF.prob_ge_3_5,
+    "prob-ge-.5": ActivePMF.prob_ge_half,
+
+    "1step-ge-3.5": ActivePMF.onestep_ge_3_5,
+    "1step-ge-3.5-approx": ActivePMF.onestep_ge_3_5_approx,
+
+    "1step-ge-.5": ActivePMF.onestep_ge_half,
+    "1step-ge-.5-approx": ActivePMF.onestep_ge_half_approx,
+}
+
+
+def make_fake_data(noise=.25, num_users=10, num_items=10, mask_type=0, data_type='float',
+                   rank=5, u_mean=0, u_std=2, v_mean=0, v_std=2):
+    '''(active_pmf.py:926-960) same RNG draws in the same order'''
+    u = np.random.normal(u_mean, u_std, (num_users, rank))
+    v = np.random.normal(v_mean, v_std, (num_items, rank))
+    real = np.dot(u, v.T)
+    if noise:
+        real += np.random.normal(0, noise, (num_users, num_items))
+
+    if data_type == 'float':
+        vals = None
+    elif data_type == 'int':
+        real = np.round(real).astype(int)
+        vals = None
+    elif data_type == 'int-bounds':
+        real = np.round(real).astype(int)
+        lo, hi = real.min(), real.max()
+        vals = range(int(np.floor(lo * 1.2 if lo < 0 else lo * .8)),
+                     int(np.ceil(hi * 1.2 if hi > 0 else hi * .8)))
+    elif data_type == 'binary':
+        real = (real > .5).astype(int)
+        vals = {0, 1}
+    elif isinstance(data_type, numbers.Integral):
+        real = np.minimum(np.maximum(np.round(real), 0), data_type).astype(int)
+        vals = range(data_type + 1)
+    else:
+        raise ValueError("Don't know how to interpret data_type '{}'".format(data_type))
+
+    ratings = get_ratings(real, mask_type)
+    return real, ratings, vals
+
+
+def get_ratings(real, mask_type=0):
+    '''(active_pmf.py:963-1010)'''
+    num_users, num_items = real.shape
+    if isinstance(mask_type, numbers.Real):
+        mask = np.random.binomial(1, mask_type, real.shape)
+    elif mask_type in {'diag', 'diagonal', 'diag-plus', 'diag-block'}:
+        mask = np.zeros_like(real)
+        np.fill_diagonal(mask, 1)
+        if mask_type == 'diag-plus':
+            if num_users != num_items:
+                warnings.warn("can't do diag-plus for non-square; doing diag")
+            else:
+                n = num_users
+                mask[-1, 1] = 1
+                mask[range(1, n - 1), range(2, n)] = 1
+        elif mask_type == 'diag-block':
+            if num_users != num_items:
+                warnings.warn("can't do diag-block for non-square; doing diag")
+            else:
+                mask[:num_users // 2, :num_items // 2] = 1
+    else:
+        raise ValueError("Don't know how to interpret mask_type '{}'".format(mask_type))
+
+    for zero_col in np.logical_not(mask.sum(axis=0)).nonzero()[0]:
+        mask[random.randrange(num_users), zero_col] = 1
+    for zero_row in np.logical_not(mask.sum(axis=1)).nonzero()[0]:
+        mask[zero_row, random.randrange(num_items)] = 1
+    assert np.all(mask.sum(axis=0) > 0)
+    assert np.all(mask.sum(axis=1) > 0)
+
+    ratings = np.zeros((int(mask.sum()), 3))
+    for idx, (i, j) in enumerate(np.transpose(mask.nonzero())):
+        ratings[idx] = [i, j, real[i, j]]
+    return ratings
+
+
+def compare(key_names, latent_d=5, processes=None, do_threading=True, steps=None,
+            discrete_exp=False, refit_lookahead=False, fit_sigmas=False,
+            real_ratings_vals=None, apmf=None, knowable=None,
+            sig_u_mean=0, sig_u_var=-1, sig_v_mean=0, sig_v_var=-1,
+            fit_type=('batch',), **kwargs):
+    '''(active_pmf.py:1013-1092).  `processes` is accepted for compatibility; candidate
+    fan-out happens on the GPU, so no worker processes are forked.'''
+    from threading import Thread, Lock
+
+    if real_ratings_vals is None:
+        real, ratings, rating_vals = make_fake_data(**kwargs)
+    else:
+        real, ratings, rating_vals = real_ratings_vals
+        if apmf:
+            assert (apmf.num_users, apmf.num_items) == real.shape
+            assert np.all(apmf.ratings == ratings)
+            assert set(apmf.rating_values) == set(rating_vals)
+            apmf.discrete_expectations = discrete_exp
+
+    if apmf is None:
+        apmf = ActivePMF(ratings, latent_d=latent_d, rating_values=rating_vals,
+                         discrete_expectations=discrete_exp, refit_lookahead=refit_lookahead,
+                         knowable=knowable, fit_type=fit_type)
+        apmf.sig_u_mean = sig_u_mean
+        apmf.sig_u_var = sig_u_var
+        apmf.sig_v_mean = sig_v_mean
+        apmf.sig_v_var = sig_v_var
+
+        print("Doing initial fit")
+        if fit_sigmas:
+            apmf.fit_with_sigmas()
+        else:
+            apmf.do_fit()
+
+        if any(KEY_FUNCS[name].do_normal_fit for name in key_names):
+            apmf.initialize_approx()
+            print("Initial approximation fit")
+            apmf.fit_normal()
+            print("Mean diff of means: {}; mean cov {}\n".format(
+                apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
+
+    results = {
+        '_real': real,
+        '_ratings': ratings,
+        '_rating_vals': rating_vals,
+        '_initial_apmf': deepcopy(apmf),
+    }
+
+    if do_threading:
+        worker_pool = _InlinePool()
+        worker_pool.access_lock = Lock()
+
+        def eval_key(key_name):
+            key = KEY_FUNCS[key_name]
+            res = _full_test_threaded(deepcopy(apmf), real, key, key.do_normal_fit,
+                                      fit_sigmas, worker_pool)
+            results[key_name] = list(itertools.islice(res, steps))
+
+        threads = [Thread(name=key_name, target=eval_key, args=(key_name,))
+                   for key_name in key_names]
+        for thread in threads:
+            thread.start()
+        for thread in threads:
+            thread.join()
+    else:
+        for key_name in key_names:
+            key = KEY_FUNCS[key_name]
+            res = full_test(deepcopy(apmf), real, key, key.do_normal_fit, fit_sigmas, processes)
+            results[key_name] = list(itertools.islice(res, steps))
+
+    return results
+
+
+def add_bool_opt(parser, name, default=False):
+    parser.add_argument('--' + name, action='store_true', default=default)
+    parser.add_argument('--no-' + name, action='store_false', dest=name.replace('-', '_'))
+
+
+def main(argv=None):
+    '''Same command line as the reference (active_pmf.py:1100-1257).'''
+    import argparse
+    import os
+    import pickle
+    import sys
+
+    key_names = set(KEY_FUNCS.keys())
+    types = {'float', 'int', 'int-bounds', 'binary'}
+    parser = argparse.ArgumentParser()
+
+    model = parser.add_argument_group("Model Options")
+    model.add_argument('--latent-d', '-D', type=int, default=5)
+    model.add_argument('--discrete-integration', nargs='?', const=True, default=False)
+    model.add_argument('--continuous-integration', action='store_false', dest='discrete_integration')
+    add_bool_opt(model, 'fit-sigmas', default=False)
+    add_bool_opt(model, 'refit-lookahead', default=False)
+    model.add_argument('--fit', default='batch')
+    model.add_argument('--sig-u-mean', type=float, default=0)
+    model.add_argument('--sig-u-var', type=float, default=-1)
+    model.add_argument('--sig-v-mean', type=float, default=0)
+    model.add_argument('--sig-v-var', type=float, default=-1)
+    model.add_argument('keys', nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names))))
+
+    problem_def = parser.add_argument_group("Problem Definiton")
+    problem_def.add_argument('--load-data', default=None, metavar='FILE')
+    add_bool_opt(problem_def, 'load-model', default=False)
+    problem_def.add_argument('--gen-rank', '-R', type=int, default=5)
+    problem_def.add_argument('--type', default='float',
+                             help="An integer (meaning values are from 0 to that integer) or "
+                                  "one of {}".format(', '.join(sorted(types))))
+    problem_def.add_argument('--u-mean', type=float, default=0)
+    problem_def.add_argument('--u-std', type=float, default=2)
+    problem_def.add_argument('--v-mean', type=float, default=0)
+    problem_def.add_argument('--v-std', type=float, default=2)
+    problem_def.add_argument('--noise', '-n', type=float, default=.25)
+    problem_def.add_argument('--num-users', '-N', type=int, default=10)
+    problem_def.add_argument('--num-items', '-M', type=int, default=10)
+    problem_def.add_argument('--mask', '-m', default=0)
+
+    running = parser.add_argument_group("Running")
+    running.add_argument('--processes', '-P', type=int, default=None)
+    add_bool_opt(running, 'threading', True)
+    running.add_argument('--steps', '-s', type=int, default=None)
+
+    results = parser.add_argument_group("Results")
+    results.add_argument('--save-results', nargs='?', default=None, const=True, metavar='FILE')
+    results.add_argument('--no-save-results', action='store_false', dest='save_results')
+    results.add_argument('--note', action='append',
+                         help="Doesn't do anything, just there to save any notes you'd like "
+                              "in the results file.")
+
+    args = parser.parse_args(argv)
+
+    try:
+        args.mask = float(args.mask)
+    except ValueError:
+        pass
+    try:
+        args.type = int(args.type)
+    except ValueError:
+        if args.type not in types:
+            raise ValueError("--type must be integer or one of {}".format(', '.join(sorted(types))))
+
+    for k in args.keys:
+        if k not in key_names:
+            sys.stderr.write("Invalid key name %s; options are %s.\n" % (
+                k, ', '.join(sorted(key_names))))
+            sys.exit(1)
+    if not args.keys:
+        args.keys = sorted(key_names)
+
+    if args.save_results is True:
+        args.save_results = 'results.pkl'
+    elif args.save_results:
+        dirname = os.path.dirname(args.save_results)
+        if dirname and not os.path.exists(dirname):
+            os.makedirs(dirname)
+
+    real_ratings_vals = None
+    apmf = None
+    knowable = None
+    if args.load_data:
+        with open(args.load_data, 'rb') as f:
+            data = np.load(f, allow_pickle=True)
+            if isinstance(data, np.ndarray):
+                data = {'_real': data}
+            real = data['_real']
+            real_ratings_vals = (
+                real,
+                data['_ratings'] if '_ratings' in data else get_ratings(real, args.mask),
+                data['_rating_vals'] if '_rating_vals' in data else None,
+            )
+            if args.load_model:
+                apmf = data['_initial_apmf']
+        knowable = np.isfinite(real)
+        knowable[real == 0] = 0
+        knowable = zip(*knowable.nonzero())
+
+    results = compare(args.keys,
+                      num_users=args.num_users, num_items=args.num_items,
+                      real_ratings_vals=real_ratings_vals, apmf=apmf, knowable=knowable,
+                      u_mean=args.u_mean, u_std=args.u_std, v_mean=args.v_mean, v_std=args.v_std,
+                      noise=args.noise, mask_type=args.mask,
+                      rank=args.gen_rank, latent_d=args.latent_d,
+                      discrete_exp=args.discrete_integration,
+                      refit_lookahead=args.refit_lookahead, fit_sigmas=args.fit_sigmas,
+                      sig_u_mean=args.sig_u_mean, sig_u_var=args.sig_u_var,
+                      sig_v_mean=args.sig_v_mean, sig_v_var=args.sig_v_var,
+                      data_type=args.type, steps=args.steps,
+                      fit_type=parse_fit_type(args.fit),
+                      processes=args.processes, do_threading=args.threading)
+
+    if args.save_results:
+        print("saving results in '{}'".format(args.save_results))
+        results['_args'] = args
+        with open(args.save_results, 'wb') as f:
+            pickle.dump(results, f)
+    return results
+
+
+if __name__ == '__main__':
+    main()

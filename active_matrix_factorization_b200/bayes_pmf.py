@@ -1,0 +1,550 @@
+"""Host mirror of the reference's ``bayes_pmf`` module (python-pmf/bayes_pmf.py + .pxd):
+Bayesian PMF by Gibbs sampling (Salakhutdinov & Mnih), with the active-learning criteria
+computed from posterior samples.
+
+The two O(data) pieces run in libamf_b200:
+  * every row/column conditional of a half-sweep (``sample_feature``, bayes_pmf.py:189-216) in
+    one launch, one CTA per row (csrc/gibbs.cu);
+  * predict / pred_variance / prob_ge_cutoff over S samples at the requested cells as one
+    streaming pass (no S dense N x M matrices).
+Random numbers are drawn on the host from numpy's global stream in the reference's order, so
+a seeded chain reproduces the reference's samples.  No CPU path exists for the numerics.
+"""
+from collections import namedtuple
+from copy import deepcopy
+from itertools import islice, repeat
+import ctypes as C
+import random
+from threading import Thread
+import warnings
+
+import numpy as np
+from scipy import stats, integrate
+import torch
+
+from . import _native as N
+from . import device as D
+from .pmf_cy import ProbabilisticMatrixFactorization, rmse, parse_fit_type  # noqa: F401
+
+
+################################################################################
+### Utilities
+
+def sample_wishart(sigma, dof):
+    '''
+    Draw from Wishart(sigma, dof) (bayes_pmf.py:41-59): d x d host algebra on draws from the
+    global numpy stream (direct scheme if dof <= 81+n and integral, else Bartlett).
+    '''
+    n = sigma.shape[0]
+    chol = np.linalg.cholesky(sigma)
+    if dof <= 81 + n and dof == round(dof):
+        X = np.dot(chol, np.random.normal(size=(n, int(dof))))
+    else:
+        A = np.diag(np.sqrt(np.random.chisquare(dof - np.arange(0, n), size=n)))
+        A[np.tri(n, k=-1, dtype=bool)] = np.random.normal(size=(n * (n - 1) // 2))
+        X = np.dot(chol, A)
+    return np.dot(X, X.T)
+
+
+def iter_mean(iterable):
+    i = iter(iterable)
+    total = next(i)
+    count = -1
+    for count, x in enumerate(i):
+        total += x
+    return total / (count + 2)
+
+
+################################################################################
+
+class BayesianPMF(ProbabilisticMatrixFactorization):
+    def __init__(self, rating_tuples, latent_d=5, subtract_mean=True, rating_values=None,
+                 discrete_expectations=True, num_integration_pts=50, knowable=None,
+                 fit_type=('batch',)):
+        super(BayesianPMF, self).__init__(rating_tuples, latent_d=latent_d,
+                                          subtract_mean=subtract_mean, knowable=knowable,
+                                          fit_type=fit_type)
+        if rating_values is not None:
+            rating_values = set(map(float, rating_values))
+            if not rating_values.issuperset(self.ratings[:, 2]):
+                raise ValueError("got ratings not in rating_values")
+        self.rating_values = rating_values
+        self.discrete_expectations = discrete_expectations
+        self.num_integration_pts = num_integration_pts
+
+        self.beta = 2  # observation noise precision
+
+        # (wishart scale, b0, degrees of freedom, mu0)   (bayes_pmf.py:97-109)
+        self.u_hyperparams = (np.eye(latent_d), 2, latent_d, np.zeros(latent_d))
+        self.v_hyperparams = (np.eye(latent_d), 2, latent_d, np.zeros(latent_d))
+
+    def __copy__(self):
+        res = BayesianPMF(self.ratings, self.latent_d)
+        res.__setstate__(self.__getstate__())
+        return res
+
+    def __deepcopy__(self, memodict):
+        res = BayesianPMF(self.ratings, self.latent_d)
+        res.__setstate__(deepcopy(self.__getstate__(), memodict))
+        return res
+
+    def __getstate__(self):
+        # the five extra keys of the compiled reference (bayes_pmf.py:123-130)
+        state = super(BayesianPMF, self).__getstate__()
+        state['discrete_expectations'] = self.discrete_expectations
+        state['rating_values'] = self._rating_values
+        state['beta'] = self.beta
+        state['u_hyperparams'] = self.u_hyperparams
+        state['v_hyperparams'] = self.v_hyperparams
+        state['num_integration_pts'] = self.num_integration_pts
+        return state
+
+    def _set_rating_values(self, vals):
+        if vals:
+            vals = tuple(sorted(vals))
+            self._rating_values = vals
+            edges = np.empty(len(vals) + 2)
+            edges[0], edges[-1] = -np.inf, np.inf
+            edges[1:-1] = vals
+            self._rating_bounds = (edges[1:] + edges[:-1]) / 2
+        else:
+            self._rating_values = None
+            self._rating_bounds = None
+
+    rating_values = property(lambda self: self._rating_values, _set_rating_values)
+    rating_bounds = property(lambda self: self._rating_bounds)
+
+    ############################################################################
+    ### Gibbs sampler
+
+    def sample_hyperparam(self, feats, do_users):
+        '''
+        Normal-Wishart posterior draw of (mu, alpha) given a factor matrix
+        (bayes_pmf.py:157-186).  d x d host algebra; the reference's scalar inner product at
+        :176 (np.dot of two 1-D vectors) is kept.
+        '''
+        wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
+        n = feats.shape[0]
+        x_bar = np.mean(feats, axis=0).T
+        s_bar = np.cov(feats, rowvar=0)
+        diff = mu0 - x_bar
+        wi_post = np.linalg.inv(np.linalg.inv(wi) + n * s_bar
+                                + (b0 * n) / (b0 + n) * np.dot(diff, diff.T))
+        wi_post /= 2
+        wi_post = wi_post + wi_post.T
+        alpha = sample_wishart(wi_post, df + n)
+        mu_temp = (b0 * mu0 + n * x_bar) / (b0 + n)
+        lam = np.linalg.cholesky(np.linalg.inv((b0 + n) * alpha))
+        mu = np.dot(lam, np.random.normal(0, 1, self.latent_d)) + mu_temp
+        return mu, alpha
+
+    def _mean_offset(self):
+        return self.mean_rating if self.subtract_mean else 0.
+
+    def _half_sweep(self, rat, side, other_t, mu, alpha, z):
+        '''all conditionals of one side in one launch; returns the new (rows, d) device tensor'''
+        lib = N.require_device()
+        name = rat.name
+        dt = D.np_dtype(name)
+        rows = rat.n_users if side == 0 else rat.n_items
+        out = torch.empty((rows, self.latent_d), dtype=D.torch_dtype(name), device=other_t.device)
+        alpha_t = D.to_device(np.atleast_2d(alpha), dt)
+        mu_t = D.to_device(np.atleast_1d(mu), dt)
+        z_t = D.to_device(z, dt)
+        N.check(lib.amf_gibbs_half_sweep(rat.handle, side, D.code(name), self.latent_d,
+                                         D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
+                                         float(self.beta), float(self._mean_offset()),
+                                         D.ptr(z_t), D.ptr(out), D.stream_ptr()))
+        return out
+
+    def _check_gibbs(self, rat):
+        failed = C.c_int(0)
+        N.check(N.load().amf_gibbs_status(rat.handle, C.byref(failed), D.stream_ptr()))
+        if failed.value:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+
+    def sample_feature(self, n, is_user, mu, alpha, oth_feats, rated_indices, ratings):
+        '''
+        One row's conditional draw (bayes_pmf.py:189-216): z ~ N(0, I) from the global stream,
+        then chol(inv(alpha + beta F'F)) z + mean on the device.
+        '''
+        name = self.dtype_name
+        rated_indices = np.asarray(rated_indices, dtype=np.int32)
+        rat = D.Ratings(1, oth_feats.shape[0], np.zeros(len(rated_indices), np.int32),
+                        rated_indices, np.asarray(ratings, dtype=float), name)
+        other_t = D.to_device(oth_feats, D.np_dtype(name))
+        z = np.random.normal(0, 1, self.latent_d)
+        out = self._half_sweep(rat, 0, other_t, mu, alpha, z[None])
+        self._check_gibbs(rat)
+        res = out[0].to(torch.float64).cpu().numpy()
+        rat.close()
+        return res
+
+    def samples(self, num_gibbs=2, fit_first=False):
+        '''
+        The Markov chain of bayes_pmf.py:227-302, started at the current MAP factors; yields
+        (user_sample, item_sample) forever.  Ratings added after the generator started are
+        ignored, like in the reference.
+        '''
+        name = self.dtype_name
+        dt = D.np_dtype(name)
+        n, m, d = self.num_users, self.num_items, self.latent_d
+        rat = D.Ratings.from_tuples(self.ratings, n, m, name)   # adjacency, rating-list order
+
+        if fit_first:
+            self.do_fit()
+
+        user_sample = self.users.copy()
+        item_sample = self.items.copy()
+        items_t = D.to_device(item_sample, dt)
+
+        while True:
+            mu_u, alpha_u = self.sample_hyperparam(user_sample, True)
+            mu_v, alpha_v = self.sample_hyperparam(item_sample, False)
+            for _gibbs in range(num_gibbs):
+                z = np.random.normal(0, 1, (n, d))          # row-major = the reference's per-row draws
+                users_t = self._half_sweep(rat, 0, items_t, mu_u, alpha_u, z)
+                z = np.random.normal(0, 1, (m, d))
+                items_t = self._half_sweep(rat, 1, users_t, mu_v, alpha_v, z)
+            self._check_gibbs(rat)
+            user_sample = users_t.to(torch.float64).cpu().numpy()
+            item_sample = items_t.to(torch.float64).cpu().numpy()
+            yield user_sample, item_sample
+
+    def samples_parallel(self, num_gibbs=2, pool=None, multiproc_mode=None, fit_first=False):
+        '''(bayes_pmf.py:306-424) the row fan-out is the GPU launch; `pool` is not needed.'''
+        if multiproc_mode == 'force' and pool is None:
+            raise ValueError("need a process pool if multiproc is forced")
+        return self.samples(num_gibbs=num_gibbs, fit_first=fit_first)
+
+    ############################################################################
+    ### Criteria over samples
+
+    def _which_indices(self, which):
+        n, m = self.num_users, self.num_items
+        if which is None:
+            which = Ellipsis
+        ii, jj = np.meshgrid(np.arange(n), np.arange(m), indexing='ij')
+        i_idx, j_idx = ii[which], jj[which]
+        return i_idx.reshape(-1), j_idx.reshape(-1), i_idx.shape
+
+    def _sample_stats(self, samples_iter, which, cutoff=0., want=('mean', 'var', 'prob')):
+        lib = N.require_device()
+        name = self.dtype_name
+        dt = D.np_dtype(name)
+        samples = list(samples_iter)
+        if not samples:
+            raise StopIteration
+        us = D.to_device(np.stack([np.asarray(u) for u, _ in samples]), dt)
+        vs = D.to_device(np.stack([np.asarray(v) for _, v in samples]), dt)
+        i_idx, j_idx, shape = self._which_indices(which)
+        ci, cj = D.to_device(i_idx, np.int32), D.to_device(j_idx, np.int32)
+        nc = ci.numel()
+        tdt = D.torch_dtype(name)
+        outs = {k: torch.empty(nc, dtype=tdt, device=ci.device) if k in want else None
+                for k in ('mean', 'var', 'prob')}
+        N.check(lib.amf_bayes_sample_stats(
+            D.code(name), nc, D.ptr(ci), D.ptr(cj), len(samples), self.num_users, self.num_items,
+            self.latent_d, D.ptr(us), D.ptr(vs), float(self._mean_offset()), float(cutoff),
+            D.ptr(outs['mean']), D.ptr(outs['var']), D.ptr(outs['prob']), 1, 1, 0, None,
+            D.stream_ptr()))
+        return {k: v.to(torch.float64).cpu().numpy().reshape(shape)
+                for k, v in outs.items() if v is not None}
+
+    def matrix_results(self, vals, which):
+        res = np.empty((self.num_users, self.num_items))
+        res.fill(np.nan)
+        res[which] = vals
+        return res
+
+    def predict(self, samples_iter, which=Ellipsis):
+        '''Mean reconstruction over the samples (bayes_pmf.py:433-438).'''
+        return self._sample_stats(samples_iter, which, want=('mean',))['mean']
+
+    def pred_variance(self, samples_iter, which=Ellipsis):
+        '''Population variance of each prediction over the samples (bayes_pmf.py:440-448).'''
+        return self._sample_stats(samples_iter, which, want=('var',))['var']
+
+    def total_variance(self, samples_iter, which=Ellipsis):
+        return self.pred_variance(samples_iter, which=which).sum()
+
+    def prob_ge_cutoff(self, samples_iter, cutoff, which=Ellipsis):
+        '''Fraction of samples predicting >= cutoff (bayes_pmf.py:528-538).'''
+        return self._sample_stats(samples_iter, which, cutoff=cutoff, want=('prob',))['prob']
+
+    def random(self, samples_iter, which=Ellipsis):
+        shape = np.empty((self.num_users, self.num_items))[which].shape
+        return np.random.rand(*shape)
+
+    def bayes_rmse(self, samples_iter, true_r, which=Ellipsis):
+        return rmse(self.predict(samples_iter, which), true_r[which])
+
+    def exp_variance(self, samples_iter, which=Ellipsis, pool=None, fit_first=True, num_samps=30):
+        '''Expected total variance after learning each R_ij (bayes_pmf.py:457-468).'''
+        return self._distribute(_exp_variance_helper, samples_iter, which, pool, fit_first, num_samps)
+
+    def _distribute(self, fn, samples_iter, which, pool, fit_first, num_samps):
+        '''(bayes_pmf.py:470-525); alpha and denom are C floats in the compiled reference.'''
+        samples = list(samples_iter)
+        i_idx, j_idx, shape = self._which_indices(which)
+        name = self.dtype_name
+        dt = D.np_dtype(name)
+        # R_ij samples at the requested cells: (S, ncand)
+        vals = np.stack([
+            self._sample_stats([s], which, want=('mean',))['mean'].reshape(-1) for s in samples])
+
+        if self.discrete_expectations and self.rating_values is not None:
+            discrete = True
+            alpha = float(np.float32(.1))
+            prev_samps = vals.shape[0]
+            denom = float(np.float32(prev_samps + alpha * len(self.rating_values)))
+            params = [(np.histogram(v, bins=self.rating_bounds)[0] + alpha) / denom for v in vals.T]
+        else:
+            if self.discrete_expectations and self.rating_values is None:
+                warnings.warn("have no rating_values; doing continuous")
+            discrete = False
+            params = list(zip(np.mean(vals, 0).flat, np.var(vals, 0).flat))
+
+        exps = map(fn, zip(repeat(self), i_idx.flat, j_idx.flat, repeat(discrete), params,
+                           repeat(fit_first), repeat(num_samps)))
+        res = np.empty(shape)
+        res.fill(np.nan)
+        for idx, exp in enumerate(exps):
+            res.flat[idx] = exp
+        return res
+
+
+def _integrate_lookahead(fn, bpmf, i, j, discrete, params, fit_first, num_samps):
+    '''(bayes_pmf.py:560-598)'''
+    i, j = int(i), int(j)
+    if (i, j) in bpmf.rated:
+        warnings.warn("Asked to check a known entry; returning NaN")
+        return np.nan
+
+    def calculate_fn(v):
+        b = deepcopy(bpmf)
+        b.add_rating(i, j, v)
+        samps = b.samples(fit_first=fit_first)
+        return fn(b, islice(samps, num_samps))
+
+    if discrete:
+        evals = np.array([calculate_fn(v) for v in bpmf.rating_values])
+        est = (evals * params).sum()
+    else:
+        mean, var = params
+        dist = stats.norm(loc=mean, scale=np.sqrt(var))
+        pts = dist.ppf(np.linspace(.001, .999, bpmf.num_integration_pts))
+        evals = np.fromiter(map(calculate_fn, pts), float, pts.size)
+        est = integrate.trapezoid(evals * dist.pdf(pts), pts)
+    return est
+
+
+def _exp_variance_helper(args):
+    return _integrate_lookahead(BayesianPMF.total_variance, *args)
+
+
+################################################################################
+
+Key = namedtuple('Key', ['nice_name', 'key_fn', 'choose_max', 'wants_pool', 'args'])
+
+KEYS = {
+    'random': Key("Random", 'random', True, False, ()),
+    'pred-variance': Key("Var[R_ij]", 'pred_variance', True, False, ()),
+
+    'exp-variance': Key("E[Var[R]]", 'exp_variance', False, True, ()),
+
+    'pred': Key("Pred", 'predict', True, False, ()),
+    'prob-ge-3.5': Key("Prob >= 3.5", 'prob_ge_cutoff', True, False, (3.5,)),
+    'prob-ge-.5': Key("Prob >= .5", 'prob_ge_cutoff', True, False, (.5,)),
+    'prob-ge-0': Key("Prob >= 0", 'prob_ge_cutoff', True, False, (0,)),
+}
+
+
+def fetch_samples(bpmf, num, *args, **kwargs):
+    samps = list(islice(bpmf.samples(*args, **kwargs), num))
+    pred = bpmf.predict(samps)
+    return samps, pred
+
+
+def full_test(bpmf, samples, real, key_name, num_samps=128, lookahead_fit='batch',
+              lookahead_samps=128, pool=None, multieval=False, init_rmse=None, test_on=Ellipsis):
+    '''Active loop driven by posterior samples (bayes_pmf.py:682-729).'''
+    key = KEYS[key_name]
+    total = real.size
+    picker_fn = getattr(bpmf, key.key_fn)
+    chooser = np.argmax if key.choose_max else np.argmin
+
+    if init_rmse is None:
+        init_rmse = bpmf.bayes_rmse(samples, real, which=test_on)
+    yield (len(bpmf.rated), init_rmse, None, None)
+
+    while bpmf.unrated:
+        print("{:<40} Picking query point {}...".format(key.nice_name, len(bpmf.rated) + 1))
+        if len(bpmf.unrated) == 1:
+            vals = None
+            i, j = next(iter(bpmf.unrated))
+        else:
+            unrated = np.array(list(bpmf.unrated)).T
+            which = tuple(unrated)
+            key_kwargs = {'which': which}
+            if key.wants_pool and pool is not None:
+                key_kwargs['pool'] = pool
+            evals = picker_fn(samples, *key.args, **key_kwargs)
+            i, j = unrated[:, chooser(evals)]
+            vals = bpmf.matrix_results(evals, which)
+
+        bpmf.add_rating(i, j, real[i, j])
+        print("{:<40} Queried ({}, {}); {}/{} known".format(key.nice_name, i, j, len(bpmf.rated), total))
+
+        samples, pred = fetch_samples(bpmf, num_samps, fit_first=True)
+        err = rmse(pred[test_on], real[test_on])
+        print("{:<40} RMSE {}: {:.5}".format(key.nice_name, len(bpmf.rated), err))
+        yield len(bpmf.rated), err, (i, j), vals
+
+
+def compare_active(key_names, latent_d, real, ratings, rating_vals=None, discrete=True,
+                   subtract_mean=True, num_steps=None, procs=None, threaded=False,
+                   fit_type=('batch',), num_samps=128, test_set='all', **kwargs):
+    '''(bayes_pmf.py:733-825); `procs` is accepted and ignored (no worker processes).'''
+    knowable = np.isfinite(real)
+    knowable[real == 0] = 0
+    pickable = knowable.copy()
+    pickable[ratings[:, 0].astype(int), ratings[:, 1].astype(int)] = 0
+
+    try:
+        test_set = float(test_set)
+    except ValueError:
+        if test_set != 'all':
+            warnings.warn("dunno what to do with test_set {}".format(test_set))
+            test_set = 'all'
+
+    if test_set == 'all':
+        test_on = knowable
+        query_on = pickable
+    else:
+        if test_set % 1 == 0 and test_set != 1:
+            avail_pts = list(zip(*pickable.nonzero()))
+            picked_indices = random.sample(avail_pts, int(test_set))
+            picker = np.zeros(pickable.shape, bool)
+            picker[tuple(np.transpose(picked_indices))] = 1
+        else:
+            picker = np.random.binomial(1, test_set, size=pickable.shape)
+        test_on = picker * pickable
+        query_on = (1 - picker) * pickable
+
+    query_set = set(zip(*query_on.nonzero()))
+    print("{} points known, {} to query, testing on {}, {} knowable, {} total".format(
+        ratings.shape[0], query_on.sum(), test_on.sum(), knowable.sum(), real.size))
+
+    bpmf_init = BayesianPMF(ratings, latent_d, subtract_mean=subtract_mean,
+                            rating_values=rating_vals, discrete_expectations=discrete,
+                            knowable=query_set, fit_type=fit_type)
+    print("Doing initial MAP fit...")
+    bpmf_init.fit()
+
+    print("Getting initial MCMC samples...")
+    samples = list(islice(bpmf_init.samples(fit_first=fit_type), num_samps))
+    init_rmse = bpmf_init.bayes_rmse(samples, real, test_on)
+    print("Initial RMSE: {}".format(init_rmse))
+    print()
+
+    results = {
+        '_real': real,
+        '_ratings': ratings,
+        '_rating_vals': rating_vals,
+        '_initial_bpmf': deepcopy(bpmf_init),
+    }
+
+    def eval_key(key_name):
+        res = full_test(deepcopy(bpmf_init), samples, real, key_name, pool=None,
+                        multieval=False, num_samps=num_samps, init_rmse=init_rmse,
+                        test_on=test_on, **kwargs)
+        results[key_name] = list(islice(res, num_steps))
+
+    if threaded:
+        threads = [Thread(name=key_name, target=eval_key, args=(key_name,))
+                   for key_name in key_names]
+        for thread in threads:
+            thread.start()
+        for thread in threads:
+            thread.join()
+    else:
+        for key_name in key_names:
+            eval_key(key_name)
+    return results
+
+
+def main(argv=None):
+    '''Same command line as the reference (bayes_pmf.py:828-938).'''
+    import argparse
+    import os
+    import pickle
+    import sys
+
+    key_names = KEYS.keys()
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--latent-d', '-D', type=int, default=5)
+    parser.add_argument('--steps', '-s', type=int, default=None)
+    parser.add_argument('--discrete', action='store_true', default=None)
+    parser.add_argument('--no-discrete', action='store_false', dest='discrete')
+    parser.add_argument('--subtract-mean', action='store_true', default=True)
+    parser.add_argument('--no-subtract-mean', action='store_false', dest='subtract_mean')
+    parser.add_argument('--fit', default='batch')
+    parser.add_argument('--lookahead-fit', default='batch')
+    parser.add_argument('--samps', '-S', type=int, default=128)
+    parser.add_argument('--lookahead-samps', type=int, default=128)
+    parser.add_argument('--threaded', action='store_true', default=True)
+    parser.add_argument('--unthreaded', action='store_false', dest='threaded')
+    parser.add_argument('--procs', '-P', type=int, default=None)
+    parser.add_argument('--test-set', default='all')
+    parser.add_argument('--load-data', required='True', metavar='FILE')
+    parser.add_argument('--save-results', nargs='?', default=True, const=True, metavar='FILE')
+    parser.add_argument('--no-save-results', action='store_false', dest='save_results')
+    parser.add_argument('--note', action='append')
+    parser.add_argument('keys', nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names))))
+    args = parser.parse_args(argv)
+
+    for k in args.keys:
+        if k not in key_names:
+            sys.stderr.write("Invalid key name %s; options are %s.\n" % (
+                k, ', '.join(sorted(key_names))))
+            sys.exit(1)
+    if not args.keys:
+        args.keys = sorted(key_names)
+
+    if args.save_results is True:
+        args.save_results = 'results.pkl'
+    elif args.save_results:
+        dirname = os.path.dirname(args.save_results)
+        if dirname and not os.path.exists(dirname):
+            os.makedirs(dirname)
+
+    with open(args.load_data, 'rb') as f:
+        data = np.load(f, allow_pickle=True)
+        if isinstance(data, np.ndarray):
+            data = {'_real': data}
+        real = data['_real']
+        ratings = data['_ratings']
+        rating_vals = data['_rating_vals'] if '_rating_vals' in data else None
+
+    if args.discrete is None:
+        args.discrete = rating_vals is not None
+
+    results = compare_active(key_names=args.keys, latent_d=args.latent_d, real=real,
+                             ratings=ratings, rating_vals=rating_vals, test_set=args.test_set,
+                             num_steps=args.steps, discrete=args.discrete,
+                             subtract_mean=args.subtract_mean, fit_type=parse_fit_type(args.fit),
+                             lookahead_fit=args.lookahead_fit, num_samps=args.samps,
+                             lookahead_samps=args.lookahead_samps, procs=args.procs,
+                             threaded=args.threaded)
+
+    if args.save_results:
+        print("\nsaving results in '{}'".format(args.save_results))
+        results['_args'] = args
+        with open(args.save_results, 'wb') as f:
+            pickle.dump(results, f)
+    return results
+
+
+if __name__ == '__main__':
+    main()

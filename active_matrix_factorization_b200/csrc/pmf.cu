@@ -70,6 +70,54 @@ momentum_kernel(T* __restrict__ inc, const T* __restrict__ G, T momentum, T scal
   }
 }
 
+// loads E consecutive entries starting at a multiple of E (16-byte aligned vector loads; the
+// same address is read by all lanes of a group, so a warp touches at most 2 lines per load)
+template <int E>
+__device__ __forceinline__ void load_idx(const int32_t* __restrict__ p, int32_t (&out)[E]) {
+  if constexpr (E % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) {
+      const int4 v = __ldcs(reinterpret_cast<const int4*>(p) + q);
+      out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+      const int2 v = __ldcs(reinterpret_cast<const int2*>(p) + q);
+      out[2 * q] = v.x; out[2 * q + 1] = v.y;
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void load_val(const float* __restrict__ p, float (&out)[E]) {
+  if constexpr (E % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(p) + q);
+      out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+      const float2 v = __ldcs(reinterpret_cast<const float2*>(p) + q);
+      out[2 * q] = v.x; out[2 * q + 1] = v.y;
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void load_val(const double* __restrict__ p, double (&out)[E]) {
+#pragma unroll
+  for (int q = 0; q < E / 2; ++q) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p) + q);
+    out[2 * q] = v.x; out[2 * q + 1] = v.y;
+  }
+}
+
+// One side of the fused loss+gradient.  A lane group owns sub-chunks of AMF_SUB=32 consecutive
+// entries of the sorted list and walks them in batches of E: the E (index, rating) pairs come
+// in with two vector loads, the E factor rows of the other side are gathered back to back
+// (E independent 16-byte loads per lane in flight), then the batch is reduced in order so the
+// row accumulator and the row-change flush see the entries sequentially.
 template <typename T, int LPR, int VPL, bool GRAD>
 __global__ void __launch_bounds__(256)
 side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -79,7 +127,8 @@ side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
                  double* __restrict__ sq_err, int64_t nnz, int64_t n_sub) {
   using V = typename Vec<T>::type;
   constexpr int N = Vec<T>::N;
-  constexpr int G = 32 / LPR;  // ratings in flight per warp
+  constexpr int G = 32 / LPR;                  // lane groups per warp
+  constexpr int E = (VPL == 1) ? 8 : 2;        // entries per batch
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, l = lane % LPR;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -94,10 +143,13 @@ side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
     T sub_sq = 0;
     const int64_t sub = base + g;
     const bool live = sub < n_sub;
-    const int64_t p0 = sub * AMF_SUB;
-    const int64_t p1 = live ? min(p0 + (int64_t)AMF_SUB, nnz) : p0;
+    const int64_t p0 = live ? sub * AMF_SUB : 0;
+    // everything below is relative to p0 so the inner loop runs on 32-bit offsets
+    const int cnt = live ? (int)min((int64_t)AMF_SUB, nnz - p0) : 0;
     int32_t row = live ? sub_row[sub] : 0;
-    int64_t row_end = live ? ptr[row + 1] : 0;
+    int row_end = live ? (int)min(ptr[row + 1] - p0, (int64_t)(AMF_SUB + 1)) : AMF_SUB + 1;
+    const int32_t* __restrict__ idx0 = idx + p0;
+    const T* __restrict__ val0 = val + p0;
     V self[VPL], acc[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -106,51 +158,69 @@ side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
                     ? reinterpret_cast<const V*>(Self + (int64_t)row * ld)[l + v * LPR]
                     : vzero(V());
     }
-#pragma unroll 4
-    for (int t = 0; t < AMF_SUB; ++t) {
-      const int64_t p = p0 + t;
-      const bool valid = p < p1;
-      if (valid && p >= row_end) {
-        // leave the finished row: publish its partial gradient, move to the row holding p
+    const bool full = __all_sync(0xffffffffu, cnt == AMF_SUB);   // warp-uniform fast path
+    for (int b = 0; b < AMF_SUB; b += E) {
+      int32_t js[E];
+      T rs[E];
+      if (full || b + E <= cnt) {
+        load_idx<E>(idx0 + b, js);
+        load_val<E>(val0 + b, rs);
+      } else {
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+          const bool ok = b + s < cnt;
+          js[s] = ok ? ld_stream(idx0 + b + s) : 0;
+          rs[s] = ok ? ld_stream(val0 + b + s) : T(0);
+        }
+      }
+      V o[E][VPL];
+#pragma unroll
+      for (int s = 0; s < E; ++s)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          o[s][v] = ((full || b + s < cnt) && have[v])
+                        ? reinterpret_cast<const V*>(Other + (int64_t)js[s] * ld)[l + v * LPR]
+                        : vzero(V());
+#pragma unroll
+      for (int s = 0; s < E; ++s) {
+        const int t = b + s;
+        const bool valid = full || t < cnt;
+        if (valid && t >= row_end) {
+          // leave the finished row: publish its partial gradient, move to the row holding t
+          if (GRAD) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              if (have[v]) vred_add(dSelf + (int64_t)row * ld + (l + v * LPR) * N, acc[v]);
+          }
+          int64_t re;
+          do { ++row; re = ptr[row + 1] - p0; } while ((int64_t)t >= re);
+          row_end = (int)min(re, (int64_t)(AMF_SUB + 1));
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            acc[v] = vzero(V());
+            if (have[v]) self[v] = reinterpret_cast<const V*>(Self + (int64_t)row * ld)[l + v * LPR];
+          }
+        }
+        T dot = 0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) dot += vdot(self[v], o[s][v]);
+#pragma unroll
+        for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        const T e = valid ? (rs[s] - mean_offset) - dot : T(0);
+        sub_sq = fma(e, e, sub_sq);
         if (GRAD) {
+          const T w = e * inv_sigma;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v)
-            if (have[v]) vred_add(dSelf + (int64_t)row * ld + (l + v * LPR) * N, acc[v]);
+          for (int v = 0; v < VPL; ++v) vfma(acc[v], w, o[s][v]);
         }
-        do { ++row; row_end = ptr[row + 1]; } while (p >= row_end);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          acc[v] = vzero(V());
-          if (have[v]) self[v] = reinterpret_cast<const V*>(Self + (int64_t)row * ld)[l + v * LPR];
-        }
-      }
-      int32_t j = 0;
-      T r = 0;
-      if (valid) { j = ld_stream(idx + p); r = ld_stream(val + p); }
-      V o[VPL];
-      T dot = 0;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        o[v] = (valid && have[v]) ? reinterpret_cast<const V*>(Other + (int64_t)j * ld)[l + v * LPR]
-                                  : vzero(V());
-        dot += vdot(self[v], o[v]);
-      }
-#pragma unroll
-      for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-      const T e = valid ? (r - dot - mean_offset) : T(0);
-      if (l == 0) sub_sq = fma(e, e, sub_sq);
-      if (GRAD) {
-        const T w = e * inv_sigma;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) vfma(acc[v], w, o[v]);
       }
     }
-    if (GRAD && live && p1 > p0) {
+    if (GRAD && cnt > 0) {
 #pragma unroll
       for (int v = 0; v < VPL; ++v)
         if (have[v]) vred_add(dSelf + (int64_t)row * ld + (l + v * LPR) * N, acc[v]);
     }
-    local_sq += (double)sub_sq;
+    if (l == 0) local_sq += (double)sub_sq;
   }
   if (sq_err) {
     double s = block_sum(local_sq);

@@ -10,6 +10,22 @@
 
 namespace amf {
 
+template <int E>
+__device__ __forceinline__ void load_idx_vec(const int32_t* __restrict__ p, int32_t (&out)[E]) {
+  if constexpr (E % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < E / 4; ++q) {
+      const int4 v = __ldcs(reinterpret_cast<const int4*>(p) + q);
+      out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
+    }
+  } else if constexpr (E == 2) {
+    const int2 v = __ldcs(reinterpret_cast<const int2*>(p));
+    out[0] = v.x; out[1] = v.y;
+  } else {
+    out[0] = __ldcs(p);
+  }
+}
+
 template <bool MAX>
 __global__ void best_final_kernel(const Best* __restrict__ part, int nparts,
                                   amf_best_t* __restrict__ out) {
@@ -30,41 +46,78 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
   return AMF_OK;
 }
 
-// MAP prediction U_i . V_j : LPR lanes per candidate, one 16-byte vector each (x VPL)
-template <typename T, int LPR, int VPL, bool MAX>
+// MAP prediction U_i . V_j.  A warp takes 32 consecutive candidates per iteration; each group
+// of LPR lanes owns LPR of them and every lane holds one 16-byte slice (x VPL) of the factor
+// rows.  All LPR row gathers of a group are issued before any is used (memory-level
+// parallelism), the user row is re-used while consecutive candidates share i (the pool is
+// sorted by user), and a transpose-reduce leaves exactly one finished dot product per lane
+// (candidate base+lane), so stores are coalesced and the arg-best costs one compare per lane.
+template <typename T, int LPR, int VPL, bool MAX, bool VECIDX>
 __global__ void __launch_bounds__(256)
 score_pred_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj, int64_t ncand,
                   const T* __restrict__ U, const T* __restrict__ Vm, int ld, int nvec,
                   T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
   using V = typename Vec<T>::type;
-  constexpr int G = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, l = lane % LPR;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  Best best{0.0, -1};
-  for (int64_t base = warp * G; base < ncand; base += nwarps * G) {
-    const int64_t c = base + g;
-    const bool valid = c < ncand;
-    const int32_t i = valid ? ld_stream(ci + c) : 0, j = valid ? ld_stream(cj + c) : 0;
-    T dot = 0;
+  T best_v = 0;
+  int64_t best_c = -1;
+  for (int64_t base = warp * 32; base < ncand; base += nwarps * 32) {
+    const int64_t c0 = base + g * LPR;        // first candidate of this lane group
+    int32_t is[LPR], js[LPR];
+    if (VECIDX && LPR >= 2 && base + 32 <= ncand) {
+      load_idx_vec<LPR>(ci + c0, is);
+      load_idx_vec<LPR>(cj + c0, js);
+    } else {
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      if (valid && (l + v * LPR) < nvec) {
-        V a = reinterpret_cast<const V*>(U + (int64_t)i * ld)[l + v * LPR];
-        V b = reinterpret_cast<const V*>(Vm + (int64_t)j * ld)[l + v * LPR];
-        dot += vdot(a, b);
+      for (int s = 0; s < LPR; ++s) {
+        const bool ok = c0 + s < ncand;
+        is[s] = ok ? __ldcs(ci + c0 + s) : 0;
+        js[s] = ok ? __ldcs(cj + c0 + s) : 0;
       }
     }
+    T p[LPR];
 #pragma unroll
-    for (int off = LPR >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    if (valid && l == 0) {
-      if (scores) __stcs(scores + c, dot);
-      if (better<MAX>((double)dot, c + index_base, best.v, best.i)) {
-        best.v = (double)dot; best.i = c + index_base;
+    for (int s = 0; s < LPR; ++s) p[s] = 0;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int chunk = l + v * LPR;
+      const bool have = chunk < nvec;
+      V b[LPR];
+#pragma unroll
+      for (int s = 0; s < LPR; ++s)
+        b[s] = have ? reinterpret_cast<const V*>(Vm + (int64_t)js[s] * ld)[chunk] : vzero(V());
+      V a = vzero(V());
+#pragma unroll
+      for (int s = 0; s < LPR; ++s) {
+        if (have && (s == 0 || is[s] != is[s - 1]))
+          a = reinterpret_cast<const V*>(U + (int64_t)is[s] * ld)[chunk];
+        p[s] += vdot(a, b[s]);
+      }
+    }
+    // transpose-reduce across the LPR lanes of the group: lane l ends with candidate l's sum
+#pragma unroll
+    for (int half = LPR >> 1; half >= 1; half >>= 1) {
+      const bool upper = (l & half) != 0;
+#pragma unroll
+      for (int t = 0; t < half; ++t) {
+        const T send = upper ? p[t] : p[t + half];
+        const T keep = upper ? p[t + half] : p[t];
+        p[t] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+      }
+    }
+    const int64_t c = base + lane;
+    if (c < ncand) {
+      if (scores) __stcs(scores + c, p[0]);
+      if (MAX ? (p[0] > best_v || best_c < 0) && (p[0] == p[0])
+              : (p[0] < best_v || best_c < 0) && (p[0] == p[0])) {
+        best_v = p[0]; best_c = c;
       }
     }
   }
+  Best best{(double)best_v, best_c < 0 ? -1 : best_c + index_base};
   best = block_best<MAX>(best);
   if (threadIdx.x == 0) part[blockIdx.x] = best;
 }
@@ -140,24 +193,29 @@ static int score_pred(int64_t ncand, const int32_t* ci, const int32_t* cj, int d
   AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
   const int nvec = ld / N;
   int lpr = pow2c(nvec), vpl = 1;
-  if (lpr > 32) { vpl = lpr / 32; lpr = 32; }
-  if (vpl > 4) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
-#define PRED(LPR_, VPL_)                                                                     \
-  score_pred_kernel<T, LPR_, VPL_, MAX><<<grid, 256, 0, s>>>(ci, cj, ncand, U, V, ld, nvec,  \
-                                                             scores, index_base, part)
+  if (lpr > 8) { vpl = lpr / 8; lpr = 8; }    // at most 8 candidates (and partial sums) per lane
+  if (vpl > 8) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
+  const bool vec = (reinterpret_cast<uintptr_t>(ci) % 16 == 0) && (reinterpret_cast<uintptr_t>(cj) % 16 == 0);
+#define PRED(LPR_, VPL_)                                                                       \
+  do {                                                                                         \
+    if (vec) score_pred_kernel<T, LPR_, VPL_, MAX, true><<<grid, 256, 0, s>>>(                 \
+        ci, cj, ncand, U, V, ld, nvec, scores, index_base, part);                              \
+    else score_pred_kernel<T, LPR_, VPL_, MAX, false><<<grid, 256, 0, s>>>(                    \
+        ci, cj, ncand, U, V, ld, nvec, scores, index_base, part);                              \
+  } while (0)
   if (vpl == 1) {
     switch (lpr) {
       case 1: PRED(1, 1); break;
       case 2: PRED(2, 1); break;
       case 4: PRED(4, 1); break;
-      case 8: PRED(8, 1); break;
-      case 16: PRED(16, 1); break;
-      default: PRED(32, 1); break;
+      default: PRED(8, 1); break;
     }
   } else if (vpl == 2) {
-    PRED(32, 2);
+    PRED(8, 2);
+  } else if (vpl <= 4) {
+    PRED(8, 4);
   } else {
-    PRED(32, 4);
+    PRED(8, 8);
   }
 #undef PRED
   AMF_LAUNCH_CHECK();
@@ -231,7 +289,7 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
   int grid;
   if (criterion == AMF_CRIT_PRED) {
     AMF_REQUIRE(U_d && V_d, "amf_score_candidates: U/V are NULL");
-    const int64_t blocks = (ncand + 63) / 64;  // >= 2 candidates per lane group before capping
+    const int64_t blocks = (ncand + 255) / 256;  // one 32-candidate batch per warp before capping
     grid = (int)(blocks < (int64_t)num_sms() * 8 ? (blocks > 0 ? blocks : 1) : (int64_t)num_sms() * 8);
   } else {
     AMF_REQUIRE(nvp && nvp->mean_u && nvp->mean_v && nvp->cov_uu && nvp->cov_vv,

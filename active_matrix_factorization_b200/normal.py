@@ -1,0 +1,102 @@
+"""Device driver for the batched variational approximation (csrc/normal.cu)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import device as D
+
+
+def fit_params(n, m, d, sigma_sq, sigma_u_sq, sigma_v_sq, learning_rate=1e-4, min_eig=1e-5,
+               kl_stop=.005, min_lr=1e-10, max_steps=0):
+    return N.NormalFitParams(int(n), int(m), int(d), float(sigma_sq), float(sigma_u_sq),
+                             float(sigma_v_sq), float(learning_rate), float(min_eig),
+                             float(kl_stop), float(min_lr), int(max_steps))
+
+
+class NormalBatch:
+    """B problems sharing one COO rating list; each may append one extra rating."""
+
+    def __init__(self, ratings, params, means, covs, extra=None):
+        """ratings (nnz,3) host array; means (B,k), covs (B,k,k) host float64; extra = optional
+        (ei, ej, er) host arrays of length B."""
+        self.lib = N.require_device()
+        self.p = params
+        self.k = (params.n + params.m) * params.d
+        ratings = np.asarray(ratings, dtype=np.float64).reshape(-1, 3)
+        self.nnz = ratings.shape[0]
+        self.ri = D.to_device(ratings[:, 0], np.int32)
+        self.rj = D.to_device(ratings[:, 1], np.int32)
+        self.rr = D.to_device(ratings[:, 2], np.float64)
+        means = np.ascontiguousarray(means, dtype=np.float64).reshape(-1, self.k)
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(-1, self.k, self.k)
+        self.B = means.shape[0]
+        assert covs.shape[0] == self.B
+        self.mean = D.to_device(means, np.float64)
+        self.cov = D.to_device(covs, np.float64)
+        if extra is not None:
+            self.ei = D.to_device(extra[0], np.int32)
+            self.ej = D.to_device(extra[1], np.int32)
+            self.er = D.to_device(extra[2], np.float64)
+        else:
+            self.ei = self.ej = self.er = None
+        self.ws = int(self.lib.amf_normal_workspace_doubles(params.n, params.m, params.d))
+        dev = self.mean.device
+        self.work = torch.empty(self.B * self.ws, dtype=torch.float64, device=dev)
+        self.kl = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.steps = torch.zeros(self.B, dtype=torch.int32, device=dev)
+
+    def _run(self, mode, trace=None, entropy=None, totvar=None):
+        N.check(self.lib.amf_normal_batched(
+            mode, self.B, self.nnz, D.ptr(self.ri), D.ptr(self.rj), D.ptr(self.rr),
+            D.ptr(self.ei), D.ptr(self.ej), D.ptr(self.er), C.byref(self.p), D.ptr(self.mean),
+            D.ptr(self.cov), D.ptr(self.work), D.ptr(self.kl), D.ptr(self.steps),
+            D.ptr(trace), 0 if trace is None else trace.shape[1], D.ptr(entropy), D.ptr(totvar),
+            D.stream_ptr()))
+
+    def kl_divergence(self):
+        self._run(N.NORMAL_KL)
+        return self.kl.cpu().numpy()
+
+    def gradient(self):
+        self._run(N.NORMAL_GRADIENT)
+        w = self.work.view(self.B, self.ws)
+        k = self.k
+        return (w[:, :k].cpu().numpy().copy(),
+                w[:, 2 * k:2 * k + k * k].reshape(self.B, k, k).cpu().numpy().copy())
+
+    def project(self):
+        self._run(N.NORMAL_PROJECT)
+        return self.cov.cpu().numpy()
+
+    def fit(self, trace_len=0, want_entropy=False, want_totvar=False):
+        """Runs fit_normal_kls on every problem.  Returns dict of host arrays."""
+        dev = self.mean.device
+        trace = torch.full((self.B, trace_len), float('nan'), dtype=torch.float64, device=dev) \
+            if trace_len else None
+        ent = torch.zeros(self.B, dtype=torch.float64, device=dev) if want_entropy else None
+        tv = torch.zeros(self.B, dtype=torch.float64, device=dev) if want_totvar else None
+        self._run(N.NORMAL_FIT, trace, ent, tv)
+        out = dict(kl=self.kl.cpu().numpy(), steps=self.steps.cpu().numpy())
+        if trace is not None:
+            out['trace'] = trace.cpu().numpy()
+        if ent is not None:
+            out['entropy'] = ent.cpu().numpy()
+        if tv is not None:
+            out['total_variance'] = tv.cpu().numpy()
+        return out
+
+    def means(self):
+        return self.mean.cpu().numpy()
+
+    def covs(self):
+        return self.cov.cpu().numpy()
+
+
+def project_psd_device(mat, min_eig):
+    mat = np.ascontiguousarray(mat, dtype=np.float64)
+    k = mat.shape[0]
+    p = fit_params(k, 0, 1, 1., 1., 1., min_eig=min_eig)
+    batch = NormalBatch(np.zeros((0, 3)), p, np.zeros((1, k)), mat[None])
+    return batch.project()[0]

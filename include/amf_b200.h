@@ -184,6 +184,43 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
                            void* prob_d, int select, int maximize, int64_t index_base,
                            amf_best_t* best_d, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Variational full-covariance approximation ("exact mode"), batched, fp64:
+ * active_pmf.py:202-240 kl_divergence, normal_exps_cy.pyx:140-303 normal_gradient,
+ * active_pmf.py:36-50 project_psd, :251-288 fit_normal_kls, and the lookahead of :635-704
+ * (_exp_with_rij: one re-fit per candidate and rating value), whose per-problem criteria
+ * :526-530 _approx_entropy and :605-606 _total_variance are computed in the same launch.
+ * B independent problems share the COO rating list (ri,rj,rr) and each may append one extra
+ * rating (extra_i[b] < 0: none).  One CTA per problem; k = (n+m)*d.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n, m, d;
+  double sigma_sq, sigma_u_sq, sigma_v_sq;
+  double learning_rate; /* normal_learning_rate, active_pmf.py:145 (1e-4) */
+  double min_eig;       /* active_pmf.py:146 (1e-5) */
+  double kl_stop;       /* convergence threshold on the KL decrease, active_pmf.py:277 (.005) */
+  double min_lr;        /* active_pmf.py:286 (1e-10) */
+  int32_t max_steps;    /* <= 0: run to convergence */
+} amf_normal_fit_params_t;
+
+#define AMF_NORMAL_FIT 0      /* fit_normal_kls on every problem; mean/cov updated in place  */
+#define AMF_NORMAL_KL 1       /* kl_out[b] = KL(mean_b, cov_b)                               */
+#define AMF_NORMAL_GRADIENT 2 /* work_b[0:k] = dKL/dmean, work_b[2k : 2k+k*k] = dKL/dcov     */
+#define AMF_NORMAL_PROJECT 3  /* cov_b <- project_psd(cov_b, min_eig)                        */
+
+/* doubles of scratch needed PER PROBLEM in work_d */
+int64_t amf_normal_workspace_doubles(int32_t n, int32_t m, int d);
+
+/* mean_d (B,k), cov_d (B,k,k) in/out; work_d (B, workspace) scratch/out; kl_out_d (B);
+ * steps_out_d (B) accepted steps; kl_trace_d (B, trace_len) KL after each accepted step or NULL;
+ * entropy_out_d / totvar_out_d (B) or NULL: log det cov / sum_ij Var[Ui.Vj] after the fit. */
+int amf_normal_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const int32_t* rj_d,
+                       const double* rr_d, const int32_t* extra_i_d, const int32_t* extra_j_d,
+                       const double* extra_r_d, const amf_normal_fit_params_t* p, double* mean_d,
+                       double* cov_d, double* work_d, double* kl_out_d, int32_t* steps_out_d,
+                       double* kl_trace_d, int trace_len, double* entropy_out_d,
+                       double* totvar_out_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,8 +50,7 @@ def gather_winner(best, world, group=None):
         rec = best.view(1, 2)
     else:
         rec = torch.empty((world, 2), dtype=torch.int64, device=best.device)
-        dist.all_gather_into_tensor(rec, best.view(1, 2), group=group) if best.is_cuda else \
-            dist.all_gather(list(rec.unbind(0)), best.view(2), group=group)
+        dist.all_gather_into_tensor(rec, best.view(1, 2).contiguous(), group=group)
     return rec
 
 

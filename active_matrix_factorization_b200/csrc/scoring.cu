@@ -332,16 +332,32 @@ int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int
   const size_t es = dtype == AMF_F32 ? 4 : 8;
   const int vecn = dtype == AMF_F32 ? 4 : 2;
   const int ld = (d + vecn - 1) / vecn * vecn;
-  void *U_d = nullptr, *V_d = nullptr, *sc_d = nullptr;
-  int32_t *ci_d = nullptr, *cj_d = nullptr;
-  amf_best_t* best_d = nullptr;
+  // grow-only staging buffers, one set per host thread and device (freed at process exit)
+  struct Stage { void* p[6]; size_t n[6]; int dev; };
+  static thread_local Stage st = {{nullptr}, {0}, -1};
+  int dev = 0;
+  AMF_CUDA(cudaGetDevice(&dev));
+  if (st.dev != dev) {
+    for (int q = 0; q < 6; ++q) { if (st.p[q]) cudaFree(st.p[q]); st.p[q] = nullptr; st.n[q] = 0; }
+    st.dev = dev;
+  }
+  auto need = [&](int q, size_t bytes) -> int {
+    if (st.n[q] >= bytes) return AMF_OK;
+    if (st.p[q]) cudaFree(st.p[q]);
+    st.p[q] = nullptr; st.n[q] = 0;
+    AMF_CUDA(cudaMalloc(&st.p[q], bytes));
+    st.n[q] = bytes;
+    return AMF_OK;
+  };
   const size_t nc = ncand > 0 ? (size_t)ncand : 1;
-  AMF_CUDA(cudaMalloc(&U_d, (size_t)n * ld * es));
-  AMF_CUDA(cudaMalloc(&V_d, (size_t)m * ld * es));
-  AMF_CUDA(cudaMalloc(&ci_d, 4 * nc));
-  AMF_CUDA(cudaMalloc(&cj_d, 4 * nc));
-  AMF_CUDA(cudaMalloc(&best_d, sizeof(amf_best_t)));
-  if (scores_h) AMF_CUDA(cudaMalloc(&sc_d, es * nc));
+  int rc;
+  if ((rc = need(0, (size_t)n * ld * es)) || (rc = need(1, (size_t)m * ld * es)) ||
+      (rc = need(2, 4 * nc)) || (rc = need(3, 4 * nc)) || (rc = need(4, sizeof(amf_best_t))) ||
+      (scores_h && (rc = need(5, es * nc))))
+    return rc;
+  void *U_d = st.p[0], *V_d = st.p[1], *sc_d = scores_h ? st.p[5] : nullptr;
+  int32_t *ci_d = (int32_t*)st.p[2], *cj_d = (int32_t*)st.p[3];
+  amf_best_t* best_d = (amf_best_t*)st.p[4];
   cudaStream_t s = nullptr;
   if (ld != d) {
     AMF_CUDA(cudaMemsetAsync(U_d, 0, (size_t)n * ld * es, s));
@@ -353,15 +369,14 @@ int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int
     AMF_CUDA(cudaMemcpyAsync(ci_d, ci_h, 4 * ncand, cudaMemcpyHostToDevice, s));
     AMF_CUDA(cudaMemcpyAsync(cj_d, cj_h, 4 * ncand, cudaMemcpyHostToDevice, s));
   }
-  int rc = amf_score_candidates(AMF_CRIT_PRED, dtype, ncand, ci_d, cj_d, d, ld, U_d, V_d, nullptr,
-                                0.0, sc_d, maximize, 0, best_d, s);
+  rc = amf_score_candidates(AMF_CRIT_PRED, dtype, ncand, ci_d, cj_d, d, ld, U_d, V_d, nullptr,
+                            0.0, sc_d, maximize, 0, best_d, s);
   if (rc == AMF_OK) {
     if (scores_h && ncand > 0)
       AMF_CUDA(cudaMemcpyAsync(scores_h, sc_d, es * ncand, cudaMemcpyDeviceToHost, s));
     AMF_CUDA(cudaMemcpyAsync(best_h, best_d, sizeof(amf_best_t), cudaMemcpyDeviceToHost, s));
     AMF_CUDA(cudaStreamSynchronize(s));
   }
-  cudaFree(U_d); cudaFree(V_d); cudaFree(ci_d); cudaFree(cj_d); cudaFree(best_d); cudaFree(sc_d);
   return rc;
 }
 

@@ -87,6 +87,7 @@ class ShardedStep:
         self.rat, self.d, self.name, self.world, self.rank = rat, d, name, world, rank
         self.index_base = 0
         self._rec = None
+        self.pool = None          # optional scoring.Pool (tiled layout) for the pred criterion
         # kernels launched by one step: 2 prior + 2 side passes; scoring + winner reduction
         self.launches_per_step = 6
 
@@ -113,11 +114,14 @@ class ShardedStep:
             self.set_candidate_offset(int(ci.numel()))
             self._rec = True
         lib = N.require_device()
-        N.check(lib.amf_score_candidates(
-            criterion, D.code(self.name), int(ci.numel()), D.ptr(ci), D.ptr(cj), self.d,
-            U.shape[1] if U is not None else 0, D.ptr(U), D.ptr(V),
-            C.byref(view) if view is not None else None, float(cutoff), None,
-            1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
+        if self.pool is not None and criterion == N.CRIT_PRED:
+            self.pool.score_pred(U, V, False, maximize, self.index_base, best)
+        else:
+            N.check(lib.amf_score_candidates(
+                criterion, D.code(self.name), int(ci.numel()), D.ptr(ci), D.ptr(cj), self.d,
+                U.shape[1] if U is not None else 0, D.ptr(U), D.ptr(V),
+                C.byref(view) if view is not None else None, float(cutoff), None,
+                1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
         if self.world > 1:
             rec = gather_winner(best, self.world)
             vals = rec[:, 0].contiguous().view(torch.float64)
@@ -154,4 +158,14 @@ class ShardedStep:
                                              D.stream_ptr()))
         e1.record()
         torch.cuda.synchronize()
-        return {"side_pass_ms": side, "score_ms": e0.elapsed_time(e1) / reps}
+        out = {"side_pass_ms": side, "score_flat_ms": e0.elapsed_time(e1) / reps}
+        out["score_ms"] = out["score_flat_ms"]
+        if self.pool is not None:
+            e0.record()
+            for _ in range(reps):
+                self.pool.score_pred(U, V, False, True, 0, best)
+            e1.record()
+            torch.cuda.synchronize()
+            out["score_tiled_ms"] = e0.elapsed_time(e1) / reps
+            out["score_ms"] = out["score_tiled_ms"]
+        return out

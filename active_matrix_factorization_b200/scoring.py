@@ -63,3 +63,68 @@ def score_normal(criterion, mean, cov, n, m, d, ii, jj, name, cutoff=0.0, maximi
     ci, cj = _cands(ii, jj)
     scores, best = score_device(criterion, name, ci, cj, d, view=view, cutoff=cutoff, maximize=maximize)
     return scores.to(torch.float64).cpu().numpy(), unpack_best(best)
+
+
+class Pool:
+    """Device-resident candidate pool bucketed by item tile (csrc/pool.cu); build it once and
+    score it every active-learning step.  Scores and the winner are reported in the caller's
+    order, exactly like the unbucketed path."""
+
+    def __init__(self, ii, jj, n_users, n_items, name, d, tile_bytes=64 * 1024, block_bytes=64 * 1024):
+        import ctypes as C
+        lib = N.require_device()
+        self.name, self.d = name, int(d)
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        ci, cj = _cands(ii, jj)
+        assert ci.dtype == torch.int32 and cj.dtype == torch.int32
+        self.ncand = int(ci.numel())
+        # the pool kernel wants a row of 1, 2, 4, 8, 16 or 32 16-byte vectors
+        vec = D.vec_elems(name)
+        nvec = (d + vec - 1) // vec
+        nvec = 1 << (nvec - 1).bit_length()
+        if nvec > 32:
+            raise ValueError("latent_d=%d is too large for the bucketed pool" % d)
+        self.ld = ld = nvec * vec
+        row_bytes = ld * (4 if name == "f32" else 8)
+        def pow2_rows(nbytes):
+            rows = max(1, min(32768, nbytes // row_bytes))
+            return 1 << (rows.bit_length() - 1)                  # power of two
+        self.tile_rows = int(pow2_rows(tile_bytes))
+        self.block_rows = int(pow2_rows(block_bytes))
+        self._h = C.c_void_p()
+        torch.cuda.current_stream().synchronize()
+        N.check(lib.amf_pool_create(C.byref(self._h), self.ncand, D.ptr(ci), D.ptr(cj),
+                                    self.n_users, self.n_items, self.tile_rows, self.block_rows,
+                                    D.stream_ptr()))
+
+    def score_pred(self, U, V, want_scores=False, maximize=True, index_base=0, best=None):
+        """U, V: device tensors padded to (rows, self.ld) -- see pad().  Returns (scores tensor
+        or None, best record tensor)."""
+        lib = N.require_device()
+        assert U.shape[1] == self.ld and V.shape[1] == self.ld, "use Pool.pad() for the factors"
+        scores = torch.empty(self.ncand, dtype=D.torch_dtype(self.name), device=U.device) \
+            if want_scores else None
+        if best is None:
+            best = torch.empty(2, dtype=torch.int64, device=U.device)
+        N.check(lib.amf_pool_score_pred(self._h, D.code(self.name), self.d, U.shape[1], D.ptr(U),
+                                        D.ptr(V), D.ptr(scores), 1 if maximize else 0,
+                                        int(index_base), D.ptr(best), D.stream_ptr()))
+        return scores, best
+
+    def pad(self, arr):
+        """host (rows, d) factors -> zero-padded (rows, self.ld) device tensor for this pool"""
+        arr = np.ascontiguousarray(arr, dtype=D.np_dtype(self.name))
+        out = torch.zeros((arr.shape[0], self.ld), dtype=D.torch_dtype(self.name), device=D.device())
+        out[:, :arr.shape[1]].copy_(torch.from_numpy(arr))
+        return out
+
+    def close(self):
+        if self._h:
+            N.load().amf_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

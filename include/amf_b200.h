@@ -150,6 +150,22 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
                          const amf_normal_view_t* nv, double cutoff, void* scores_d,
                          int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
 
+/* Candidate pool handle: the pool bucketed once by (item tile of tile_rows items, user block of
+ * block_rows users), local indices packed in 4 bytes per candidate, so the scoring kernel keeps
+ * the tile of V resident in shared memory and streams the U blocks through a double-buffered TMA
+ * pipeline; built from the caller's (i, j) arrays, remembers the caller's order.  Replaces the `pool` list / `unrated` set iterated in
+ * active_pmf.py:725-770 when the same pool is scored repeatedly (every active-learning step). */
+typedef struct amf_pool amf_pool_t;
+int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
+                    int32_t n_users, int32_t n_items, int tile_rows, int block_rows, void* stream);
+int amf_pool_destroy(amf_pool_t* h);
+int64_t amf_pool_size(const amf_pool_t* h);
+/* AMF_CRIT_PRED over the pool: scores_d (T[ncand], caller's order) may be NULL; best_d as in
+ * amf_score_candidates (index = position in the caller's order + index_base, lowest wins ties). */
+int amf_pool_score_pred(const amf_pool_t* h, int dtype, int d, int ld, const void* U_d,
+                        const void* V_d, void* scores_d, int maximize, int64_t index_base,
+                        amf_best_t* best_d, void* stream);
+
 /* End-to-end host variant of AMF_CRIT_PRED: host candidate arrays and factors in, scores
  * (may be NULL) and winner out; synchronises. */
 int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,

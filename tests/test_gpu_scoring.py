@@ -57,3 +57,49 @@ def test_pred_large_random(S, dtype, tol):
     ref = np.einsum("nd,nd->n", U[ii], V[jj])
     np.testing.assert_allclose(vals, ref, rtol=tol, atol=tol * np.abs(ref).max())
     assert vals[bi] == vals.max() and bi == int(np.argmax(vals))
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 1e-5)])
+@pytest.mark.parametrize("n,m,d,nc,tile_bytes", [(3000, 2000, 32, 300_000, 64 * 1024),
+                                                  (500, 777, 10, 50_000, 4096),
+                                                  (64, 50, 5, 3000, 64 * 1024),
+                                                  (200, 1500, 48, 20_000, 16 * 1024),
+                                                  (300, 9000, 32, 400_000, 64 * 1024),
+                                                  (30, 20, 2, 600, 1024)])
+def test_tiled_pool_matches_flat_and_oracle(S, n, m, d, nc, tile_bytes, dtype, tol):
+    """the shared-memory-tiled pool kernel (TMA-loaded item tiles) gives the same scores, in the
+    caller's order, and the same winner as the flat kernel and the oracle"""
+    import torch
+    from active_matrix_factorization_b200 import device as D
+    rng = np.random.RandomState(n + d)
+    U, V = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    ii, jj = rng.randint(0, n, nc), rng.randint(0, m, nc)       # caller's order: unsorted
+    ii[5], jj[5] = ii[nc - 7], jj[nc - 7]                        # a duplicate pair -> exact tie
+    flat, (fv, fi) = S.score_pred(U, V, ii, jj, dtype)
+    pool = S.Pool(ii, jj, n, m, dtype, d, tile_bytes=tile_bytes, block_bytes=max(256, tile_bytes // 4))
+    Ut, Vt = pool.pad(U), pool.pad(V)
+    for maximize in (True, False):
+        sc, best = pool.score_pred(Ut, Vt, want_scores=True, maximize=maximize)
+        got = sc.double().cpu().numpy()
+        bv, bi = S.unpack_best(best)
+        np.testing.assert_allclose(got, flat, rtol=tol, atol=tol * np.abs(flat).max())
+        ref = np.einsum("nd,nd->n", U[ii], V[jj])
+        np.testing.assert_allclose(got, ref, rtol=tol, atol=tol * np.abs(ref).max())
+        want = int(np.argmax(got) if maximize else np.argmin(got))
+        assert bi == want and bv == got[want]
+    _, best = pool.score_pred(Ut, Vt, want_scores=False, index_base=1000)
+    assert S.unpack_best(best)[1] == fi + 1000
+    pool.close()
+
+
+def test_tiled_pool_ties_and_empty(S):
+    from active_matrix_factorization_b200 import device as D
+    U = np.ones((5, 3)); V = np.ones((40, 3))
+    ii = np.array([4, 1, 2, 3, 0, 0]); jj = np.array([39, 1, 20, 3, 0, 17])
+    pool = S.Pool(ii, jj, 5, 40, "f64", 3, tile_bytes=512, block_bytes=64)   # several buckets, all tied
+    Ut, Vt = pool.pad(U), pool.pad(V)
+    _, best = pool.score_pred(Ut, Vt)
+    assert S.unpack_best(best) == (3.0, 0)                       # first in the caller's order
+    empty = S.Pool(ii[:0], jj[:0], 5, 40, "f64", 3)
+    _, best = empty.score_pred(Ut, Vt)
+    assert S.unpack_best(best)[1] == -1

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "amf_score_candidates": [_INT, _INT, _I64, _P, _P, _INT, _INT, _P, _P,
                              C.POINTER(NormalView), _F64, _P, _INT, _I64, _P, _P],
     "amf_gibbs_half_sweep": [_P, _INT, _INT, _INT, _P, _P, _P, _F64, _F64, _P, _P, _P],
+    "amf_gibbs_half_sweep_rows": [_P, _INT, _INT, _INT, _P, _P, _P, _F64, _F64, _P, _P, _I32, _I32, _P],
     "amf_gibbs_status": [_P, C.POINTER(_INT), _P],
     "amf_bayes_sample_stats": [_INT, _I64, _P, _P, _INT, _I32, _I32, _INT, _P, _P, _F64, _F64,
                                _P, _P, _P, _INT, _INT, _I64, _P, _P],

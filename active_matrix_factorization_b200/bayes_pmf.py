@@ -151,10 +151,15 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         alpha_t = D.to_device(np.atleast_2d(alpha), dt)
         mu_t = D.to_device(np.atleast_1d(mu), dt)
         z_t = D.to_device(z, dt)
-        N.check(lib.amf_gibbs_half_sweep(rat.handle, side, D.code(name), self.latent_d,
-                                         D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
-                                         float(self.beta), float(self._mean_offset()),
-                                         D.ptr(z_t), D.ptr(out), D.stream_ptr()))
+        from . import parallel as P
+        world, rank = P.world_rank()
+        lo, hi = P.shard_bounds(rows, world, rank)
+        N.check(lib.amf_gibbs_half_sweep_rows(rat.handle, side, D.code(name), self.latent_d,
+                                              D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
+                                              float(self.beta), float(self._mean_offset()),
+                                              D.ptr(z_t), D.ptr(out), lo, hi, D.stream_ptr()))
+        if world > 1:       # rows of this side are split over the ranks
+            out = P.all_gather_rows(out, rows, world)
         return out
 
     def _check_gibbs(self, rat):

@@ -67,7 +67,8 @@ __device__ void tri_inverse_lower(const double* L, double* Linv, int d, int lda)
 template <typename T>
 __global__ void __launch_bounds__(GIBBS_THREADS)
 gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                  const T* __restrict__ val, int rows, int d, const T* __restrict__ other,
+                  const T* __restrict__ val, int row_begin, int rows, int d,
+                  const T* __restrict__ other,
                   const T* __restrict__ alpha, const T* __restrict__ mu, double beta,
                   double mean_offset, const T* __restrict__ z, T* __restrict__ out,
                   int* __restrict__ fail) {
@@ -83,7 +84,7 @@ gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
   const int tid = threadIdx.x;
   const int ldt = d + 1;
 
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+  for (int row = row_begin + blockIdx.x; row < rows; row += gridDim.x) {
     const int64_t p0 = ptr[row], p1 = ptr[row + 1];
     // ---- Gram matrix F'F and F'(r - offset), accumulated per thread over (k,l) pairs ------
     T acc[GIBBS_MAXACC];
@@ -201,18 +202,24 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
 template <typename T>
 static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, const T* alpha,
                         const T* mu, double beta, double mean_offset, const T* z, T* out,
-                        cudaStream_t s) {
-  const int rows = side == 0 ? h->n_users : h->n_items;
+                        int row_begin, int row_end, cudaStream_t s) {
+  const int all_rows = side == 0 ? h->n_users : h->n_items;
+  if (row_end < 0 || row_end > all_rows) row_end = all_rows;
+  if (row_begin < 0) row_begin = 0;
+  if (row_begin >= row_end) return AMF_OK;
+  const int rows = row_end;
   const size_t smem = sizeof(double) * (2 * d * (d + 1) + 2 * d + GIBBS_TILE) +
                       sizeof(T) * GIBBS_TILE * (d + 1);
   AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);
   AMF_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
-  const int grid = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  const int span = row_end - row_begin;
+  const int grid = span < num_sms() * 8 ? span : num_sms() * 8;
   gibbs_rows_kernel<T><<<grid, GIBBS_THREADS, smem, s>>>(h->ptr[side], h->idx[side],
-                                                         (const T*)h->val[side], rows, d, other,
-                                                         alpha, mu, beta, mean_offset, z, out, fail);
+                                                         (const T*)h->val[side], row_begin, rows,
+                                                         d, other, alpha, mu, beta, mean_offset,
+                                                         z, out, fail);
   AMF_LAUNCH_CHECK();
   return AMF_OK;
 }
@@ -224,9 +231,22 @@ using namespace amf;
 extern "C" {
 #pragma GCC visibility push(default)
 
+int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d,
+                              const void* other_d, const void* alpha_d, const void* mu_d,
+                              double beta, double mean_offset, const void* z_d, void* out_d,
+                              int32_t row_begin, int32_t row_end, void* stream);
+
 int amf_gibbs_half_sweep(const amf_ratings_t* h, int side, int dtype, int d, const void* other_d,
                          const void* alpha_d, const void* mu_d, double beta, double mean_offset,
                          const void* z_d, void* out_d, void* stream) {
+  return amf_gibbs_half_sweep_rows(h, side, dtype, d, other_d, alpha_d, mu_d, beta, mean_offset,
+                                   z_d, out_d, 0, -1, stream);
+}
+
+int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d,
+                              const void* other_d, const void* alpha_d, const void* mu_d,
+                              double beta, double mean_offset, const void* z_d, void* out_d,
+                              int32_t row_begin, int32_t row_end, void* stream) {
   AMF_REQUIRE(h && other_d && alpha_d && mu_d && z_d && out_d, "amf_gibbs_half_sweep: NULL argument");
   AMF_REQUIRE(side == 0 || side == 1, "amf_gibbs_half_sweep: side must be 0 or 1");
   AMF_REQUIRE(dtype == h->dtype, "amf_gibbs_half_sweep: dtype does not match the rating list");
@@ -236,10 +256,10 @@ int amf_gibbs_half_sweep(const amf_ratings_t* h, int side, int dtype, int d, con
   if (dtype == AMF_F32)
     return gibbs_launch<float>(h, side, d, (const float*)other_d, (const float*)alpha_d,
                                (const float*)mu_d, beta, mean_offset, (const float*)z_d,
-                               (float*)out_d, s);
+                               (float*)out_d, row_begin, row_end, s);
   return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
                               (const double*)mu_d, beta, mean_offset, (const double*)z_d,
-                              (double*)out_d, s);
+                              (double*)out_d, row_begin, row_end, s);
 }
 
 int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream) {

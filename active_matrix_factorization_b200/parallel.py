@@ -20,6 +20,68 @@ except Exception:  # pragma: no cover
     dist = None
 
 
+def world_rank():
+    """(world_size, rank) of the default process group, (1, 0) when not initialised"""
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def all_gather_rows(local_full, rows, world, group=None):
+    """`local_full` is a (rows, d) tensor in which this rank filled rows shard_bounds(rows, world,
+    rank); returns the tensor with every rank's rows (all-gather of padded equal-size shards)."""
+    rank = dist.get_rank(group)
+    per = (rows + world - 1) // world + 1
+    lo, hi = shard_bounds(rows, world, rank)
+    send = torch.zeros((per,) + tuple(local_full.shape[1:]), dtype=local_full.dtype,
+                       device=local_full.device)
+    send[:hi - lo] = local_full[lo:hi]
+    recv = torch.empty((world * per,) + tuple(local_full.shape[1:]), dtype=local_full.dtype,
+                       device=local_full.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    out = torch.empty_like(local_full)
+    for r in range(world):
+        a, b = shard_bounds(rows, world, r)
+        out[a:b] = recv[r * per:r * per + (b - a)]
+    return out
+
+
+def sharded_key_vals(model, pool, key, device=None, group=None):
+    """Multi-GPU `_get_key_vals` (active_pmf.py:739-770): the pool is cut into contiguous shards,
+    every rank evaluates its shard with the batched GPU path, the scores are all-gathered and
+    every rank returns the full list aligned with `pool`.  Works for every criterion, including
+    the lookahead ones (each (candidate, value) problem is independent)."""
+    pool = list(pool)
+    world, rank = world_rank()
+    if world == 1:
+        return model._get_key_vals(pool, key, None, None)
+    lo, hi = shard_bounds(len(pool), world, rank)
+    local = model._get_key_vals(pool[lo:hi], key, None, None)
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) \
+            if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    full = torch.zeros((len(pool), 1), dtype=torch.float64, device=device)
+    if hi > lo:
+        full[lo:hi, 0] = torch.tensor(local, dtype=torch.float64, device=device)
+    return all_gather_rows(full, len(pool), world, group)[:, 0].cpu().tolist()
+
+
+def sharded_pick_query_point(model, pool=None, key=None, group=None):
+    """Multi-GPU `pick_query_point` (active_pmf.py:709-737): same answer on every rank."""
+    import operator
+    if pool is None:
+        pool = model.unrated
+    pool = list(pool)
+    if key is None:
+        key = type(model).pred_variance
+    if len(pool) == 0:
+        raise ValueError("can't pick a query point from an empty pool")
+    if len(pool) == 1:
+        return pool[0]
+    vals = sharded_key_vals(model, pool, key, group=group)
+    return getattr(key, 'chooser', max)(zip(pool, vals), key=operator.itemgetter(1))[0]
+
+
 def shard_bounds(total, world, rank):
     """Contiguous, balanced [lo, hi) of `total` items for `rank` of `world`."""
     base, extra = divmod(int(total), int(world))

@@ -232,7 +232,10 @@ def run_reference(a):
         return
     rng = np.random.RandomState(1234)
     n, m, d = a.users, a.items, a.latent_d
-    s = a.cpu_sample
+    # bounded sample: keep the whole run (warm-up + steps) within ~3 minutes of host time
+    # (the reference spends ~10 us per rating on gradient+LL+construction)
+    budget_s = 180.0 / max(1, a.steps + a.warmup)
+    s = int(min(a.cpu_sample, max(20_000, budget_s * 1e5)))
     ri, rj = rng.randint(0, n, s), rng.randint(0, m, s)
     U = (rng.standard_normal((n, d)) / np.sqrt(np.sqrt(d))).astype(np.float32)
     V = (rng.standard_normal((m, d)) / np.sqrt(np.sqrt(d))).astype(np.float32)

@@ -186,6 +186,13 @@ int amf_gibbs_half_sweep(const amf_ratings_t* h, int side, int dtype, int d, con
                          const void* alpha_d, const void* mu_d, double beta, double mean_offset,
                          const void* z_d, void* out_d, void* stream);
 
+/* Same for rows [row_begin, row_end) only (row_end < 0: to the last row): the multi-GPU split of
+ * a half-sweep; z_d and out_d are still indexed by absolute row. */
+int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d,
+                              const void* other_d, const void* alpha_d, const void* mu_d,
+                              double beta, double mean_offset, const void* z_d, void* out_d,
+                              int32_t row_begin, int32_t row_end, void* stream);
+
 /* 1 in *failed if any row of the last half-sweep on this handle met a non-positive-definite
  * precision/covariance (np.linalg.cholesky would have raised LinAlgError); synchronises. */
 int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream);

@@ -74,6 +74,23 @@ def _worker(rank, world, port, out):
         emp[0] = torch.tensor([99.0 if rank == 0 else 1.0], dtype=torch.float64).view(torch.int64)[0]
         emp[1] = -1 if rank == 0 else 12
         assert P.winner_from_records(P.gather_winner(emp, world), True) == (1.0, 12)
+        # ---- class-level helpers: sharded criterion evaluation over a pool --------------------
+        class FakeModel:                     # stands in for ActivePMF: scores = i*100 + j
+            unrated = {(1, 2), (3, 4)}
+            def _get_key_vals(self, pool, key, procs, worker_pool):
+                return [100.0 * i + j for i, j in pool]
+            def pred_variance(self, ij):
+                pass
+        FakeModel.pred_variance.chooser = max
+        pool = [(i, j) for i in range(7) for j in range(5)]
+        vals = P.sharded_key_vals(FakeModel(), pool, FakeModel.pred_variance)
+        assert vals == [100.0 * i + j for i, j in pool]
+        assert P.sharded_pick_query_point(FakeModel(), pool, FakeModel.pred_variance) == (6, 4)
+        rows = torch.zeros((11, 3), dtype=torch.float64)
+        lo, hi = P.shard_bounds(11, world, rank)
+        rows[lo:hi] = torch.arange(lo, hi, dtype=torch.float64)[:, None] + 1
+        got = P.all_gather_rows(rows, 11, world)
+        assert torch.equal(got[:, 0], torch.arange(1, 12, dtype=torch.float64))
         out[rank] = 1
     finally:
         dist.destroy_process_group()

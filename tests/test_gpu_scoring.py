@@ -103,3 +103,40 @@ def test_tiled_pool_ties_and_empty(S):
     empty = S.Pool(ii[:0], jj[:0], 5, 40, "f64", 3)
     _, best = empty.score_pred(Ut, Vt)
     assert S.unpack_best(best)[1] == -1
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 2e-5)])
+def test_block_diagonal_view_matches_oracle(S, dtype, tol):
+    """Per-row posterior blocks (cov_uv = NULL): the criterion of candidate (i, j) touches only
+    A_i, B_j and the two mean rows, so it is checked at any scale by giving the oracle a tiny
+    2-row model that holds those blocks (hard parts)."""
+    import torch
+    from active_matrix_factorization_b200 import _native as N
+    from active_matrix_factorization_b200 import device as D
+    rng = np.random.RandomState(3)
+    n, m, d, nc = 50, 40, 10, 2000
+    mu, mv = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    def spd(count):
+        x = rng.normal(size=(count, d, d))
+        return np.einsum("bij,bkj->bik", x, x) / d + np.eye(d) * .1
+    A, B = spd(n), spd(m)
+    ii, jj = rng.randint(0, n, nc), rng.randint(0, m, nc)
+    dt = D.np_dtype(dtype)
+    t = {k: D.to_device(v, dt) for k, v in dict(mu=mu, mv=mv, A=A, B=B).items()}
+    view = N.NormalView(t["mu"].data_ptr(), d, t["mv"].data_ptr(), d,
+                        t["A"].data_ptr(), d * d, d, t["B"].data_ptr(), d * d, d, None, 0, 0, 0)
+    ci, cj = D.to_device(ii, np.int32), D.to_device(jj, np.int32)
+    for crit, cutoff in ((N.CRIT_APPROX_MEAN, 0.), (N.CRIT_PRED_VARIANCE, 0.), (N.CRIT_PROB_GE, 3.5)):
+        sc, best = S.score_device(crit, dtype, ci, cj, d, view=view, cutoff=cutoff)
+        got = sc.double().cpu().numpy()
+        ref = np.empty(nc)
+        for c in range(0, nc, 7):        # the oracle on a 1-user, 1-item model holding the blocks
+            u, v = O.index_maps(1, 1, d)
+            mean = np.concatenate((mu[ii[c]], mv[jj[c]]))
+            cov = np.zeros((2 * d, 2 * d)); cov[:d, :d] = A[ii[c]]; cov[d:, d:] = B[jj[c]]
+            e, var = O.pred_mean_var(u, v, mean, cov, 0, 0)
+            ref[c] = {N.CRIT_APPROX_MEAN: e, N.CRIT_PRED_VARIANCE: var}.get(crit, O.prob_ge_cutoff(e, var, 3.5))
+        sel = np.arange(0, nc, 7)
+        ptol = tol if crit != N.CRIT_PROB_GE else tol * 50
+        np.testing.assert_allclose(got[sel], ref[sel], rtol=ptol, atol=ptol * np.abs(ref[sel]).max())
+        assert S.unpack_best(best)[1] == int(np.argmax(got))

@@ -78,6 +78,11 @@ PROTOTYPES = {
     "amf_pool_destroy": [_P],
     "amf_pool_size": [_P],
     "amf_pool_score_pred": [_P, _INT, _INT, _INT, _P, _P, _P, _INT, _I64, _P, _P],
+    "amf_mn_workspace_doubles": [_I32, _I32, _INT],
+    "amf_mn_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
+                       _P, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],
+    "amf_mn_score_candidates": [_INT, _INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _F64, _P,
+                                _INT, _I64, _P, _P],
     "amf_score_pred_host": [_INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT,
                             C.POINTER(Best)],
 }
@@ -104,7 +109,8 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = _I64 if name in ("amf_ratings_nnz", "amf_normal_workspace_doubles", "amf_pool_size") else _INT
+        fn.restype = _I64 if name in ("amf_ratings_nnz", "amf_normal_workspace_doubles", "amf_pool_size",
+                                   "amf_mn_workspace_doubles") else _INT
     _lib = lib
     return lib
 

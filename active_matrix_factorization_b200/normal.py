@@ -100,3 +100,92 @@ def project_psd_device(mat, min_eig):
     p = fit_params(k, 0, 1, 1., 1., 1., min_eig=min_eig)
     batch = NormalBatch(np.zeros((0, 3)), p, np.zeros((1, k)), mat[None])
     return batch.project()[0]
+
+
+class MnBatch:
+    """B matrix-normal problems MN(mean, Sigma, Omega) sharing one COO rating list (csrc/mn.cu)."""
+
+    def __init__(self, ratings, params, means, sigs, oms, extra=None):
+        self.lib = N.require_device()
+        self.p = params
+        self.nui = params.n + params.m
+        self.d = params.d
+        ratings = np.asarray(ratings, dtype=np.float64).reshape(-1, 3)
+        self.nnz = ratings.shape[0]
+        self.ri = D.to_device(ratings[:, 0], np.int32)
+        self.rj = D.to_device(ratings[:, 1], np.int32)
+        self.rr = D.to_device(ratings[:, 2], np.float64)
+        means = np.ascontiguousarray(means, dtype=np.float64).reshape(-1, self.nui, self.d)
+        self.B = means.shape[0]
+        self.mean = D.to_device(means, np.float64)
+        self.sig = D.to_device(np.ascontiguousarray(sigs, dtype=np.float64).reshape(self.B, self.nui, self.nui), np.float64)
+        self.om = D.to_device(np.ascontiguousarray(oms, dtype=np.float64).reshape(self.B, self.d, self.d), np.float64)
+        if extra is not None:
+            self.ei = D.to_device(extra[0], np.int32)
+            self.ej = D.to_device(extra[1], np.int32)
+            self.er = D.to_device(extra[2], np.float64)
+        else:
+            self.ei = self.ej = self.er = None
+        self.ws = int(self.lib.amf_mn_workspace_doubles(params.n, params.m, params.d))
+        dev = self.mean.device
+        self.work = torch.empty(self.B * self.ws, dtype=torch.float64, device=dev)
+        self.kl = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.steps = torch.zeros(self.B, dtype=torch.int32, device=dev)
+
+    def _run(self, mode, trace=None, entropy=None, totvar=None):
+        N.check(self.lib.amf_mn_batched(
+            mode, self.B, self.nnz, D.ptr(self.ri), D.ptr(self.rj), D.ptr(self.rr),
+            D.ptr(self.ei), D.ptr(self.ej), D.ptr(self.er), C.byref(self.p), D.ptr(self.mean),
+            D.ptr(self.sig), D.ptr(self.om), D.ptr(self.work), D.ptr(self.kl), D.ptr(self.steps),
+            D.ptr(trace), 0 if trace is None else trace.shape[1], D.ptr(entropy), D.ptr(totvar),
+            D.stream_ptr()))
+
+    def kl_divergence(self):
+        self._run(N.NORMAL_KL)
+        return self.kl.cpu().numpy()
+
+    def gradient(self):
+        self._run(N.NORMAL_GRADIENT)
+        w = self.work.view(self.B, self.ws)
+        nd, n2, d2 = self.nui * self.d, self.nui * self.nui, self.d * self.d
+        gm = w[:, :nd].reshape(self.B, self.nui, self.d).cpu().numpy().copy()
+        gs = w[:, 2 * nd:2 * nd + n2].reshape(self.B, self.nui, self.nui).cpu().numpy().copy()
+        o0 = 2 * nd + 5 * n2
+        go = w[:, o0:o0 + d2].reshape(self.B, self.d, self.d).cpu().numpy().copy()
+        return gm, gs, go
+
+    def fit(self, trace_len=0, want_entropy=False, want_totvar=False):
+        dev = self.mean.device
+        trace = torch.full((self.B, trace_len), float('nan'), dtype=torch.float64, device=dev) \
+            if trace_len else None
+        ent = torch.zeros(self.B, dtype=torch.float64, device=dev) if want_entropy else None
+        tv = torch.zeros(self.B, dtype=torch.float64, device=dev) if want_totvar else None
+        self._run(N.NORMAL_FIT, trace, ent, tv)
+        out = dict(kl=self.kl.cpu().numpy(), steps=self.steps.cpu().numpy())
+        if trace is not None:
+            out['trace'] = trace.cpu().numpy()
+        if ent is not None:
+            out['entropy'] = ent.cpu().numpy()
+        if tv is not None:
+            out['total_variance'] = tv.cpu().numpy()
+        return out
+
+    def state(self):
+        return self.mean.cpu().numpy(), self.sig.cpu().numpy(), self.om.cpu().numpy()
+
+
+def mn_score(criterion, mean, sig, om, n, m, d, ii, jj, name="f64", cutoff=0.0, maximize=True):
+    """criteria over candidates under MN(mean, Sigma, Omega); returns (scores, (best, index))"""
+    from . import scoring as S
+    lib = N.require_device()
+    dt = D.np_dtype(name)
+    mean_t, sig_t, om_t = D.to_device(mean, dt), D.to_device(sig, dt), D.to_device(om, dt)
+    ci, cj = S._cands(ii, jj)
+    nc = int(ci.numel())
+    scores = torch.empty(nc, dtype=D.torch_dtype(name), device=ci.device)
+    best = torch.empty(2, dtype=torch.int64, device=ci.device)
+    N.check(lib.amf_mn_score_candidates(criterion, D.code(name), nc, D.ptr(ci), D.ptr(cj), n, m, d,
+                                        D.ptr(mean_t), D.ptr(sig_t), D.ptr(om_t), float(cutoff),
+                                        D.ptr(scores), 1 if maximize else 0, 0, D.ptr(best),
+                                        D.stream_ptr()))
+    return scores.to(torch.float64).cpu().numpy(), S.unpack_best(best)

@@ -244,6 +244,31 @@ int amf_normal_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const 
                        double* kl_trace_d, int trace_len, double* entropy_out_d,
                        double* totvar_out_d, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Matrix-normal approximation MN(mean, Sigma, Omega) (the variant the
+ * reference's drugbank / movielens runs use): matrix_normal_exps_cy.pyx:159-216
+ * mn_kl_divergence, :219-485 matrixnormal_gradient, mn_active_pmf.py:242-288 fit_normal_kls,
+ * :513-521 _approx_entropy, :597-598 _total_variance and the lookahead of :627-697.
+ * mean (B, N+M, d), sig (B, N+M, N+M), om (B, d, d), all fp64; same batching and parameter
+ * struct as amf_normal_batched.  Modes: AMF_NORMAL_FIT, AMF_NORMAL_KL, AMF_NORMAL_GRADIENT
+ * (gradient outputs in work_b: d/dmean at [0, nui*d), d/dSigma at [2*nui*d, +nui*nui),
+ * d/dOmega at [2*nui*d + 5*nui*nui, +d*d), nui = N+M).
+ * ------------------------------------------------------------------------------------------ */
+int64_t amf_mn_workspace_doubles(int32_t n, int32_t m, int d);
+int amf_mn_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const int32_t* rj_d,
+                   const double* rr_d, const int32_t* extra_i_d, const int32_t* extra_j_d,
+                   const double* extra_r_d, const amf_normal_fit_params_t* p, double* mean_d,
+                   double* sig_d, double* om_d, double* work_d, double* kl_out_d,
+                   int32_t* steps_out_d, double* kl_trace_d, int trace_len, double* entropy_out_d,
+                   double* totvar_out_d, void* stream);
+/* AMF_CRIT_APPROX_MEAN / _PRED_VARIANCE / _PROB_GE under the matrix-normal approximation
+ * (mn_active_pmf.py:300-315, :431-438, :505-511): per candidate only Sigma[i,i], Sigma[j,j],
+ * Sigma[i,j], the two mean rows and Omega are read. */
+int amf_mn_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t* ci_d,
+                            const int32_t* cj_d, int32_t n, int32_t m, int d, const void* mean_d,
+                            const void* sig_d, const void* om_d, double cutoff, void* scores_d,
+                            int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

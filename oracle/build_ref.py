@@ -50,6 +50,17 @@ PATCHES = {
         (r"evals\[list\(zip\(\*pool\)\)\]", "evals[tuple(zip(*pool))]"),       # 5
         (r"scipy\.integrate\.simps", "scipy.integrate.simpson"),               # 8
     ],
+    # the matrix-normal variant the reference runs on drugbank / movielens
+    "matrix_normal_exps_cy.pyx": [
+        (r"DTYPE = np\.float\b", "DTYPE = np.float64"),                       # 1
+    ],
+    "mn_active_pmf.py": [
+        (r"np\.array\(self\.ratings, dtype=float, copy=False\)",
+         "np.asarray(self.ratings, dtype=float)"),                             # 3
+        (r"evals\[list\(zip\(\*pool\)\)\]", "evals[tuple(zip(*pool))]"),       # 5
+        (r"scipy\.integrate\.simps", "scipy.integrate.simpson"),               # 8
+        (r"import scipy\.integrate", "import scipy.integrate\nimport scipy.linalg"),
+    ],
     # pure-python twins, only used by the reference's own known-answer test
     "normal_exps.py": [
         (r"for i, j, rating in apmf\.ratings:",
@@ -66,6 +77,7 @@ setup(
     include_dirs=[np.get_include()],
     ext_modules=[
         Extension("normal_exps_cy", ["normal_exps_cy.c"]),
+        Extension("matrix_normal_exps_cy", ["matrix_normal_exps_cy.c"]),
         Extension("pmf_cy", ["pmf_cy.c"]),
         Extension("bayes_pmf", ["bayes_pmf.c"]),
     ],
@@ -76,7 +88,7 @@ setup(
 def built():
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
     return all(os.path.exists(os.path.join(OUT, m + suffix))
-               for m in ("pmf_cy", "normal_exps_cy", "bayes_pmf"))
+               for m in ("pmf_cy", "normal_exps_cy", "matrix_normal_exps_cy", "bayes_pmf"))
 
 
 def build(force=False):
@@ -100,6 +112,7 @@ def build(force=False):
     cy = [sys.executable, "-m", "cython", "-3"]
     subprocess.check_call(cy + ["pmf_cy.pyx"], cwd=OUT, env=env)
     subprocess.check_call(cy + ["normal_exps_cy.pyx"], cwd=OUT, env=env)
+    subprocess.check_call(cy + ["matrix_normal_exps_cy.pyx"], cwd=OUT, env=env)
     subprocess.check_call(cy + ["-Xbinding=false", "bayes_pmf.py"], cwd=OUT, env=env)
     subprocess.check_call([sys.executable, "setup_ref.py"], cwd=OUT, env=env)
     shutil.rmtree(os.path.join(OUT, "build"), ignore_errors=True)

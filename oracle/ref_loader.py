@@ -30,7 +30,8 @@ def load():
     class NS:
         pass
     ns = NS()
-    for name in ("pmf_cy", "normal_exps_cy", "active_pmf", "bayes_pmf"):
+    for name in ("pmf_cy", "normal_exps_cy", "matrix_normal_exps_cy", "active_pmf",
+                 "mn_active_pmf", "bayes_pmf"):
         mod = importlib.import_module(name)
         if not os.path.abspath(mod.__file__).startswith(REF_DIR):
             raise ImportError("%s resolved to %s, not oracle/_ref" % (name, mod.__file__))

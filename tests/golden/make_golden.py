@@ -199,8 +199,54 @@ def case_gibbs():
     save("gibbs_15x12_d3", **out)
 
 
+# ---- case 6: matrix-normal posterior -----------------------------------
+def case_matrix_normal():
+    MN = ref.mn_active_pmf.MNActivePMF
+    mn_grad = ref.matrix_normal_exps_cy.matrixnormal_gradient
+    import contextlib, io
+    out = {}
+    # (a) d = 3, random SPD Sigma / Omega: KL, gradient, criteria
+    n, m, d = 9, 11, 3
+    rng, R, users, items = random_problem(17, n, m, d, 45, values=(1., 2., 3., 4., 5.))
+    a = MN(R, d)
+    a.users, a.items = users.copy(), items.copy()
+    a.sigma_sq, a.sigma_u_sq, a.sigma_v_sq = 0.8, 5.0, 12.0
+    a.initialize_approx()
+    s1, s2 = rng.normal(size=(n + m, n + m)), rng.normal(size=(d, d))
+    a.mean = a.mean + rng.normal(0, .1, a.mean.shape)
+    a.cov_useritems = s1 @ s1.T / (n + m) + np.eye(n + m) * .5
+    a.cov_latents = s2 @ s2.T / d + np.eye(d) * .3
+    gm, gs, go = mn_grad(a)
+    ii, jj = all_cells(n, m)
+    mv = np.array([a.approx_pred_mean_var(i, j) for i, j in zip(ii, jj)])
+    out.update(a_ratings=R, a_users=users, a_items=items, a_mean=a.mean, a_sig=a.cov_useritems,
+               a_om=a.cov_latents, a_hyp=np.array([a.sigma_sq, a.sigma_u_sq, a.sigma_v_sq]),
+               a_kl=a.kl_divergence(), a_gm=gm, a_gs=gs, a_go=go, a_cand_i=ii, a_cand_j=jj,
+               a_pred_mean=mv[:, 0], a_pred_var=mv[:, 1],
+               a_prob_ge_3_5=np.array([a.prob_ge_3_5((i, j)) for i, j in zip(ii, jj)]),
+               a_entropy=a._approx_entropy())
+    # (b) toy fit + lookahead from the identity initialisation (deterministic)
+    n, m, d = 5, 6, 2
+    rng, R, users, items = random_problem(23, n, m, d, 12, values=(0., 1.), scale=.7)
+    b = MN(R, d, rating_values={0, 1}, discrete_expectations=True)
+    b.users, b.items = users.copy(), items.copy()
+    b.fit()
+    b.initialize_approx()
+    kls = list(b.fit_normal_kls())
+    cand = sorted(b.unrated)
+    ci, cj = np.array(cand).T
+    out.update(b_ratings=R, b_users=b.users, b_items=b.items, b_kls=np.array(kls), b_mean=b.mean,
+               b_sig=b.cov_useritems, b_om=b.cov_latents, b_cand_i=ci, b_cand_j=cj,
+               b_pred_var=np.array([b.pred_variance(c) for c in cand]),
+               b_entropy=b._approx_entropy(), b_total_variance=b._total_variance())
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["b_uv_entropy"] = np.array([b.exp_approx_entropy(c) for c in cand[:6]])
+        out["b_exp_total_variance"] = np.array([b.exp_total_variance(c) for c in cand[:6]])
+    save("matrix_normal", **out)
+
+
 if __name__ == "__main__":
     cases = dict(known_answer=case_known_answer, d5=case_d5, fit=case_fit,
-                 lookahead=case_lookahead, gibbs=case_gibbs)
+                 lookahead=case_lookahead, gibbs=case_gibbs, matrix_normal=case_matrix_normal)
     for name in (sys.argv[1:] or list(cases)):
         cases[name]()

@@ -56,17 +56,21 @@ __device__ __forceinline__ double mn_e2_k(const double* mu, const double* mv, co
 }
 
 __device__ double mn_kl(const MnProblem& P, const double* mean, const double* sig,
-                        const double* om, double* wsig, double* wom, double* red, int* flag) {
+                        const double* om, double* wsig, double* wom, double* red, int* flag,
+                        bool dense = true) {
   const int d = P.d, nui = P.nui, nu = P.n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  // entropy term
-  for (int t = tid; t < nui * nui; t += nt) wsig[t] = sig[t];
-  for (int t = tid; t < d * d; t += nt) wom[t] = om[t];
-  __syncthreads();
-  const double ld_sig = blk_cholesky(wsig, nui, red, flag);
-  const double ld_om = blk_cholesky(wom, d, red, flag);
-  double kl = -(ld_sig * d + ld_om * nui) / 2.;
+  // entropy term (skipped when the caller does the dense algebra itself)
+  double kl = 0;
+  if (dense) {
+    for (int t = tid; t < nui * nui; t += nt) wsig[t] = sig[t];
+    for (int t = tid; t < d * d; t += nt) wom[t] = om[t];
+    __syncthreads();
+    const double ld_sig = blk_cholesky(wsig, nui, red, flag);
+    const double ld_om = blk_cholesky(wom, d, red, flag);
+    kl = -(ld_sig * d + ld_om * nui) / 2.;
+  }
   // prior terms (quirks: no item trace, sigma_u_sq twice)
   double tr_om = 0;
   for (int k = 0; k < d; ++k) tr_om += om[k * d + k];
@@ -95,7 +99,8 @@ __device__ double mn_kl(const MnProblem& P, const double* mean, const double* si
 
 __device__ void mn_grad(const MnProblem& P, const double* mean, const double* sig,
                         const double* om, double* gm, double* gs, double* go, double* w1,
-                        double* w2, double* wo1, double* wo2, double* red, int* flag) {
+                        double* w2, double* wo1, double* wo2, double* red, int* flag,
+                        bool dense = true) {
   const int d = P.d, nui = P.nui, nu = P.n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -180,6 +185,7 @@ __device__ void mn_grad(const MnProblem& P, const double* mean, const double* si
     gs[(int64_t)t * nui + t] += tr_om / (2 * (t < nu ? P.sigma_u_sq : P.sigma_v_sq));
   for (int t = tid; t < d; t += nt)
     go[t * d + t] += su / (2 * P.sigma_u_sq) + sv / (2 * P.sigma_v_sq);
+  if (!dense) { __syncthreads(); return; }
   // entropy terms: g -= scale/2 * (inv + inv' o (1 - I))   (pyx:475-485)
   for (int t = tid; t < nui * nui; t += nt) w1[t] = sig[t];
   for (int t = tid; t < d * d; t += nt) wo1[t] = om[t];
@@ -265,13 +271,13 @@ __global__ void __launch_bounds__(MN_THREADS) mn_fit_kernel(MnArgs a) {
     double* go = w3 + n2;  double* nom = go + d2;
     double* wo1 = nom + d2;  double* wo2 = wo1 + d2;  double* wo3 = wo2 + d2;
 
-    if (a.mode == 1) {
-      const double kl = mn_kl(P, mean, sig, om, w1, wo1, red, &flag);
+    if (a.mode == 1 || a.mode == 4) {
+      const double kl = mn_kl(P, mean, sig, om, w1, wo1, red, &flag, a.mode == 1);
       if (tid == 0) a.kl_out[b] = kl;
       continue;
     }
-    if (a.mode == 2) {
-      mn_grad(P, mean, sig, om, gm, gs, go, w1, w2, wo1, wo2, red, &flag);
+    if (a.mode == 2 || a.mode == 5) {
+      mn_grad(P, mean, sig, om, gm, gs, go, w1, w2, wo1, wo2, red, &flag, a.mode == 2);
       continue;
     }
     double lr = a.lr0;
@@ -402,10 +408,10 @@ int amf_mn_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const int3
                    int32_t* steps_out_d, double* kl_trace_d, int trace_len, double* entropy_out_d,
                    double* totvar_out_d, void* stream) {
   AMF_REQUIRE(p && mean_d && sig_d && om_d && work_d, "amf_mn_batched: NULL argument");
-  AMF_REQUIRE(mode >= 0 && mode <= 2, "amf_mn_batched: bad mode %d", mode);
+  AMF_REQUIRE((mode >= 0 && mode <= 2) || mode == 4 || mode == 5, "amf_mn_batched: bad mode %d", mode);
   AMF_REQUIRE(B >= 0 && nnz >= 0 && p->n > 0 && p->m > 0 && p->d > 0, "amf_mn_batched: bad sizes");
   AMF_REQUIRE(mode != 0 || (kl_out_d && steps_out_d), "amf_mn_batched: fit needs kl_out/steps_out");
-  AMF_REQUIRE(mode != 1 || kl_out_d, "amf_mn_batched: kl mode needs kl_out");
+  AMF_REQUIRE((mode != 1 && mode != 4) || kl_out_d, "amf_mn_batched: kl mode needs kl_out");
   if (B == 0) return AMF_OK;
   const int64_t nui = (int64_t)p->n + p->m;
   AMF_REQUIRE(nui * nui < (1ll << 31), "amf_mn_batched: N+M=%lld too large", (long long)nui);

@@ -34,6 +34,11 @@ class MNActivePMFEvaluator(_apmf.ActivePMFEvaluator):
 
 
 class MNActivePMF(ActivePMF):
+    # problems with more than this many rows in Sigma use the host-driven "wide" fit (cuSOLVER
+    # for the (N+M)^2 algebra) instead of the one-CTA-per-problem kernel
+    wide_threshold = 96
+    max_normal_steps = 0      # > 0 caps the accepted steps of one fit_normal (0: to convergence)
+
     def __init__(self, rating_tuples, latent_d=1, rating_values=None,
                  discrete_expectations=False, refit_lookahead=False, knowable=None,
                  fit_type=('batch',)):
@@ -92,8 +97,17 @@ class MNActivePMF(ActivePMF):
     def fit_normal_kls(self):
         '''(mn_active_pmf.py:242-288) one launch; the KL of each accepted step is yielded after'''
         self._require_approx()
-        batch = _normal.MnBatch(self.ratings, self._fit_params(), self.mean[None],
-                                self.cov_useritems[None], self.cov_latents[None])
+        if self.num_users + self.num_items > self.wide_threshold:
+            wide = _normal.MnWide(self.ratings, self._fit_params(), self.mean, self.cov_useritems,
+                                  self.cov_latents)
+            mean, sig, om, kls = wide.fit(max_steps=self.max_normal_steps)
+            if kls:
+                self.mean, self.cov_useritems, self.cov_latents = mean, sig, om
+            for kl in kls:
+                yield float(kl)
+            return
+        batch = _normal.MnBatch(self.ratings, self._fit_params(max_steps=self.max_normal_steps),
+                                self.mean[None], self.cov_useritems[None], self.cov_latents[None])
         trace_len = 1 << 16
         res = batch.fit(trace_len=trace_len)
         steps = int(res['steps'][0])
@@ -140,6 +154,9 @@ class MNActivePMF(ActivePMF):
             return np.array([self._refit_one_host_driven(i, j, v, what) for i, j, v in pairs_vals])
         if what == 'pred_entropy_bound':
             self._pred_entropy_bound()
+        if self.num_users + self.num_items > self.wide_threshold:
+            # large Sigma: each re-fit is one wide (host-driven) fit
+            return np.array([self._refit_one_wide(i, j, v, what) for i, j, v in pairs_vals])
         ei = np.array([p[0] for p in pairs_vals], dtype=np.int32)
         ej = np.array([p[1] for p in pairs_vals], dtype=np.int32)
         er = np.array([p[2] for p in pairs_vals], dtype=np.float64)
@@ -166,6 +183,21 @@ class MNActivePMF(ActivePMF):
                     out[s + b] = self._criterion_on((mean[b], sig[b], om[b]), None, what,
                                                     (int(ei[s + b]), int(ej[s + b])), er[s + b])
         return out
+
+    def _refit_one_wide(self, i, j, v, what):
+        r2 = np.append(self.ratings, [[i, j, v]], 0)
+        wide = _normal.MnWide(r2, self._fit_params(), self.mean, self.cov_useritems, self.cov_latents)
+        mean, sig, om, _ = wide.fit(max_steps=self.max_normal_steps)
+        if what == 'entropy':
+            su, lu = _apmf._slogdet(sig)
+            sl, ll = _apmf._slogdet(om)
+            return 0.5 * (self.latent_d * lu + (self.num_users + self.num_items) * ll)
+        if what == 'total_variance':
+            ii, jj = self._all_cells()
+            var, _ = _normal.mn_score(N.CRIT_PRED_VARIANCE, mean, sig, om, self.num_users,
+                                      self.num_items, self.latent_d, ii, jj)
+            return float(var.sum())
+        return self._criterion_on((mean, sig, om), None, what, (i, j), v)
 
     def _criterion_on(self, state, _unused, what, ij, v):
         mean, sig, om = state

@@ -189,3 +189,92 @@ def mn_score(criterion, mean, sig, om, n, m, d, ii, jj, name="f64", cutoff=0.0, 
                                         D.ptr(scores), 1 if maximize else 0, 0, D.ptr(best),
                                         D.stream_ptr()))
     return scores.to(torch.float64).cpu().numpy(), S.unpack_best(best)
+
+
+class MnWide:
+    """One LARGE matrix-normal problem (N+M in the hundreds or thousands): the line search of
+    mn_active_pmf.py:242-288 driven from the host, with the rating/prior terms from csrc/mn.cu
+    (sparse modes) and the (N+M)^2 dense algebra -- eigendecomposition for project_psd, Cholesky
+    for log-det and inverse -- done grid-wide by cuSOLVER through torch.  The single-CTA kernel
+    is the right tool for thousands of small lookahead problems, not for one big one."""
+
+    MN_KL_SPARSE, MN_GRADIENT_SPARSE = 4, 5
+
+    def __init__(self, ratings, params, mean, sig, om):
+        self.b = MnBatch(ratings, params, mean[None], sig[None], om[None])
+        self.p = params
+        self.nui, self.d = self.b.nui, self.b.d
+
+    @staticmethod
+    def _logdet(mat):
+        chol, info = torch.linalg.cholesky_ex(mat)
+        if int(info.item()) != 0:
+            return None, None
+        return 2.0 * torch.log(torch.diagonal(chol)).sum(), chol
+
+    def kl(self, mean, sig, om):
+        b = self.b
+        b.mean, b.sig, b.om = mean.reshape(1, self.nui, self.d), sig.reshape(1, self.nui, self.nui), om.reshape(1, self.d, self.d)
+        b._run(self.MN_KL_SPARSE)
+        ls, _ = self._logdet(sig)
+        lo, _ = self._logdet(om)
+        if ls is None or lo is None:
+            return float('nan')
+        return float((b.kl[0] - (ls * self.d + lo * self.nui) / 2.0).item())
+
+    def gradient(self, mean, sig, om):
+        b = self.b
+        b.mean, b.sig, b.om = mean.reshape(1, self.nui, self.d), sig.reshape(1, self.nui, self.nui), om.reshape(1, self.d, self.d)
+        b._run(self.MN_GRADIENT_SPARSE)
+        w = b.work.view(1, b.ws)
+        nd, n2, d2 = self.nui * self.d, self.nui * self.nui, self.d * self.d
+        gm = w[0, :nd].reshape(self.nui, self.d).clone()
+        gs = w[0, 2 * nd:2 * nd + n2].reshape(self.nui, self.nui).clone()
+        o0 = 2 * nd + 5 * n2
+        go = w[0, o0:o0 + d2].reshape(self.d, self.d).clone()
+        for g, mat, scale in ((gs, sig, self.d / 2.0), (go, om, self.nui / 2.0)):
+            inv = torch.linalg.inv(mat)
+            eye = torch.eye(mat.shape[0], dtype=mat.dtype, device=mat.device)
+            g -= scale * (inv + inv.T * (1 - eye))
+        return gm, gs, go
+
+    @staticmethod
+    def project(mat, min_eig):
+        mat = (mat + mat.T) / 2
+        w, q = torch.linalg.eigh(mat)
+        if float(w.min().item()) < min_eig:
+            mat = (q * torch.clamp(w, min=min_eig)) @ q.T
+            mat = (mat + mat.T) / 2
+        return mat
+
+    def fit(self, max_steps=0, callback=None):
+        """Returns (mean, sig, om, [kl per accepted step]) as host arrays."""
+        p = self.p
+        mean, sig, om = self.b.mean[0].clone(), self.b.sig[0].clone(), self.b.om[0].clone()
+        lr = p.learning_rate
+        old = self.kl(mean, sig, om)
+        kls, done = [], False
+        while not done:
+            gm, gs, go = self.gradient(mean, sig, om)
+            while True:
+                nm = mean - lr * gm
+                ns = self.project(sig - lr * gs, p.min_eig)
+                no = self.project(om - lr * go, p.min_eig)
+                new = self.kl(nm, ns, no)
+                if new < old:
+                    mean, sig, om = nm, ns, no
+                    lr *= 1.25
+                    if old - new < p.kl_stop:
+                        done = True
+                    kls.append(new)
+                    if callback is not None:
+                        callback(new)
+                    old = new
+                    break
+                lr *= .5
+                if lr < p.min_lr:
+                    done = True
+                    break
+            if max_steps and len(kls) >= max_steps:
+                break
+        return mean.cpu().numpy(), sig.cpu().numpy(), om.cpu().numpy(), kls

@@ -252,8 +252,12 @@ int amf_normal_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const 
  * mean (B, N+M, d), sig (B, N+M, N+M), om (B, d, d), all fp64; same batching and parameter
  * struct as amf_normal_batched.  Modes: AMF_NORMAL_FIT, AMF_NORMAL_KL, AMF_NORMAL_GRADIENT
  * (gradient outputs in work_b: d/dmean at [0, nui*d), d/dSigma at [2*nui*d, +nui*nui),
- * d/dOmega at [2*nui*d + 5*nui*nui, +d*d), nui = N+M).
+ * d/dOmega at [2*nui*d + 5*nui*nui, +d*d), nui = N+M).  Modes AMF_MN_KL_SPARSE (4) and
+ * AMF_MN_GRADIENT_SPARSE (5) leave out the log-det / inverse terms so that a caller with one
+ * large problem can do that dense algebra grid-wide (cuSOLVER) instead of inside one CTA.
  * ------------------------------------------------------------------------------------------ */
+#define AMF_MN_KL_SPARSE 4
+#define AMF_MN_GRADIENT_SPARSE 5
 int64_t amf_mn_workspace_doubles(int32_t n, int32_t m, int d);
 int amf_mn_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const int32_t* rj_d,
                    const double* rr_d, const int32_t* extra_i_d, const int32_t* extra_j_d,

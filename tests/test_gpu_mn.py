@@ -82,3 +82,21 @@ def test_mn_driver_two_steps(M):
     for k in ('pred-variance', 'prob-ge-.5'):
         assert len(res[k]) == 3 and res[k][2][0] == len(ratings) + 2
         assert res[k][1][4].shape == (6, 6)
+
+
+def test_mn_wide_path_matches_batched_kernel(M, golden):
+    """the host-driven wide fit (cuSOLVER dense algebra + sparse-mode kernels) walks the same
+    line search as the one-CTA kernel and the reference"""
+    g = golden("matrix_normal")
+    b = M.MNActivePMF(g["b_ratings"], 2, rating_values={0, 1}, discrete_expectations=True)
+    b.users, b.items = g["b_users"].copy(), g["b_items"].copy()
+    b.wide_threshold = 0
+    b.initialize_approx()
+    kls = list(b.fit_normal_kls())
+    assert len(kls) == len(g["b_kls"])
+    np.testing.assert_allclose(kls, g["b_kls"], rtol=1e-8)
+    np.testing.assert_allclose(b.cov_useritems, g["b_sig"], rtol=1e-6, atol=1e-8)
+    pool = list(zip(g["b_cand_i"].tolist(), g["b_cand_j"].tolist()))
+    b.mean, b.cov_useritems, b.cov_latents = g["b_mean"].copy(), g["b_sig"].copy(), g["b_om"].copy()
+    ent = np.array(b._get_key_vals(pool[:2], M.MNActivePMF.exp_approx_entropy, None, None))
+    np.testing.assert_allclose(ent, g["b_uv_entropy"][:2], rtol=1e-5)

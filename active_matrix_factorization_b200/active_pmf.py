@@ -527,13 +527,22 @@ class ActivePMF(ProbabilisticMatrixFactorization):
     def _get_key_vals(self, pool, key, procs=None, worker_pool=None):
         '''Criterion value for every pair of `pool`, aligned with its iteration order
         (active_pmf.py:739-770) -- evaluated in batched GPU launches.'''
-        pool = list(pool)
-        if not pool:
-            return []
         name = getattr(key, '__name__', None)
+        if isinstance(pool, np.ndarray) and pool.ndim == 2 and pool.shape[1] == 2:
+            # array pools (large candidate sets) skip the per-tuple Python work
+            if pool.shape[0] == 0:
+                return []
+            ii = np.ascontiguousarray(pool[:, 0], dtype=np.int32)
+            jj = np.ascontiguousarray(pool[:, 1], dtype=np.int32)
+            if name not in ('pred', 'pred_variance', 'prob_ge_3_5', 'prob_ge_half'):
+                pool = [(int(i), int(j)) for i, j in pool]
+        else:
+            pool = list(pool)
+            if not pool:
+                return []
+            ii, jj = zip(*pool) if name != 'random_weighting' else ((), ())
         if name == 'random_weighting':
-            return [random.random() for _ in pool]
-        ii, jj = zip(*pool)
+            return [random.random() for _ in range(len(pool))]
         if name == 'pred':
             vals, _ = _scoring.score_pred(self.users, self.items, ii, jj, self.dtype_name)
             return vals.tolist()

@@ -241,6 +241,7 @@ struct MnArgs {
   double* kl_trace; int trace_len;
   double *entropy_out, *totvar_out;
   int mode;
+  bool smem_state;
 };
 
 __host__ __device__ inline int64_t mn_workspace(int64_t nui, int64_t d) {
@@ -261,10 +262,23 @@ __global__ void __launch_bounds__(MN_THREADS) mn_fit_kernel(MnArgs a) {
     P.sigma_sq = a.sigma_sq; P.sigma_u_sq = a.sigma_u_sq; P.sigma_v_sq = a.sigma_v_sq;
     const int nui = P.nui, d = P.d;
     const int64_t n2 = (int64_t)nui * nui, d2 = (int64_t)d * d, nd = (int64_t)nui * d;
-    double* mean = a.mean + b * nd;
-    double* sig = a.sig + b * n2;
-    double* om = a.om + b * d2;
-    double* W = a.work + b * mn_workspace(nui, d);
+    double* mean_g = a.mean + b * nd;
+    double* sig_g = a.sig + b * n2;
+    double* om_g = a.om + b * d2;
+    // small problems keep the state and all work matrices in shared memory (see normal.cu)
+    const bool in_smem = a.smem_state;
+    const int64_t kmax_ = nui > d ? nui : d;
+    double* S = sh + blk_scratch_doubles(kmax_);
+    double* mean = in_smem ? S : mean_g;
+    double* sig = in_smem ? S + nd : sig_g;
+    double* om = in_smem ? S + nd + n2 : om_g;
+    double* W = in_smem ? S + nd + n2 + d2 : a.work + b * mn_workspace(nui, d);
+    if (in_smem) {
+      for (int t = tid; t < nd; t += nt) mean[t] = mean_g[t];
+      for (int64_t t = tid; t < n2; t += nt) sig[t] = sig_g[t];
+      for (int t = tid; t < d2; t += nt) om[t] = om_g[t];
+      __syncthreads();
+    }
     double* gm = W;  double* nmean = W + nd;
     double* gs = W + 2 * nd;  double* nsig = gs + n2;
     double* w1 = nsig + n2;  double* w2 = w1 + n2;  double* w3 = w2 + n2;
@@ -278,6 +292,13 @@ __global__ void __launch_bounds__(MN_THREADS) mn_fit_kernel(MnArgs a) {
     }
     if (a.mode == 2 || a.mode == 5) {
       mn_grad(P, mean, sig, om, gm, gs, go, w1, w2, wo1, wo2, red, &flag, a.mode == 2);
+      if (in_smem) {            // the caller reads the gradient from the global workspace
+        double* Wg = a.work + b * mn_workspace(nui, d);
+        for (int t = tid; t < nd; t += nt) Wg[t] = gm[t];
+        for (int64_t t = tid; t < n2; t += nt) Wg[2 * nd + t] = gs[t];
+        for (int t = tid; t < d2; t += nt) Wg[2 * nd + 5 * n2 + t] = go[t];
+        __syncthreads();
+      }
       continue;
     }
     double lr = a.lr0;
@@ -314,6 +335,11 @@ __global__ void __launch_bounds__(MN_THREADS) mn_fit_kernel(MnArgs a) {
       if (a.max_steps > 0 && steps >= a.max_steps) break;
     }
     if (tid == 0) { a.kl_out[b] = old_kl; a.steps_out[b] = steps; }
+    if (in_smem) {
+      for (int t = tid; t < nd; t += nt) mean_g[t] = mean[t];
+      for (int64_t t = tid; t < n2; t += nt) sig_g[t] = sig[t];
+      for (int t = tid; t < d2; t += nt) om_g[t] = om[t];
+    }
     if (a.entropy_out) {
       for (int64_t t = tid; t < n2; t += nt) w1[t] = sig[t];
       for (int t = tid; t < d2; t += nt) wo1[t] = om[t];
@@ -425,7 +451,13 @@ int amf_mn_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const int3
   a.steps_out = steps_out_d; a.kl_trace = kl_trace_d; a.trace_len = trace_len;
   a.entropy_out = entropy_out_d; a.totvar_out = totvar_out_d; a.mode = mode;
   const int64_t kmax = nui > p->d ? nui : p->d;
-  const size_t smem = sizeof(double) * (32 + 2 * (kmax / 2 + 2));
+  size_t smem = sizeof(double) * (size_t)blk_scratch_doubles(kmax);
+  const size_t state = sizeof(double) * (size_t)(nui * p->d + nui * nui + (int64_t)p->d * p->d +
+                                                mn_workspace(nui, p->d));
+  a.smem_state = smem + state <= 200 * 1024;
+  if (a.smem_state) smem += state;
+  AMF_CUDA(cudaFuncSetAttribute(mn_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
   mn_fit_kernel<<<B, MN_THREADS, smem, (cudaStream_t)stream>>>(a);
   AMF_LAUNCH_CHECK();
   return AMF_OK;

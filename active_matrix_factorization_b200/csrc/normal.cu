@@ -248,6 +248,7 @@ struct FitArgs {
   double* entropy_out; // B or NULL : slogdet(cov) after the fit
   double* totvar_out;  // B or NULL : total predictive variance after the fit
   int mode;            // 0 fit, 1 kl only, 2 gradient only (grad -> work), 3 project only
+  bool smem_state;     // state + work matrices live in shared memory (small k)
 };
 
 __device__ NormalProblem make_problem(const FitArgs& a, int b) {
@@ -269,9 +270,21 @@ __global__ void __launch_bounds__(NRM_THREADS) normal_fit_kernel(FitArgs a) {
     const NormalProblem P = make_problem(a, b);
     const int k = P.k;
     const int64_t kk2 = (int64_t)k * k;
-    double* mean = a.mean + (int64_t)b * k;
-    double* cov = a.cov + (int64_t)b * kk2;
-    double* W = a.work + (int64_t)b * (2 * k + 5 * kk2);
+    double* mean_g = a.mean + (int64_t)b * k;
+    double* cov_g = a.cov + (int64_t)b * kk2;
+    // Small problems (the lookahead batches) keep the state and all work matrices in shared
+    // memory: every Jacobi / Cholesky phase is then a shared-memory round trip instead of an L2
+    // one.  Larger k falls back to the per-problem global workspace.
+    const bool in_smem = a.smem_state;
+    double* S = sh + blk_scratch_doubles(k);
+    double* mean = in_smem ? S : mean_g;
+    double* cov = in_smem ? S + k : cov_g;
+    double* W = in_smem ? S + k + kk2 : a.work + (int64_t)b * (2 * k + 5 * kk2);
+    if (in_smem) {
+      for (int t = tid; t < k; t += nt) mean[t] = mean_g[t];
+      for (int64_t t = tid; t < kk2; t += nt) cov[t] = cov_g[t];
+      __syncthreads();
+    }
     double* gm = W;               // k
     double* nmean = W + k;        // k
     double* gc = W + 2 * k;       // k*k
@@ -287,10 +300,20 @@ __global__ void __launch_bounds__(NRM_THREADS) normal_fit_kernel(FitArgs a) {
     }
     if (a.mode == 2) {
       kl_gradient(P, mean, cov, gm, gc, w1, w2, red, &flag);
+      if (in_smem) {            // the caller reads the gradient from the global workspace
+        double* Wg = a.work + (int64_t)b * (2 * k + 5 * kk2);
+        for (int t = tid; t < k; t += nt) Wg[t] = gm[t];
+        for (int64_t t = tid; t < kk2; t += nt) Wg[2 * k + t] = gc[t];
+        __syncthreads();
+      }
       continue;
     }
     if (a.mode == 3) {
       blk_project_psd(cov, k, a.min_eig, w1, w2, cs, red);
+      if (in_smem) {
+        for (int64_t t = tid; t < kk2; t += nt) cov_g[t] = cov[t];
+        __syncthreads();
+      }
       continue;
     }
 
@@ -325,6 +348,10 @@ __global__ void __launch_bounds__(NRM_THREADS) normal_fit_kernel(FitArgs a) {
       if (a.max_steps > 0 && steps >= a.max_steps) break;
     }
     if (tid == 0) { a.kl_out[b] = old_kl; a.steps_out[b] = steps; }
+    if (in_smem) {
+      for (int t = tid; t < k; t += nt) mean_g[t] = mean[t];
+      for (int64_t t = tid; t < kk2; t += nt) cov_g[t] = cov[t];
+    }
     if (a.entropy_out) {
       for (int64_t t = tid; t < kk2; t += nt) w1[t] = cov[t];
       __syncthreads();
@@ -375,7 +402,12 @@ int amf_normal_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const 
   a.mean = mean_d; a.cov = cov_d; a.work = work_d; a.kl_out = kl_out_d; a.steps_out = steps_out_d;
   a.kl_trace = kl_trace_d; a.trace_len = trace_len; a.entropy_out = entropy_out_d;
   a.totvar_out = totvar_out_d; a.mode = mode;
-  const size_t smem = sizeof(double) * (32 + 2 * (k / 2 + 2));
+  size_t smem = sizeof(double) * (size_t)blk_scratch_doubles(k);
+  const size_t state = sizeof(double) * (size_t)(3 * k + 6 * k * k);   // mean, cov + workspace
+  a.smem_state = smem + state <= 200 * 1024;
+  if (a.smem_state) smem += state;
+  AMF_CUDA(cudaFuncSetAttribute(normal_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
   cudaStream_t s = (cudaStream_t)stream;
   normal_fit_kernel<<<B, NRM_THREADS, smem, s>>>(a);
   AMF_LAUNCH_CHECK();

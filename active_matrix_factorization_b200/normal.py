@@ -204,6 +204,7 @@ class MnWide:
         self.b = MnBatch(ratings, params, mean[None], sig[None], om[None])
         self.p = params
         self.nui, self.d = self.b.nui, self.b.d
+        self._clamped = {}
 
     @staticmethod
     def _logdet(mat):
@@ -238,11 +239,21 @@ class MnWide:
             g -= scale * (inv + inv.T * (1 - eye))
         return gm, gs, go
 
-    @staticmethod
-    def project(mat, min_eig):
+    def project(self, mat, min_eig, key):
+        """project_psd of mn_active_pmf.py:42-67.  When the previous projection of this matrix
+        did not need clamping, first ask a Cholesky of (mat - min_eig*I) whether lambda_min >=
+        min_eig -- then the reference returns the symmetrised matrix unchanged and the
+        eigendecomposition is skipped."""
         mat = (mat + mat.T) / 2
+        if not self._clamped.get(key, True):
+            eye = torch.eye(mat.shape[0], dtype=mat.dtype, device=mat.device)
+            _, info = torch.linalg.cholesky_ex(mat - min_eig * eye)
+            if int(info.item()) == 0:
+                return mat
         w, q = torch.linalg.eigh(mat)
-        if float(w.min().item()) < min_eig:
+        clamp = float(w.min().item()) < min_eig
+        self._clamped[key] = clamp
+        if clamp:
             mat = (q * torch.clamp(w, min=min_eig)) @ q.T
             mat = (mat + mat.T) / 2
         return mat
@@ -258,8 +269,8 @@ class MnWide:
             gm, gs, go = self.gradient(mean, sig, om)
             while True:
                 nm = mean - lr * gm
-                ns = self.project(sig - lr * gs, p.min_eig)
-                no = self.project(om - lr * go, p.min_eig)
+                ns = self.project(sig - lr * gs, p.min_eig, 'sig')
+                no = self.project(om - lr * go, p.min_eig, 'om')
                 new = self.kl(nm, ns, no)
                 if new < old:
                     mean, sig, om = nm, ns, no

@@ -195,7 +195,7 @@ sample_stats_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ 
   if (threadIdx.x == 0) part[blockIdx.x] = best;
 }
 
-int acquire_partials(Best** out);
+int acquire_partials(Best** out, cudaStream_t s);
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
 
@@ -281,7 +281,7 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
   AMF_REQUIRE(select >= 0 && select <= 2, "amf_bayes_sample_stats: bad select");
   cudaStream_t s = (cudaStream_t)stream;
   Best* part = nullptr;
-  int rc = acquire_partials(&part);
+  int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
   const int64_t blocks = (ncand + 127) / 128;
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? (blocks > 0 ? blocks : 1)
@@ -295,6 +295,7 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
 #undef STATS
   AMF_LAUNCH_CHECK();
   if (best_d) return launch_best_final(part, grid, maximize != 0, best_d, s);
+  AMF_CUDA(cudaFreeAsync(part, s));
   return AMF_OK;
 }
 

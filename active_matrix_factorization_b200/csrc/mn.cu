@@ -398,7 +398,7 @@ mn_score_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj, 
   if (threadIdx.x == 0) part[blockIdx.x] = best;
 }
 
-int acquire_partials(Best** out);
+int acquire_partials(Best** out, cudaStream_t s);
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
 
@@ -473,7 +473,7 @@ int amf_mn_score_candidates(int criterion, int dtype, int64_t ncand, const int32
   AMF_REQUIRE(mean_d && sig_d && om_d && best_d, "amf_mn_score_candidates: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
   Best* part = nullptr;
-  int rc = acquire_partials(&part);
+  int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
   const int64_t blocks = (ncand + 127) / 128;
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? (blocks > 0 ? blocks : 1)

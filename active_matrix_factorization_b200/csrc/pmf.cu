@@ -15,6 +15,10 @@
 // AMF_SUB=32 consecutive entries and finds its starting row in the precomputed sub_row table.
 #include "common.cuh"
 
+#ifndef AMF_SIDE_MIN_BLOCKS
+#define AMF_SIDE_MIN_BLOCKS 4   // caps the side pass at 64 registers: 4 CTAs (32 warps) per SM
+#endif
+
 namespace amf {
 
 template <typename T>
@@ -119,7 +123,7 @@ __device__ __forceinline__ void load_val(const double* __restrict__ p, double (&
 // (E independent 16-byte loads per lane in flight), then the batch is reduced in order so the
 // row accumulator and the row-change flush see the entries sequentially.
 template <typename T, int LPR, int VPL, bool GRAD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AMF_SIDE_MIN_BLOCKS)
 side_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                  const T* __restrict__ val, const int32_t* __restrict__ sub_row,
                  const T* __restrict__ Self, const T* __restrict__ Other, int ld, int nvec,

@@ -37,7 +37,7 @@ struct amf_pool {
 
 namespace amf {
 
-int acquire_partials(Best** out);
+int acquire_partials(Best** out, cudaStream_t s);
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
 
@@ -517,7 +517,7 @@ int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const vo
   const int vecn = dtype == AMF_F32 ? 4 : 2;
   AMF_REQUIRE(ld >= d && ld % vecn == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, vecn);
   Best* part = nullptr;
-  int rc = acquire_partials(&part);
+  int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
   void* tmp_scores = nullptr;
   if (scores_d && h->npad > 0) {

@@ -43,6 +43,7 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
   if (maximize) best_final_kernel<true><<<1, 256, 0, s>>>(part_d, nparts, out_d);
   else best_final_kernel<false><<<1, 256, 0, s>>>(part_d, nparts, out_d);
   AMF_LAUNCH_CHECK();
+  AMF_CUDA(cudaFreeAsync(const_cast<Best*>(part_d), s));   // pairs with acquire_partials
   return AMF_OK;
 }
 
@@ -244,25 +245,11 @@ static int score_normal(int crit, int64_t ncand, const int32_t* ci, const int32_
   return AMF_OK;
 }
 
-// per-device scratch for the per-block partial winners (one slot per host thread is not needed:
-// the buffer is only touched by kernels ordered on the caller's stream; distinct streams get
-// distinct slices through a small ring)
-static Best* partials(int device, int slot) {
-  static Best* bufs[64][8] = {{nullptr}};
-  if (device >= 64) return nullptr;
-  if (!bufs[device][slot]) {
-    if (cudaMalloc(&bufs[device][slot], sizeof(Best) * 8192) != cudaSuccess) return nullptr;
-  }
-  return bufs[device][slot];
-}
-
-int acquire_partials(Best** out) {
-  static thread_local int rr = 0;
-  int dev = 0;
-  AMF_CUDA(cudaGetDevice(&dev));
-  Best* p = partials(dev, (rr++) & 7);
-  AMF_REQUIRE(p != nullptr, "could not allocate arg-best scratch");
-  *out = p;
+// scratch for the per-block partial winners: a stream-ordered allocation per call, released by
+// launch_best_final on the same stream, so concurrent callers (one host thread per criterion,
+// active_pmf.py:1064-1079) never share a buffer
+int acquire_partials(Best** out, cudaStream_t s) {
+  AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(out), sizeof(Best) * 8192, s));
   return AMF_OK;
 }
 
@@ -284,7 +271,7 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
   AMF_REQUIRE(ncand >= 0 && d > 0, "amf_score_candidates: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
   Best* part = nullptr;
-  int rc = acquire_partials(&part);
+  int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
   int grid;
   if (criterion == AMF_CRIT_PRED) {

@@ -75,6 +75,46 @@ class ProbabilisticMatrixFactorization(object):
         self.users = np.random.random((n, self.latent_d))
         self.items = np.random.random((m, self.latent_d))
 
+    @classmethod
+    def from_coo(cls, i, j, r, num_users, num_items, latent_d=1, subtract_mean=False,
+                 fit_type=('batch',), init=None):
+        """Large-data constructor: the rating list is given as three arrays
+        (numpy or CUDA torch tensors: user ids, item ids, values) and goes straight into the
+        device layout -- no (nnz, 3) float64 array, no Python sets of all N*M cells (the
+        reference's constructor is O(N*M), pmf_cy.pyx:69-72).  ``ratings`` is materialised
+        lazily only if somebody reads it; ``rated`` / ``unrated`` are empty (pass explicit
+        candidate pools).  ``init`` = (users, items) or None for the reference's U(0,1) draws."""
+        import torch
+        self = cls.__new__(cls)
+        self._dev = {}
+        self.learning_rate, self.min_learning_rate, self.stop_thresh = 1e-4, 1e-10, 1e-2
+        self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq = 1., 10., 10.
+        self.sig_u_mean = self.sig_v_mean = 0.
+        self.sig_u_var = self.sig_v_var = -1.
+        self.latent_d, self.subtract_mean = int(latent_d), bool(subtract_mean)
+        self.fit_type = tuple(fit_type)
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        name = self.dtype_name
+        if isinstance(i, torch.Tensor):
+            ti, tj = i.to(torch.int32), j.to(torch.int32)
+            tr = r.to(D.torch_dtype(name))
+        else:
+            ti, tj = D.to_device(np.asarray(i), np.int32), D.to_device(np.asarray(j), np.int32)
+            tr = D.to_device(np.asarray(r), D.np_dtype(name))
+        rat = D.Ratings(self.num_users, self.num_items, ti, tj, tr, name)
+        self._coo = (ti, tj, tr)
+        self._ratings = None
+        self._dev['rat'] = rat
+        self._dev['rat_key'] = (name, 'coo', rat.nnz)
+        self.mean_rating = rat.mean()
+        self.rated, self.unrated = set(), set()
+        if init is None:
+            self.users = np.random.random((self.num_users, self.latent_d))
+            self.items = np.random.random((self.num_items, self.latent_d))
+        else:
+            self.users, self.items = init
+        return self
+
     # ---- host <-> device bookkeeping -----------------------------------------------------
     @property
     def dtype_name(self):
@@ -82,11 +122,21 @@ class ProbabilisticMatrixFactorization(object):
 
     @property
     def ratings(self):
+        if self._ratings is None and self.__dict__.get('_coo') is not None:
+            ti, tj, tr = self._coo            # from_coo(): build the (nnz, 3) array on demand
+            self._ratings = np.column_stack((ti.cpu().numpy(), tj.cpu().numpy(),
+                                             tr.double().cpu().numpy())).astype(float)
         return self._ratings
+
+    def _num_ratings(self):
+        if self._ratings is None and self.__dict__.get('_coo') is not None:
+            return int(self._coo[0].numel())
+        return self._ratings.shape[0]
 
     @ratings.setter
     def ratings(self, value):
         self._ratings = value
+        self._coo = None
         self._drop_device('rat')
 
     @property
@@ -129,6 +179,14 @@ class ProbabilisticMatrixFactorization(object):
             self._items = D.from_padded(dev['V'], self.latent_d)
 
     def _rating_handle(self):
+        if self._ratings is None and self.__dict__.get('_coo') is not None:
+            if self._dev.get('rat') is None or self._dev.get('rat_key', (None,))[0] != self.dtype_name:
+                ti, tj, tr = self._coo
+                self._drop_device('rat')
+                self._dev['rat'] = D.Ratings(self.num_users, self.num_items, ti, tj,
+                                             tr.to(D.torch_dtype(self.dtype_name)), self.dtype_name)
+                self._dev['rat_key'] = (self.dtype_name, 'coo', self._dev['rat'].nnz)
+            return self._dev['rat']
         key = (self.dtype_name, id(self._ratings), self._ratings.shape[0])
         rat = self._dev.get('rat')
         if rat is None or self._dev.get('rat_key') != key:
@@ -252,7 +310,7 @@ class ProbabilisticMatrixFactorization(object):
     def ll_prior_adjustment(self):
         """(pmf_cy.pyx:195-199)"""
         return float(-.5 * (
-            np.log(self.sigma_sq) * self.ratings.shape[0]
+            np.log(self.sigma_sq) * self._num_ratings()
             + self.num_users * self.latent_d * np.log(self.sigma_u_sq)
             + self.num_items * self.latent_d * np.log(self.sigma_v_sq)))
 
@@ -295,7 +353,7 @@ class ProbabilisticMatrixFactorization(object):
 
     def update_sigma(self):
         """(pmf_cy.pyx:225-234)"""
-        self.sigma_sq = self._sq_error() / self.ratings.shape[0]
+        self.sigma_sq = self._sq_error() / self._num_ratings()
 
     def update_sigma_uv(self):
         """(pmf_cy.pyx:236-255)"""
@@ -423,7 +481,7 @@ class ProbabilisticMatrixFactorization(object):
             dev['U'], dev['V'], dev['host_stale'] = U, V, True
             # training error over ALL of self.ratings (pmf_cy.pyx:347-349)
             sums = D.loss_grad(self._rating_handle(), self.latent_d, U, V, self._params())
-            err = float(np.float32(np.sqrt(float(sums[0].item()) / self.ratings.shape[0])))
+            err = float(np.float32(np.sqrt(float(sums[0].item()) / self._num_ratings())))
             yield err
             if dev.pop('host_set', False):     # caller replaced the factors
                 self._pull()

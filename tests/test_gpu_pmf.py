@@ -171,3 +171,36 @@ def test_linearity_at_scale(amf):
     lin_v = np.zeros((m, d)); np.add.at(lin_v, jj, U[ii] * r[:, None])
     assert rel_err(out[1][1] - out[0][1], lin_u) < 1e-5
     assert rel_err(out[1][2] - out[0][2], lin_v) < 1e-5
+
+
+def test_from_coo_matches_tuple_constructor(amf):
+    """the COO constructor (no (nnz,3) array, no N*M sets) gives the same
+    objective, gradient and fit as the reference-style constructor; device tensors accepted."""
+    import torch
+    rng = np.random.RandomState(4)
+    n, m, d, nnz = 120, 90, 8, 3000
+    cells = rng.permutation(n * m)[:nnz]
+    ii, jj = cells // m, cells % m
+    ii[0], jj[0] = n - 1, m - 1
+    r = rng.normal(3, 1, nnz)
+    R = np.column_stack((ii, jj, r)).astype(float)
+    U, V = rng.normal(0, .3, (n, d)), rng.normal(0, .3, (m, d))
+    a = make_model(amf, R, U, V, d, "f64", True)
+    PMF = amf.ProbabilisticMatrixFactorization
+    for args in ((ii, jj, r), (torch.from_numpy(ii).cuda(), torch.from_numpy(jj).cuda(), torch.from_numpy(r).cuda())):
+        b = PMF.from_coo(*args, num_users=n, num_items=m, latent_d=d, subtract_mean=True,
+                         init=(U.copy(), V.copy()))
+        assert b.unrated == set() and b.mean_rating == pytest.approx(a.mean_rating, rel=1e-12)
+        assert b.log_likelihood() == pytest.approx(a.log_likelihood(), rel=1e-12)
+        assert b.full_ll() == pytest.approx(a.full_ll(), rel=1e-12)
+        ga, gb = a.gradient(), b.gradient()
+        np.testing.assert_allclose(gb[0], ga[0], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(gb[1], ga[1], rtol=1e-11, atol=1e-12)
+        assert b.ratings.shape == (nnz, 3)                    # lazily materialised, same content
+        assert sorted(map(tuple, b.ratings)) == sorted(map(tuple, R))
+    b = PMF.from_coo(ii, jj, r, n, m, d, True, init=(U.copy(), V.copy()))
+    a2 = make_model(amf, R, U, V, d, "f64", True)
+    la, lb = list(a2.fit_lls()), list(b.fit_lls())
+    assert len(la) == len(lb)
+    np.testing.assert_allclose(lb, la, rtol=1e-9)
+    np.testing.assert_allclose(b.users, a2.users, rtol=1e-7, atol=1e-9)

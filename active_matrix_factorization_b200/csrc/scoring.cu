@@ -249,6 +249,21 @@ static int score_normal(int crit, int64_t ncand, const int32_t* ci, const int32_
 // launch_best_final on the same stream, so concurrent callers (one host thread per criterion,
 // active_pmf.py:1064-1079) never share a buffer
 int acquire_partials(Best** out, cudaStream_t s) {
+  // keep freed blocks in the device's default pool across synchronisations: with the default
+  // release threshold (0) every sync trims the pool and the next allocation goes to the driver
+  static bool tuned[64] = {false};
+  int dev = 0;
+  AMF_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !tuned[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 64ull << 20;
+      uint64_t cur = 0;
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+      if (cur < keep) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned[dev] = true;
+  }
   AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(out), sizeof(Best) * 8192, s));
   return AMF_OK;
 }

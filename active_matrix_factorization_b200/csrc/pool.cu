@@ -23,7 +23,8 @@ struct amf_pool {
   int n_tiles, n_ublocks;
   int64_t n_buckets;     // n_tiles * n_ublocks, bucket = tile * n_ublocks + ublock
   uint32_t* cw;          // [npad] packed local indices  il | jl << 16   (0xffffffff = padding)
-  uint32_t* orig;        // [npad] position in the caller's pool
+  uint32_t* orig;        // [npad] position in the caller's pool (POOL_TOMBSTONE = removed)
+  uint32_t* pos_of;      // [ncand] bucketed position of the caller's candidate c
   int64_t* bptr;         // [n_buckets+1] padded start of every bucket
   int32_t* bcnt;         // [n_buckets]   real candidates in every bucket
   // work list: non-empty buckets cut into segments of at most POOL_WORD_CAP candidates
@@ -81,7 +82,7 @@ __global__ void pool_scatter_kernel(const uint64_t* __restrict__ keys,
                                     const uint32_t* __restrict__ perm, int64_t n, int ibits,
                                     int jbits, const int64_t* __restrict__ start,
                                     const int64_t* __restrict__ bptr, uint32_t* __restrict__ cw,
-                                    uint32_t* __restrict__ orig) {
+                                    uint32_t* __restrict__ orig, uint32_t* __restrict__ pos_of) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
        p += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t k = keys[p];
@@ -91,11 +92,13 @@ __global__ void pool_scatter_kernel(const uint64_t* __restrict__ keys,
     const int64_t q = bptr[b] + (p - start[b]);
     cw[q] = il | (jl << 16);
     orig[q] = perm[p];
+    pos_of[perm[p]] = (uint32_t)q;
   }
 }
 
 constexpr int POOL_WORD_CAP = 4096;   // packed index words staged per segment (16 KB)
 constexpr int POOL_THREADS = 512;
+constexpr uint32_t POOL_TOMBSTONE = 0xffffffffu;   // orig[] value of a removed candidate
 constexpr int POOL_MAX_STAGES = 8;
 
 static int bits_for_count(uint64_t x) {
@@ -325,8 +328,10 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
       const bool live = base + lane < cnt;
       if (scores && live) __stcs(scores + cb + base + lane, p[0]);
       if (live && (MAX ? (p[0] >= best_v) : (p[0] <= best_v))) {     // rare after warm-up
-        const int64_t o = (int64_t)orig[cb + base + lane];
-        if (best_o < 0 || (MAX ? (p[0] > best_v) : (p[0] < best_v)) || o < best_o) {
+        const uint32_t ou = orig[cb + base + lane];
+        const int64_t o = (int64_t)ou;
+        if (ou != POOL_TOMBSTONE &&
+            (best_o < 0 || (MAX ? (p[0] > best_v) : (p[0] < best_v)) || o < best_o)) {
           best_v = p[0]; best_o = o;
         }
       }
@@ -345,7 +350,7 @@ __global__ void unpermute_kernel(const T* __restrict__ in, const uint32_t* __res
                                  T* __restrict__ out) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < npad;
        t += (int64_t)gridDim.x * blockDim.x)
-    if (cw[t] != 0xffffffffu) out[orig[t]] = in[t];
+    if (cw[t] != 0xffffffffu && orig[t] != POOL_TOMBSTONE) out[orig[t]] = in[t];
 }
 
 template <typename T, bool MAX>
@@ -388,7 +393,7 @@ extern "C" {
 
 int amf_pool_destroy(amf_pool_t* h) {
   if (!h) return AMF_OK;
-  cudaFree(h->cw); cudaFree(h->orig); cudaFree(h->bptr); cudaFree(h->bcnt); cudaFree(h->tmp_scores);
+  cudaFree(h->cw); cudaFree(h->orig); cudaFree(h->pos_of); cudaFree(h->bptr); cudaFree(h->bcnt); cudaFree(h->tmp_scores);
   cudaFree(h->seg_bucket); cudaFree(h->seg_ptr); cudaFree(h->seg_cnt);
   delete h;
   return AMF_OK;
@@ -463,9 +468,10 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
     POOL_CUDA(cudaMalloc(&h->cw, 4 * (size_t)(total_pad > 0 ? total_pad : 1) + 256));
     POOL_CUDA(cudaMalloc(&h->orig, 4 * (size_t)(total_pad > 0 ? total_pad : 1) + 256));
     POOL_CUDA(cudaMemsetAsync(h->cw, 0xff, 4 * (size_t)(total_pad > 0 ? total_pad : 1) + 256, s));
+    POOL_CUDA(cudaMalloc(&h->pos_of, 4 * cnt));
     if (ncand > 0) {
       pool_scatter_kernel<<<grid, 256, 0, s>>>(keys_out, perm, ncand, ibits, jbits, start, h->bptr,
-                                               h->cw, h->orig);
+                                               h->cw, h->orig, h->pos_of);
       POOL_CUDA(cudaGetLastError());
     }
     // segment list
@@ -505,6 +511,25 @@ done:
 }
 
 int64_t amf_pool_size(const amf_pool_t* h) { return h ? h->ncand : -1; }
+
+__global__ void pool_remove_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t ncand,
+                                   const uint32_t* __restrict__ pos_of,
+                                   uint32_t* __restrict__ orig) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = idx[t];
+    if (c >= 0 && c < ncand) orig[pos_of[c]] = amf::POOL_TOMBSTONE;
+  }
+}
+
+int amf_pool_remove(amf_pool_t* h, int64_t n, const int64_t* idx_d, void* stream) {
+  AMF_REQUIRE(h && (n == 0 || idx_d), "amf_pool_remove: NULL argument");
+  if (n <= 0 || h->ncand == 0) return AMF_OK;
+  const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  pool_remove_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx_d, n, h->ncand, h->pos_of, h->orig);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
 
 int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,
                         const void* V_d, void* scores_d, int maximize, int64_t index_base,

@@ -111,6 +111,13 @@ class Pool:
                                         int(index_base), D.ptr(best), D.stream_ptr()))
         return scores, best
 
+    def remove(self, indices):
+        """Drop candidates (positions in the caller's order) from the pool, O(1) each: what
+        `unrated.difference_update` does for the reference's set (pmf_cy.pyx:152)."""
+        idx = torch.as_tensor(np.atleast_1d(np.asarray(indices, dtype=np.int64))).to(D.device())
+        N.check(N.require_device().amf_pool_remove(self._h, int(idx.numel()), D.ptr(idx),
+                                                   D.stream_ptr()))
+
     def pad(self, arr):
         """host (rows, d) factors -> zero-padded (rows, self.ld) device tensor for this pool"""
         arr = np.ascontiguousarray(arr, dtype=D.np_dtype(self.name))

@@ -160,6 +160,11 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
                     int32_t n_users, int32_t n_items, int tile_rows, int block_rows, void* stream);
 int amf_pool_destroy(amf_pool_t* h);
 int64_t amf_pool_size(const amf_pool_t* h);
+/* Removes candidates (given by their positions in the caller's order) from the pool in O(1)
+ * each: they no longer compete for the winner and their score slots are left untouched.  This
+ * is `unrated.difference_update(new_items)` (pmf_cy.pyx:152) for a device-resident pool: the
+ * active loop queries one candidate per step and keeps scoring the rest. */
+int amf_pool_remove(amf_pool_t* h, int64_t n, const int64_t* idx_d, void* stream);
 /* AMF_CRIT_PRED over the pool: scores_d (T[ncand], caller's order) may be NULL; best_d as in
  * amf_score_candidates (index = position in the caller's order + index_base, lowest wins ties). */
 int amf_pool_score_pred(const amf_pool_t* h, int dtype, int d, int ld, const void* U_d,

@@ -104,3 +104,41 @@ def test_parse_fit_type():
     from active_matrix_factorization_b200.pmf_cy import parse_fit_type
     assert parse_fit_type('batch') == ('batch',)
     assert parse_fit_type('mini-valid,100,30,1.5') == ('mini-valid', 100, 30, 1.5)
+
+
+def test_error_conventions_of_the_active_classes():
+    """SURVEY.md 8b error conventions that need no device: same exception types and messages
+    as the reference (active_pmf.py:121-122,206-207,731-732; pmf_cy.pyx:144-145;
+    normal_exps_cy.pyx:149-150; bayes_pmf.py:88-89)."""
+    from active_matrix_factorization_b200 import active_pmf as A, bayes_pmf as Bm, mn_active_pmf as M
+    R = _toy()
+    with pytest.raises(ValueError, match="got ratings not in rating_values"):
+        A.ActivePMF(R, 2, rating_values={7, 8})
+    with pytest.raises(ValueError, match="got ratings not in rating_values"):
+        Bm.BayesianPMF(R, 2, rating_values={7, 8})
+    a = A.ActivePMF(R, 2, rating_values={1, 2, 3, 4, 5})
+    assert a.rating_values == (1., 2., 3., 4., 5.) and a.rating_bounds[0] == -np.inf
+    assert a.rating_bounds[1] == 1.5 and a.rating_bounds[-1] == np.inf
+    with pytest.raises(ValueError, match="got ratings with bad values"):
+        a.add_rating(0, 1, 9.0)
+    with pytest.raises(ValueError, match="run initialize_approx first"):
+        a.kl_divergence()
+    with pytest.raises(TypeError, match="run initialize_approx first"):
+        A.normal_gradient(a)
+    with pytest.raises(ValueError, match="empty pool"):
+        a.pick_query_point(pool=[])
+    assert a.pick_query_point(pool=[(3, 3)]) == (3, 3)           # single element: no evaluation
+    assert a.approx_dim == (4 + 5) * 2 and a.u.shape == (2, 4) and a.v[0, 0] == 8
+    mn = M.MNActivePMF(R, 2)
+    with pytest.raises(ValueError, match="run initialize_approx first"):
+        mn.kl_divergence()
+    with pytest.raises(TypeError):
+        M.matrixnormal_gradient(mn)
+    assert not hasattr(mn, "cov") and mn.cov_useritems is None
+    assert set(M.KEY_FUNCS) == set(A.KEY_FUNCS) - {"pred-entropy-bound", "pred-entropy-bound-approx"}
+    for f in A.KEY_FUNCS.values():
+        assert f.chooser in (min, max)
+    b = Bm.BayesianPMF(R, 3)
+    assert b.beta == 2 and b.subtract_mean and b.u_hyperparams[2] == 3
+    st = b.__getstate__()
+    assert {'discrete_expectations', 'rating_values', 'beta', 'u_hyperparams', 'v_hyperparams'} <= set(st)

@@ -140,3 +140,31 @@ def test_block_diagonal_view_matches_oracle(S, dtype, tol):
         ptol = tol if crit != N.CRIT_PROB_GE else tol * 50
         np.testing.assert_allclose(got[sel], ref[sel], rtol=ptol, atol=ptol * np.abs(ref[sel]).max())
         assert S.unpack_best(best)[1] == int(np.argmax(got))
+
+
+def test_pool_remove_matches_shrinking_set(S):
+    """an active loop on a device-resident pool: query the winner, remove it, score again --
+    the winners come out in the order of the sorted scores, like max() over a shrinking set"""
+    rng = np.random.RandomState(11)
+    n, m, d, nc = 300, 700, 32, 40_000
+    U, V = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    ii, jj = rng.randint(0, n, nc), rng.randint(0, m, nc)
+    pool = S.Pool(ii, jj, n, m, "f64", d)
+    Ut, Vt = pool.pad(U), pool.pad(V)
+    ref = np.einsum("nd,nd->n", U[ii], V[jj])
+    order = np.argsort(-ref, kind="stable")
+    picked = []
+    for step in range(6):
+        _, best = pool.score_pred(Ut, Vt)
+        v, idx = S.unpack_best(best)
+        assert v == pytest.approx(ref[idx], rel=1e-12)
+        picked.append(idx)
+        pool.remove([idx])
+    assert picked == order[:6].tolist()
+    pool.remove(order[6:20])                       # batch removal
+    _, best = pool.score_pred(Ut, Vt)
+    assert S.unpack_best(best)[1] == int(order[20])
+    sc, _ = pool.score_pred(Ut, Vt, want_scores=True)
+    alive = np.ones(nc, bool); alive[order[:20]] = False
+    np.testing.assert_allclose(sc.cpu().numpy()[alive], ref[alive], rtol=1e-11, atol=1e-12)
+    pool.close()

@@ -903,58 +903,63 @@ def add_bool_opt(parser, name, default=False):
     parser.add_argument('--no-' + name, action='store_false', dest=name.replace('-', '_'))
 
 
+# command line of the reference (active_pmf.py:1109-1160), as data: (group, flags, options)
+_CLI = [
+    ("Model Options", ('--latent-d', '-D'), dict(type=int, default=5)),
+    ("Model Options", ('--discrete-integration',), dict(nargs='?', const=True, default=False)),
+    ("Model Options", ('--continuous-integration',), dict(action='store_false', dest='discrete_integration')),
+    ("Model Options", 'bool', ('fit-sigmas', False)),
+    ("Model Options", 'bool', ('refit-lookahead', False)),
+    ("Model Options", ('--fit',), dict(default='batch')),
+    ("Model Options", ('--sig-u-mean',), dict(type=float, default=0)),
+    ("Model Options", ('--sig-u-var',), dict(type=float, default=-1)),
+    ("Model Options", ('--sig-v-mean',), dict(type=float, default=0)),
+    ("Model Options", ('--sig-v-var',), dict(type=float, default=-1)),
+    ("Problem Definiton", ('--load-data',), dict(default=None, metavar='FILE')),
+    ("Problem Definiton", 'bool', ('load-model', False)),
+    ("Problem Definiton", ('--gen-rank', '-R'), dict(type=int, default=5)),
+    ("Problem Definiton", ('--type',), dict(default='float')),
+    ("Problem Definiton", ('--u-mean',), dict(type=float, default=0)),
+    ("Problem Definiton", ('--u-std',), dict(type=float, default=2)),
+    ("Problem Definiton", ('--v-mean',), dict(type=float, default=0)),
+    ("Problem Definiton", ('--v-std',), dict(type=float, default=2)),
+    ("Problem Definiton", ('--noise', '-n'), dict(type=float, default=.25)),
+    ("Problem Definiton", ('--num-users', '-N'), dict(type=int, default=10)),
+    ("Problem Definiton", ('--num-items', '-M'), dict(type=int, default=10)),
+    ("Problem Definiton", ('--mask', '-m'), dict(default=0)),
+    ("Running", ('--processes', '-P'), dict(type=int, default=None)),
+    ("Running", 'bool', ('threading', True)),
+    ("Running", ('--steps', '-s'), dict(type=int, default=None)),
+    ("Results", ('--save-results',), dict(nargs='?', default=None, const=True, metavar='FILE')),
+    ("Results", ('--no-save-results',), dict(action='store_false', dest='save_results')),
+    ("Results", ('--note',), dict(action='append')),
+]
+
+
+def build_parser(spec, key_names):
+    import argparse
+    parser = argparse.ArgumentParser()
+    groups = {}
+    for group, flags, opts in spec:
+        g = groups.setdefault(group, parser.add_argument_group(group))
+        if flags == 'bool':
+            add_bool_opt(g, *opts)
+        else:
+            g.add_argument(*flags, **opts)
+    parser.add_argument('keys', nargs='*',
+                        help="Choices: {}.".format(', '.join(sorted(key_names))))
+    return parser
+
+
 def main(argv=None):
     '''Same command line as the reference (active_pmf.py:1100-1257).'''
-    import argparse
     import os
     import pickle
     import sys
 
     key_names = set(KEY_FUNCS.keys())
     types = {'float', 'int', 'int-bounds', 'binary'}
-    parser = argparse.ArgumentParser()
-
-    model = parser.add_argument_group("Model Options")
-    model.add_argument('--latent-d', '-D', type=int, default=5)
-    model.add_argument('--discrete-integration', nargs='?', const=True, default=False)
-    model.add_argument('--continuous-integration', action='store_false', dest='discrete_integration')
-    add_bool_opt(model, 'fit-sigmas', default=False)
-    add_bool_opt(model, 'refit-lookahead', default=False)
-    model.add_argument('--fit', default='batch')
-    model.add_argument('--sig-u-mean', type=float, default=0)
-    model.add_argument('--sig-u-var', type=float, default=-1)
-    model.add_argument('--sig-v-mean', type=float, default=0)
-    model.add_argument('--sig-v-var', type=float, default=-1)
-    model.add_argument('keys', nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names))))
-
-    problem_def = parser.add_argument_group("Problem Definiton")
-    problem_def.add_argument('--load-data', default=None, metavar='FILE')
-    add_bool_opt(problem_def, 'load-model', default=False)
-    problem_def.add_argument('--gen-rank', '-R', type=int, default=5)
-    problem_def.add_argument('--type', default='float',
-                             help="An integer (meaning values are from 0 to that integer) or "
-                                  "one of {}".format(', '.join(sorted(types))))
-    problem_def.add_argument('--u-mean', type=float, default=0)
-    problem_def.add_argument('--u-std', type=float, default=2)
-    problem_def.add_argument('--v-mean', type=float, default=0)
-    problem_def.add_argument('--v-std', type=float, default=2)
-    problem_def.add_argument('--noise', '-n', type=float, default=.25)
-    problem_def.add_argument('--num-users', '-N', type=int, default=10)
-    problem_def.add_argument('--num-items', '-M', type=int, default=10)
-    problem_def.add_argument('--mask', '-m', default=0)
-
-    running = parser.add_argument_group("Running")
-    running.add_argument('--processes', '-P', type=int, default=None)
-    add_bool_opt(running, 'threading', True)
-    running.add_argument('--steps', '-s', type=int, default=None)
-
-    results = parser.add_argument_group("Results")
-    results.add_argument('--save-results', nargs='?', default=None, const=True, metavar='FILE')
-    results.add_argument('--no-save-results', action='store_false', dest='save_results')
-    results.add_argument('--note', action='append',
-                         help="Doesn't do anything, just there to save any notes you'd like "
-                              "in the results file.")
-
+    parser = build_parser(_CLI, key_names)
     args = parser.parse_args(argv)
 
     try:

@@ -488,25 +488,27 @@ def main(argv=None):
 
     key_names = KEYS.keys()
     parser = argparse.ArgumentParser()
-    parser.add_argument('--latent-d', '-D', type=int, default=5)
-    parser.add_argument('--steps', '-s', type=int, default=None)
-    parser.add_argument('--discrete', action='store_true', default=None)
-    parser.add_argument('--no-discrete', action='store_false', dest='discrete')
-    parser.add_argument('--subtract-mean', action='store_true', default=True)
-    parser.add_argument('--no-subtract-mean', action='store_false', dest='subtract_mean')
-    parser.add_argument('--fit', default='batch')
-    parser.add_argument('--lookahead-fit', default='batch')
-    parser.add_argument('--samps', '-S', type=int, default=128)
-    parser.add_argument('--lookahead-samps', type=int, default=128)
-    parser.add_argument('--threaded', action='store_true', default=True)
-    parser.add_argument('--unthreaded', action='store_false', dest='threaded')
-    parser.add_argument('--procs', '-P', type=int, default=None)
-    parser.add_argument('--test-set', default='all')
-    parser.add_argument('--load-data', required='True', metavar='FILE')
-    parser.add_argument('--save-results', nargs='?', default=True, const=True, metavar='FILE')
-    parser.add_argument('--no-save-results', action='store_false', dest='save_results')
-    parser.add_argument('--note', action='append')
-    parser.add_argument('keys', nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names))))
+    for flags, opts in (
+            (('--latent-d', '-D'), dict(type=int, default=5)),
+            (('--steps', '-s'), dict(type=int, default=None)),
+            (('--discrete',), dict(action='store_true', default=None)),
+            (('--no-discrete',), dict(action='store_false', dest='discrete')),
+            (('--subtract-mean',), dict(action='store_true', default=True)),
+            (('--no-subtract-mean',), dict(action='store_false', dest='subtract_mean')),
+            (('--fit',), dict(default='batch')),
+            (('--lookahead-fit',), dict(default='batch')),
+            (('--samps', '-S'), dict(type=int, default=128)),
+            (('--lookahead-samps',), dict(type=int, default=128)),
+            (('--threaded',), dict(action='store_true', default=True)),
+            (('--unthreaded',), dict(action='store_false', dest='threaded')),
+            (('--procs', '-P'), dict(type=int, default=None)),
+            (('--test-set',), dict(default='all')),
+            (('--load-data',), dict(required='True', metavar='FILE')),
+            (('--save-results',), dict(nargs='?', default=True, const=True, metavar='FILE')),
+            (('--no-save-results',), dict(action='store_false', dest='save_results')),
+            (('--note',), dict(action='append')),
+            (('keys',), dict(nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names)))))):
+        parser.add_argument(*flags, **opts)
     args = parser.parse_args(argv)
 
     for k in args.keys:

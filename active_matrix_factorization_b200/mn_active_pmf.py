@@ -377,34 +377,17 @@ def compare(key_names, real, ratings, rating_vals=None, latent_d=5, knowable=Non
 
 def main(argv=None):
     '''Same command line as the reference (mn_active_pmf.py:1011-1132).'''
-    import argparse
     import os
     import pickle
     import sys
 
     key_names = set(KEY_FUNCS.keys())
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--load-data', default=None, metavar='FILE')
-    model = parser.add_argument_group("Model Options")
-    model.add_argument('--latent-d', '-D', type=int, default=5)
-    model.add_argument('--discrete-integration', nargs='?', const=True, default=False)
-    model.add_argument('--continuous-integration', action='store_false', dest='discrete_integration')
-    add_bool_opt(model, 'fit-sigmas', default=False)
-    add_bool_opt(model, 'refit-lookahead', default=False)
-    model.add_argument('--fit', default='batch')
-    model.add_argument('--sig-u-mean', type=float, default=0)
-    model.add_argument('--sig-u-var', type=float, default=-1)
-    model.add_argument('--sig-v-mean', type=float, default=0)
-    model.add_argument('--sig-v-var', type=float, default=-1)
-    model.add_argument('keys', nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names))))
-    running = parser.add_argument_group("Running")
-    running.add_argument('--processes', '-P', type=int, default=None)
-    add_bool_opt(running, 'threading', True)
-    running.add_argument('--steps', '-s', type=int, default=None)
-    results = parser.add_argument_group("Results")
-    results.add_argument('--save-results', default=True, metavar='FILE')
-    results.add_argument('--no-save-results', action='store_false', dest='save_results')
-    results.add_argument('--note', action='append')
+    spec = [e for e in _apmf._CLI if e[0] == "Model Options" or e[0] == "Running"]
+    spec += [("Problem", ('--load-data',), dict(default=None, metavar='FILE')),
+             ("Results", ('--save-results',), dict(default=True, metavar='FILE')),
+             ("Results", ('--no-save-results',), dict(action='store_false', dest='save_results')),
+             ("Results", ('--note',), dict(action='append'))]
+    parser = _apmf.build_parser(spec, key_names)
     args = parser.parse_args(argv)
 
     for k in args.keys:

@@ -125,8 +125,11 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         '''
         wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
         n = feats.shape[0]
-        x_bar = np.mean(feats, axis=0).T
-        s_bar = np.cov(feats, rowvar=0)
+        # the O(N d^2) moments of the factor matrix on the device; d x d algebra + RNG on the host
+        ft = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float64)).to(D.device())
+        x_bar = ft.mean(dim=0).cpu().numpy()
+        s_bar = np.atleast_2d(torch.cov(ft.T).cpu().numpy()) if feats.shape[1] > 1 else \
+            np.array(float(ft.var(unbiased=True).item()))
         diff = mu0 - x_bar
         wi_post = np.linalg.inv(np.linalg.inv(wi) + n * s_bar
                                 + (b0 * n) / (b0 + n) * np.dot(diff, diff.T))

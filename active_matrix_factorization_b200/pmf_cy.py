@@ -358,8 +358,8 @@ class ProbabilisticMatrixFactorization(object):
     def update_sigma_uv(self):
         """(pmf_cy.pyx:236-255)"""
         d, n, m = self.latent_d, self.num_users, self.num_items
-        user_norm2 = float(np.sum(self.users * self.users))
-        item_norm2 = float(np.sum(self.items * self.items))
+        sums, _, _ = self._loss_grad_host(self.users, self.items, False)   # |U|^2, |V|^2 on device
+        user_norm2, item_norm2 = float(sums[1]), float(sums[2])
         if self.sig_u_var > 0:
             self.sigma_u_sq = user_norm2 / (n * d + 2 + 2 * (np.log(self.sigma_u_sq) - self.sig_u_mean) / self.sig_u_var)
         else:
@@ -545,10 +545,22 @@ class ProbabilisticMatrixFactorization(object):
         return pred.cpu().numpy()
 
     def rmse(self, real, on=None):
-        """(pmf_cy.pyx:422-426)"""
-        if on is None:
-            return rmse(self.predicted_matrix(), real)
-        return rmse_on(self.predicted_matrix(), real, on)
+        """(pmf_cy.pyx:422-426) -- prediction, difference and mean on the device; C float result"""
+        dev = D.device()
+        u = torch.from_numpy(np.ascontiguousarray(self.users, dtype=np.float64)).to(dev)
+        v = torch.from_numpy(np.ascontiguousarray(self.items, dtype=np.float64)).to(dev)
+        pred = u @ v.T
+        if self.subtract_mean:
+            pred += self.mean_rating
+        diff = torch.from_numpy(np.ascontiguousarray(real, dtype=np.float64)).to(dev) - pred
+        if on is not None:
+            on_arr = np.asarray(on)
+            if on_arr.dtype == bool and on_arr.shape == diff.shape:
+                diff = diff[torch.from_numpy(on_arr).to(dev)]
+            else:
+                diff = diff[tuple(torch.as_tensor(np.asarray(x)).to(dev) for x in on)] \
+                    if isinstance(on, tuple) else diff[torch.as_tensor(on_arr).to(dev)]
+        return float(np.float32(torch.sqrt(torch.mean(diff * diff)).item()))
 
     def print_latent_vectors(self):
         print("Users:")

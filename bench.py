@@ -53,6 +53,17 @@ def workload_name(a):
         a.users, a.items, a.latent_d, a.nnz, a.ncand)
 
 
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
+    kernels, from the committed `ncu --set full` capture of this same command
+    (profiles/r01d_final_ncu_full_raw.csv); None if the summary file is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -407,6 +418,8 @@ def run_ours(a):
         return
 
     hbm_peak, peak_kind = peaks()
+    traffic = measured_traffic() if (a.users, a.items, a.latent_d, a.nnz, a.ncand, a.dtype) == (
+        200_000, 50_000, 32, 50_000_000, 100_000_000, "f32") else {}
     tables = (n + m) * d * es
     score_bytes = ncand * 8 + tables
     grad_bytes = nnz * 12 + 2 * tables
@@ -427,11 +440,13 @@ def run_ours(a):
         },
         "roofline": {"kernel": "pool_pred_kernel (V tile in shared memory via TMA)" if a.pool == "tiled" else "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
                      "peak_source": peak_kind, "unit": "GB/s", "frac": score_gbs / hbm_peak,
-                     "algorithmic_bytes": score_bytes, "kernel_ms": scorek_ms, "traffic": None,
+                     "algorithmic_bytes": score_bytes, "kernel_ms": scorek_ms,
+                     "traffic": traffic.get("pool_pred_kernel" if a.pool == "tiled" else "score_pred_kernel"),
                      "flat_kernel_ms": score_flat_ms, "pool_build_ms": pool_ms},
         "roofline_gradient": {"kernel": "side_pass_kernel x2 + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
                               "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": grad_gbs / hbm_peak,
-                              "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms, "traffic": None},
+                              "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms,
+                              "traffic": traffic.get("side_pass_kernel_x2")},
         "e2e": {"value": ncand_all / e2e_score_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(ncand * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
                 "pmf_ratings_per_sec_iter": nnz_all / e2e_grad_s,

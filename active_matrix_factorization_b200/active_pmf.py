@@ -106,6 +106,7 @@ def _criterion(name, normal_fit, spawn, chooser):
 
 class ActivePMF(ProbabilisticMatrixFactorization):
     verbose_lookahead = False   # the reference prints one line per lookahead (active_pmf.py:702-703)
+    max_normal_steps = 0        # > 0 caps the accepted steps of one fit_normal (0: to convergence)
 
     def __init__(self, rating_tuples, latent_d=1, rating_values=None,
                  discrete_expectations=False, refit_lookahead=False, knowable=None,
@@ -205,7 +206,8 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         '''
         if self.mean is None or self.cov is None:
             raise ValueError("run initialize_approx first")
-        batch = _normal.NormalBatch(self.ratings, self._fit_params(), self.mean[None], self.cov[None])
+        batch = _normal.NormalBatch(self.ratings, self._fit_params(max_steps=self.max_normal_steps),
+                                    self.mean[None], self.cov[None])
         trace_len = 1 << 14
         res = batch.fit(trace_len=trace_len)
         steps = int(res['steps'][0])

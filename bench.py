@@ -187,9 +187,14 @@ def cpu_reference_sample(a, prob_host, sample):
     R[0, 0], R[1, 1] = n - 1, m - 1        # pin the model shape (reference infers it from max id)
     pool = list(zip(ci[:s_c].tolist(), cj[:s_c].tolist()))
     out = {"cores": 1, "unit": UNIT}
+    ref = None
     if build_ref.built():
-        from oracle import ref_loader
-        ref = ref_loader.load()
+        try:
+            from oracle import ref_loader
+            ref = ref_loader.load()
+        except Exception as exc:          # e.g. a box whose Python cannot load the built modules
+            out["reference_unavailable"] = repr(exc)
+    if ref is not None:
         apmf = ref.active_pmf.ActivePMF(R, d, knowable=())
         apmf.users, apmf.items = U.astype(float), V.astype(float)
         t0 = time.perf_counter()

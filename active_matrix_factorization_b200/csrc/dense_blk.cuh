@@ -48,14 +48,21 @@ __device__ inline double blk_cholesky(double* A, int k, double* red, int* flag) 
   return *flag ? ld : NAN;
 }
 
-// Linv (lower) = L^-1 ; one thread per column
+// Linv (lower) = L^-1.  Four lanes per column (forward substitution L x = e_c), the inner
+// product of row i split over the lanes and reduced with two shuffles.
 __device__ inline void blk_tri_inverse(const double* L, double* Linv, int k) {
-  for (int c = threadIdx.x; c < k; c += blockDim.x) {
-    for (int i = 0; i < k; ++i) {
-      if (i < c) { Linv[(int64_t)i * k + c] = 0.0; continue; }
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int q = c; q < i; ++q) s -= L[(int64_t)i * k + q] * Linv[(int64_t)q * k + c];
-      Linv[(int64_t)i * k + c] = s / L[(int64_t)i * k + i];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int sub = tid & 3;
+  const unsigned mask = 0xFu << ((tid & 31) & ~3);
+  for (int c = tid >> 2; c < k; c += nt >> 2) {
+    for (int i = sub; i < c; i += 4) Linv[(int64_t)i * k + c] = 0.0;
+    for (int i = c; i < k; ++i) {
+      double s = 0;
+      for (int q = c + sub; q < i; q += 4) s += L[(int64_t)i * k + q] * Linv[(int64_t)q * k + c];
+      s += __shfl_xor_sync(mask, s, 1);
+      s += __shfl_xor_sync(mask, s, 2);
+      if (sub == 0) Linv[(int64_t)i * k + c] = ((i == c ? 1.0 : 0.0) - s) / L[(int64_t)i * k + i];
+      __syncwarp(mask);
     }
   }
   __syncthreads();

@@ -17,7 +17,9 @@ namespace amf {
 constexpr int GIBBS_THREADS = 128;
 constexpr int GIBBS_TILE = 32;   // rated rows staged per tile
 constexpr int GIBBS_MAXD = 64;
-constexpr int GIBBS_MAXACC = (GIBBS_MAXD * GIBBS_MAXD + GIBBS_THREADS - 1) / GIBBS_THREADS;
+// the Gram matrix F'F is accumulated in registers as 2 x 2 blocks of its upper triangle:
+// (d/2)(d/2+1)/2 blocks, GIBBS_MAXBLK per thread at the largest d
+constexpr int GIBBS_MAXBLK = ((GIBBS_MAXD / 2) * (GIBBS_MAXD / 2 + 1) / 2 + GIBBS_THREADS - 1) / GIBBS_THREADS;
 
 // in-place lower Cholesky of the d x d matrix A (leading dimension lda) in shared memory.
 // Returns false (to all threads) if a pivot is not positive.
@@ -50,15 +52,23 @@ __device__ bool chol_lower(double* A, int d, int lda, int* flag) {
   return *flag != 0;
 }
 
-// Linv = inverse of the lower-triangular L (both d x d in shared memory, distinct buffers)
+// Linv = inverse of the lower-triangular L (both d x d in shared memory, distinct buffers).
+// Four lanes cooperate on one column (forward substitution L x = e_c): the inner product of
+// row i is split over the lanes and reduced with two shuffles, so a column costs ~d short steps
+// instead of ~d^2/2 dependent shared-memory round trips.
 __device__ void tri_inverse_lower(const double* L, double* Linv, int d, int lda) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int c = tid; c < d; c += nt) {          // column c of the inverse: L x = e_c
-    for (int i = 0; i < d; ++i) {
-      if (i < c) { Linv[i * lda + c] = 0.0; continue; }
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) s -= L[i * lda + k] * Linv[k * lda + c];
-      Linv[i * lda + c] = s / L[i * lda + i];
+  const int sub = tid & 3;
+  const unsigned mask = 0xFu << ((tid & 31) & ~3);
+  for (int c = tid >> 2; c < d; c += nt >> 2) {
+    for (int i = sub; i < c; i += 4) Linv[i * lda + c] = 0.0;
+    for (int i = c; i < d; ++i) {
+      double s = 0;
+      for (int k = c + sub; k < i; k += 4) s += L[i * lda + k] * Linv[k * lda + c];
+      s += __shfl_xor_sync(mask, s, 1);
+      s += __shfl_xor_sync(mask, s, 2);
+      if (sub == 0) Linv[i * lda + c] = ((i == c ? 1.0 : 0.0) - s) / L[i * lda + i];
+      __syncwarp(mask);
     }
   }
   __syncthreads();
@@ -74,39 +84,60 @@ gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
                   int* __restrict__ fail) {
   extern __shared__ double smem[];
   const int lda = d + 1;
+  const int dp = (d + 1) & ~1;      // d rounded up to even: the tile is read two columns at a time
+  const int ldt = dp + 2;           // even row stride keeps the 2-element loads aligned
+  const int hb = dp / 2;            // 2 x 2 blocks per side
+  const int nblk = hb * (hb + 1) / 2;
   double* A = smem;                 // d x lda : Lambda -> chol -> ...
   double* Bm = A + d * lda;         // d x lda : scratch
   double* rhs = Bm + d * lda;       // d
   double* mean = rhs + d;           // d
   double* tile_r = mean + d;        // GIBBS_TILE
-  T* tile = reinterpret_cast<T*>(tile_r + GIBBS_TILE);   // GIBBS_TILE x (d+1)
+  T* tile = reinterpret_cast<T*>(tile_r + GIBBS_TILE);   // GIBBS_TILE x ldt
   __shared__ int flag;
   const int tid = threadIdx.x;
-  const int ldt = d + 1;
+
+  // this thread's blocks (bk <= bl) of the upper triangle
+  int bks[GIBBS_MAXBLK], bls[GIBBS_MAXBLK];
+#pragma unroll
+  for (int a = 0; a < GIBBS_MAXBLK; ++a) {
+    int blk = tid + a * GIBBS_THREADS, bk = 0;
+    if (blk < nblk) {
+      while (blk >= hb - bk) { blk -= hb - bk; ++bk; }
+      bks[a] = bk; bls[a] = bk + blk;
+    } else {
+      bks[a] = -1; bls[a] = 0;
+    }
+  }
 
   for (int row = row_begin + blockIdx.x; row < rows; row += gridDim.x) {
     const int64_t p0 = ptr[row], p1 = ptr[row + 1];
-    // ---- Gram matrix F'F and F'(r - offset), accumulated per thread over (k,l) pairs ------
-    T acc[GIBBS_MAXACC];
+    // ---- Gram matrix F'F (2 x 2 register blocks) and F'(r - offset) ------------------------
+    T acc[GIBBS_MAXBLK][4];
 #pragma unroll
-    for (int a = 0; a < GIBBS_MAXACC; ++a) acc[a] = 0;
+    for (int a = 0; a < GIBBS_MAXBLK; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0;
     T racc = 0;                                  // thread k < d accumulates rhs[k]
     for (int64_t base = p0; base < p1; base += GIBBS_TILE) {
       const int cnt = (int)min((int64_t)GIBBS_TILE, p1 - base);
-      for (int t = tid; t < cnt * d; t += GIBBS_THREADS) {
-        const int e = t / d, k = t % d;
-        tile[e * ldt + k] = other[(int64_t)idx[base + e] * d + k];
+      for (int t = tid; t < cnt * dp; t += GIBBS_THREADS) {
+        const int e = t / dp, k = t - e * dp;
+        tile[e * ldt + k] = k < d ? other[(int64_t)idx[base + e] * d + k] : T(0);
       }
       for (int t = tid; t < cnt; t += GIBBS_THREADS) tile_r[t] = (double)val[base + t] - mean_offset;
       __syncthreads();
 #pragma unroll
-      for (int a = 0; a < GIBBS_MAXACC; ++a) {
-        const int pr = tid + a * GIBBS_THREADS;
-        if (pr < d * d) {
-          const int k = pr / d, l = pr % d;
-          T s = acc[a];
-          for (int e = 0; e < cnt; ++e) s = fma(tile[e * ldt + k], tile[e * ldt + l], s);
-          acc[a] = s;
+      for (int a = 0; a < GIBBS_MAXBLK; ++a) {
+        if (bks[a] >= 0) {
+          const T* pa = tile + 2 * bks[a];
+          const T* pb = tile + 2 * bls[a];
+          T s00 = acc[a][0], s01 = acc[a][1], s10 = acc[a][2], s11 = acc[a][3];
+          for (int e = 0; e < cnt; ++e) {
+            const T a0 = pa[e * ldt], a1 = pa[e * ldt + 1];
+            const T b0 = pb[e * ldt], b1 = pb[e * ldt + 1];
+            s00 = fma(a0, b0, s00); s01 = fma(a0, b1, s01);
+            s10 = fma(a1, b0, s10); s11 = fma(a1, b1, s11);
+          }
+          acc[a][0] = s00; acc[a][1] = s01; acc[a][2] = s10; acc[a][3] = s11;
         }
       }
       if (tid < d) {
@@ -118,11 +149,17 @@ gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
     }
     // ---- Lambda = alpha + beta F'F ; rhs = beta F'r + alpha mu ---------------------------
 #pragma unroll
-    for (int a = 0; a < GIBBS_MAXACC; ++a) {
-      const int pr = tid + a * GIBBS_THREADS;
-      if (pr < d * d) {
-        const int k = pr / d, l = pr % d;
-        A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)acc[a];
+    for (int a = 0; a < GIBBS_MAXBLK; ++a) {
+      if (bks[a] >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = 2 * bks[a] + (q >> 1), l = 2 * bls[a] + (q & 1);
+          if (k < d && l < d) {
+            A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)acc[a][q];
+            if (k != l && bks[a] != bls[a])
+              A[l * lda + k] = (double)alpha[l * d + k] + beta * (double)acc[a][q];
+          }
+        }
       }
     }
     if (tid < d) {
@@ -209,7 +246,7 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
   if (row_begin >= row_end) return AMF_OK;
   const int rows = row_end;
   const size_t smem = sizeof(double) * (2 * d * (d + 1) + 2 * d + GIBBS_TILE) +
-                      sizeof(T) * GIBBS_TILE * (d + 1);
+                      sizeof(T) * GIBBS_TILE * (((d + 1) & ~1) + 2);
   AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);

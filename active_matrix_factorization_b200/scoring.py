@@ -70,7 +70,7 @@ class Pool:
     score it every active-learning step.  Scores and the winner are reported in the caller's
     order, exactly like the unbucketed path."""
 
-    def __init__(self, ii, jj, n_users, n_items, name, d, tile_bytes=64 * 1024, block_bytes=64 * 1024):
+    def __init__(self, ii, jj, n_users, n_items, name, d, tile_bytes=128 * 1024):
         import ctypes as C
         lib = N.require_device()
         self.name, self.d = name, int(d)
@@ -90,12 +90,10 @@ class Pool:
             rows = max(1, min(32768, nbytes // row_bytes))
             return 1 << (rows.bit_length() - 1)                  # power of two
         self.tile_rows = int(pow2_rows(tile_bytes))
-        self.block_rows = int(pow2_rows(block_bytes))
         self._h = C.c_void_p()
         torch.cuda.current_stream().synchronize()
         N.check(lib.amf_pool_create(C.byref(self._h), self.ncand, D.ptr(ci), D.ptr(cj),
-                                    self.n_users, self.n_items, self.tile_rows, self.block_rows,
-                                    D.stream_ptr()))
+                                    self.n_users, self.n_items, self.tile_rows, D.stream_ptr()))
 
     def score_pred(self, U, V, want_scores=False, maximize=True, index_base=0, best=None):
         """U, V: device tensors padded to (rows, self.ld) -- see pad().  Returns (scores tensor

@@ -150,14 +150,16 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
                          const amf_normal_view_t* nv, double cutoff, void* scores_d,
                          int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
 
-/* Candidate pool handle: the pool bucketed once by (item tile of tile_rows items, user block of
- * block_rows users), local indices packed in 4 bytes per candidate, so the scoring kernel keeps
- * the tile of V resident in shared memory and streams the U blocks through a double-buffered TMA
- * pipeline; built from the caller's (i, j) arrays, remembers the caller's order.  Replaces the `pool` list / `unrated` set iterated in
+/* Candidate pool handle: the pool bucketed once by item tile (tile_rows items, a power of two),
+ * each candidate packed into 4 bytes (i << log2(tile_rows) | j % tile_rows; needs
+ * bits(n_users) + log2(tile_rows) <= 32), sorted by user inside a tile.  The scoring kernel keeps
+ * the tile of V resident in shared memory (TMA bulk copies), holds the user row in registers and
+ * re-fetches it only when the user changes; built from the caller's (i, j) arrays, remembers the
+ * caller's order.  Replaces the `pool` list / `unrated` set iterated in
  * active_pmf.py:725-770 when the same pool is scored repeatedly (every active-learning step). */
 typedef struct amf_pool amf_pool_t;
 int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
-                    int32_t n_users, int32_t n_items, int tile_rows, int block_rows, void* stream);
+                    int32_t n_users, int32_t n_items, int tile_rows, void* stream);
 int amf_pool_destroy(amf_pool_t* h);
 int64_t amf_pool_size(const amf_pool_t* h);
 /* Removes candidates (given by their positions in the caller's order) from the pool in O(1)

@@ -76,7 +76,7 @@ def test_tiled_pool_matches_flat_and_oracle(S, n, m, d, nc, tile_bytes, dtype, t
     ii, jj = rng.randint(0, n, nc), rng.randint(0, m, nc)       # caller's order: unsorted
     ii[5], jj[5] = ii[nc - 7], jj[nc - 7]                        # a duplicate pair -> exact tie
     flat, (fv, fi) = S.score_pred(U, V, ii, jj, dtype)
-    pool = S.Pool(ii, jj, n, m, dtype, d, tile_bytes=tile_bytes, block_bytes=max(256, tile_bytes // 4))
+    pool = S.Pool(ii, jj, n, m, dtype, d, tile_bytes=tile_bytes)
     Ut, Vt = pool.pad(U), pool.pad(V)
     for maximize in (True, False):
         sc, best = pool.score_pred(Ut, Vt, want_scores=True, maximize=maximize)
@@ -96,7 +96,7 @@ def test_tiled_pool_ties_and_empty(S):
     from active_matrix_factorization_b200 import device as D
     U = np.ones((5, 3)); V = np.ones((40, 3))
     ii = np.array([4, 1, 2, 3, 0, 0]); jj = np.array([39, 1, 20, 3, 0, 17])
-    pool = S.Pool(ii, jj, 5, 40, "f64", 3, tile_bytes=512, block_bytes=64)   # several buckets, all tied
+    pool = S.Pool(ii, jj, 5, 40, "f64", 3, tile_bytes=512)   # several tiles, all tied
     Ut, Vt = pool.pad(U), pool.pad(V)
     _, best = pool.score_pred(Ut, Vt)
     assert S.unpack_best(best) == (3.0, 0)                       # first in the caller's order

@@ -27,6 +27,7 @@
 namespace amf {
 constexpr int POOL_RUN = 16;                    // batches of 32 candidates per chunk
 constexpr int POOL_CHUNK = 32 * POOL_RUN;       // candidates per chunk (one warp, one grab)
+static_assert(POOL_RUN >= 2, "the index words are prefetched two batches ahead");
 constexpr int POOL_THREADS = 1024;              // one CTA per SM
 constexpr uint32_t POOL_TOMBSTONE = 0xffffffffu;   // orig[] value of padding / removed candidates
 }  // namespace amf
@@ -35,8 +36,8 @@ struct amf_pool {
   int64_t ncand;         // candidates given by the caller
   int64_t npad;          // entries in the bucketed arrays (every tile padded to whole chunks)
   int32_t n_users, n_items;
-  int tile_rows;         // TJ: items per tile (V tile resident in shared memory), power of two
-  int jbits;             // log2(tile_rows)
+  int tile_rows;         // TJ: items per tile (V tile resident in shared memory)
+  int jbits;             // bits of the local item index: ceil(log2(tile_rows))
   int n_tiles;
   int64_t n_chunks;      // npad / POOL_CHUNK
   uint32_t* cw;          // [npad] packed indices  i << jbits | j % TJ   (padding: 0)
@@ -52,12 +53,12 @@ namespace amf {
 int acquire_partials(Best** out, cudaStream_t s);
 
 __global__ void pool_keys_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj,
-                                 int64_t n, int jbits, int ibits, uint64_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+                                 int64_t n, int tile_rows, int jbits, int ibits,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
        t += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t i = (uint32_t)ci[t], j = (uint32_t)cj[t];
-    const uint64_t tile = j >> jbits, jl = j & ((1ull << jbits) - 1);
+    const uint64_t tile = j / (uint32_t)tile_rows, jl = j % (uint32_t)tile_rows;
     keys[t] = (((tile << ibits) | i) << jbits) | jl;
     vals[t] = (uint32_t)t;
   }
@@ -180,19 +181,18 @@ template <typename T, int NVEC, bool MAX>
 __global__ void __launch_bounds__(POOL_THREADS, 1)
 pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ orig,
                  const int64_t* __restrict__ tile_cstart, int n_tiles, int64_t n_chunks,
-                 int jbits, int n_items, const T* __restrict__ U, const T* __restrict__ Vm,
-                 T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
+                 int jbits, int tile_rows, int n_items, const T* __restrict__ U,
+                 const T* __restrict__ Vm, T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
   using V = typename Vec<T>::type;
   constexpr int CPL = NVEC >= 4 ? NVEC / 4 : 1;       // 16-byte slices per lane
   constexpr uint32_t ROW_BYTES = NVEC * 16;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_v;
-  __shared__ unsigned long long s_ctr;
+  __shared__ unsigned int s_ctr;
   const uint32_t smem0 = smem_u32(smem_raw);
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, l = lane & 3;
-  const int tile_rows = 1 << jbits;
-  const uint32_t jmask = (uint32_t)tile_rows - 1;
+  const uint32_t jmask = (1u << jbits) - 1;
   const bool have = l < NVEC;                         // rows narrower than four slices
   // slice t of this lane: off[t] = (l + 4 * ((t + group parity) mod CPL)) * 16 = off[0] ^ xo[t]
   const uint32_t off0 = (uint32_t)((have ? l : 0) + 4 * ((g & 1) % CPL)) * 16u;
@@ -215,7 +215,7 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
     }
     t_cur = lo;
   }
-  T best_v = MAX ? -INFINITY : INFINITY;
+  T best_v = MAX ? -INFINITY : INFINITY, thr = best_v;
   int64_t best_o = -1;
   V a[CPL];
 #pragma unroll
@@ -228,7 +228,7 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
     const int64_t seg_end = min(c_hi, tile_cstart[t_cur + 1]);
     __syncthreads();                                  // previous tile and counter are done with
     if (threadIdx.x == 0) {
-      s_ctr = (unsigned long long)c;
+      s_ctr = 0;
       const int rows = min(tile_rows, n_items - t_cur * tile_rows);
       const uint32_t bytes = (uint32_t)rows * ROW_BYTES;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -243,17 +243,19 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
     phase_v ^= 1;
 
     for (;;) {
-      unsigned long long grab = 0;
-      if (lane == 0) grab = atomicAdd(&s_ctr, 1ull);
-      const int64_t chunk = (int64_t)__shfl_sync(0xffffffffu, grab, 0);
+      unsigned int grab = 0;
+      if (lane == 0) grab = atomicAdd(&s_ctr, 1u);
+      const int64_t chunk = c + (int64_t)__shfl_sync(0xffffffffu, grab, 0);
       if (chunk >= seg_end) break;
       const int64_t cb = chunk * POOL_CHUNK;
       const uint4* wp = reinterpret_cast<const uint4*>(cw + cb) + g;
-      uint4 wn = __ldcs(wp);
+      // index words two batches ahead (HBM latency)
+      uint4 w1 = __ldcs(wp), w2 = __ldcs(wp + 8);
 #pragma unroll 1
       for (int r = 0; r < POOL_RUN; ++r) {
-        const uint4 w4 = wn;
-        if (r + 1 < POOL_RUN) wn = __ldcs(wp + (r + 1) * 8);
+        const uint4 w4 = w1;
+        w1 = w2;
+        if (r + 2 < POOL_RUN) w2 = __ldcs(wp + (r + 2) * 8);
         const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
         T p[4];
 #pragma unroll
@@ -290,13 +292,26 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
         }
         const int64_t pos = cb + r * 32 + lane;
         if (scores) __stcs(scores + pos, p[0]);
-        if (MAX ? (p[0] >= best_v) : (p[0] <= best_v)) {          // rare after warm-up
-          const uint32_t ou = orig[pos];
-          const int64_t o = (int64_t)ou;
-          if (ou != POOL_TOMBSTONE &&
-              (best_o < 0 || (MAX ? (p[0] > best_v) : (p[0] < best_v)) || o < best_o)) {
-            best_v = p[0]; best_o = o;
+        // arg-best: `thr` is the best value any lane of this warp holds; only scores that reach
+        // it (ties included: a lower index may still win) look up their original position
+        const bool reach = MAX ? (p[0] >= thr) : (p[0] <= thr);
+        if (__any_sync(0xffffffffu, reach)) {
+          if (reach) {
+            const uint32_t ou = orig[pos];
+            const int64_t o = (int64_t)ou;
+            if (ou != POOL_TOMBSTONE &&
+                (best_o < 0 || (MAX ? (p[0] > best_v) : (p[0] < best_v)) ||
+                 (p[0] == best_v && o < best_o))) {
+              best_v = p[0]; best_o = o;
+            }
           }
+          T v = best_v;                               // +-inf while the lane holds nothing
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const T other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = MAX ? (other > v ? other : v) : (other < v ? other : v);
+          }
+          thr = v;
         }
       }
     }
@@ -327,7 +342,8 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
     AMF_CUDA(cudaFuncSetAttribute(pool_pred_kernel<T, NVEC_, MAX>,                              \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     pool_pred_kernel<T, NVEC_, MAX><<<grid, POOL_THREADS, smem, s>>>(                           \
-        h->cw, h->orig, h->tile_cstart, h->n_tiles, h->n_chunks, h->jbits, h->n_items, U, V,    \
+        h->cw, h->orig, h->tile_cstart, h->n_tiles, h->n_chunks, h->jbits, h->tile_rows,        \
+        h->n_items, U, V,                                                                       \
         scores_tmp, index_base, part);                                                          \
   } while (0)
   switch (nvec) {            // the row width is a compile-time constant of the kernel
@@ -365,8 +381,7 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
                     int32_t n_users, int32_t n_items, int tile_rows, void* stream) {
   AMF_REQUIRE(out && n_users > 0 && n_items > 0, "amf_pool_create: bad arguments");
   AMF_REQUIRE(ncand >= 0 && ncand < (1ll << 32) - 2 * POOL_CHUNK, "amf_pool_create: ncand out of range");
-  AMF_REQUIRE(tile_rows >= 1 && tile_rows <= 32768 && (tile_rows & (tile_rows - 1)) == 0,
-              "amf_pool_create: tile_rows must be a power of two <= 32768");
+  AMF_REQUIRE(tile_rows >= 1 && tile_rows <= 32768, "amf_pool_create: tile_rows must be in [1, 32768]");
   int jbits = 0;
   while ((1 << jbits) < tile_rows) ++jbits;
   const int ibits = bits_for_count((uint64_t)n_users);
@@ -407,7 +422,7 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
     POOL_CUDA(cudaMalloc(&vals, 4 * cnt));
     POOL_CUDA(cudaMalloc(&perm, 4 * cnt));
     if (ncand > 0) {
-      pool_keys_kernel<<<grid, 256, 0, s>>>(ci_d, cj_d, ncand, jbits, ibits, keys, vals);
+      pool_keys_kernel<<<grid, 256, 0, s>>>(ci_d, cj_d, ncand, tile_rows, jbits, ibits, keys, vals);
       POOL_CUDA(cudaGetLastError());
       POOL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, perm,
                                                 ncand, 0, ibits + jbits + tbits, s));
@@ -495,7 +510,7 @@ int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const vo
     tmp_scores = h->tmp_scores;
   }
   const size_t smem = (size_t)h->tile_rows * ld * es;
-  AMF_REQUIRE(smem <= 224 * 1024, "item tile (%d rows of %d) does not fit shared memory",
+  AMF_REQUIRE(smem <= 225 * 1024, "item tile (%d rows of %d) does not fit shared memory",
               h->tile_rows, ld);
   int64_t grid64 = (int64_t)num_sms();
   if (grid64 > h->n_chunks) grid64 = h->n_chunks > 0 ? h->n_chunks : 1;

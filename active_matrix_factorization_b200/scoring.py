@@ -70,7 +70,7 @@ class Pool:
     score it every active-learning step.  Scores and the winner are reported in the caller's
     order, exactly like the unbucketed path."""
 
-    def __init__(self, ii, jj, n_users, n_items, name, d, tile_bytes=128 * 1024):
+    def __init__(self, ii, jj, n_users, n_items, name, d, tile_bytes=224 * 1024):
         import ctypes as C
         lib = N.require_device()
         self.name, self.d = name, int(d)
@@ -86,10 +86,8 @@ class Pool:
             raise ValueError("latent_d=%d is too large for the bucketed pool" % d)
         self.ld = ld = nvec * vec
         row_bytes = ld * (4 if name == "f32" else 8)
-        def pow2_rows(nbytes):
-            rows = max(1, min(32768, nbytes // row_bytes))
-            return 1 << (rows.bit_length() - 1)                  # power of two
-        self.tile_rows = int(pow2_rows(tile_bytes))
+        # as many item rows as fit the shared-memory budget (the kernel takes any tile height)
+        self.tile_rows = int(max(1, min(32768, tile_bytes // row_bytes)))
         self._h = C.c_void_p()
         torch.cuda.current_stream().synchronize()
         N.check(lib.amf_pool_create(C.byref(self._h), self.ncand, D.ptr(ci), D.ptr(cj),

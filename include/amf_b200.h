@@ -150,9 +150,9 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
                          const amf_normal_view_t* nv, double cutoff, void* scores_d,
                          int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
 
-/* Candidate pool handle: the pool bucketed once by item tile (tile_rows items, a power of two),
- * each candidate packed into 4 bytes (i << log2(tile_rows) | j % tile_rows; needs
- * bits(n_users) + log2(tile_rows) <= 32), sorted by user inside a tile.  The scoring kernel keeps
+/* Candidate pool handle: the pool bucketed once by item tile (tile_rows items),
+ * each candidate packed into 4 bytes (i << ceil(log2(tile_rows)) | j % tile_rows; needs
+ * bits(n_users) + ceil(log2(tile_rows)) <= 32), sorted by user inside a tile.  The scoring kernel keeps
  * the tile of V resident in shared memory (TMA bulk copies), holds the user row in registers and
  * re-fetches it only when the user changes; built from the caller's (i, j) arrays, remembers the
  * caller's order.  Replaces the `pool` list / `unrated` set iterated in

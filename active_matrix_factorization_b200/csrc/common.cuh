@@ -139,6 +139,17 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
 
 }  // namespace amf
 
+// One side of the tiled copy of the rating list (tiled.cu): entries bucketed by tile of the
+// "tile side" matrix, sorted by the row of the "stream side" inside a tile.
+struct amf_tiled_side {
+  int tile_rows, jbits, n_tiles;
+  int64_t n_chunks, npad;
+  uint32_t* cw;           // [npad] stream row << jbits | local tile row   (padding: 0)
+  void* rv;               // [npad] ratings (padding: 0)
+  int64_t* tile_cstart;   // [n_tiles+1] first chunk of every tile
+  int64_t* tile_count;    // [n_tiles] entries of every tile
+};
+
 struct amf_ratings {
   int32_t n_users, n_items;
   int64_t nnz;
@@ -154,6 +165,10 @@ struct amf_ratings {
   size_t stage_bytes[8];
   double* sums_d;
   int device;
+  // side 0: users stream past item tiles (dU); side 1: items stream past user tiles (dV)
+  amf_tiled_side tiled[2];
+  int tiled_row_bytes;    // padded factor-row size the tiles were cut for (0 = not built)
+  int tiled_mode;         // AMF_LAYOUT_AUTO / _ROWS / _TILED
 };
 
 #define AMF_SUB 32

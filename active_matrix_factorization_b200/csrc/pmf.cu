@@ -21,6 +21,13 @@
 
 namespace amf {
 
+// tiled.cu: the shared-memory-tiled copy of the list and the fused pass that runs on it
+int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V, const void* dU,
+                  const void* dV, bool* use, cudaStream_t s);
+template <typename T>
+int tiled_loss_grad(const amf_ratings* h, int ld, const T* U, const T* V, T inv_sigma,
+                    T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s);
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 prior_kernel(const T* __restrict__ X, int64_t count, T neg_inv_sigma, T* __restrict__ dX,
@@ -349,6 +356,10 @@ static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V
   if (h->nnz == 0) return AMF_OK;
   const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
   int rc;
+  bool tiled = false;
+  rc = tiled_prepare(const_cast<amf_ratings*>(h), (size_t)ld * sizeof(T), U, V, dU, dV, &tiled, s);
+  if (rc != AMF_OK) return rc;
+  if (tiled) return tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s);
   if (dU) {
     rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
     if (rc != AMF_OK) return rc;

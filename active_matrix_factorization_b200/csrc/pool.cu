@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tile_stream.cuh"
 
 namespace amf {
 constexpr int POOL_RUN = 16;                    // batches of 32 candidates per chunk
@@ -107,65 +108,6 @@ static int bits_for_count(uint64_t x) {
   int b = 1;
   while (b < 63 && (1ull << b) < x) ++b;
   return b;
-}
-
-// ---- TMA (bulk async copy) + mbarrier helpers: inline PTX for sm_100a ----------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-__device__ __forceinline__ float4 lds_v(uint32_t addr, float4) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double2 lds_v(uint32_t addr, double2) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-// read-only 16-byte load of a factor-row slice (L2 resident)
-__device__ __forceinline__ float4 ldg_v(const unsigned char* p, float4) {
-  return __ldg(reinterpret_cast<const float4*>(p));
-}
-__device__ __forceinline__ double2 ldg_v(const unsigned char* p, double2) {
-  return __ldg(reinterpret_cast<const double2*>(p));
-}
-__device__ __forceinline__ float vdot_acc(const float4& a, const float4& b, float acc) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
-}
-__device__ __forceinline__ double vdot_acc(const double2& a, const double2& b, double acc) {
-  return fma(a.x, b.x, fma(a.y, b.y, acc));
 }
 
 // PRED over a bucketed pool.  One CTA per SM owns a contiguous range of chunks; for every item

@@ -131,6 +131,7 @@ static int build_side(amf_ratings* h, int side, const int32_t* key_d, const int3
 
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
+void tiled_free(amf_ratings* h);
 
 }  // namespace amf
 
@@ -213,6 +214,7 @@ int amf_ratings_destroy(amf_ratings_t* h) {
   }
   for (int k = 0; k < 8; ++k) cudaFree(h->stage[k]);
   cudaFree(h->sums_d);
+  amf::tiled_free(h);
   delete h;
   return AMF_OK;
 }

@@ -98,6 +98,14 @@ class Ratings:
             N.check(lib.amf_ratings_create_host(C.byref(self._h), self.n_users, self.n_items,
                                                 self.nnz, N.host_ptr(i), N.host_ptr(j),
                                                 N.host_ptr(r), code(name)))
+        layout = os.environ.get("AMF_B200_LAYOUT", "auto")
+        if layout != "auto":
+            self.set_layout(layout)
+
+    def set_layout(self, mode):
+        """'auto' | 'rows' | 'tiled': which copy of the list the fused loss+gradient runs on
+        (amf_ratings_set_layout)."""
+        N.check(N.load().amf_ratings_set_layout(self.handle, {"auto": 0, "rows": 1, "tiled": 2}[mode]))
 
     @classmethod
     def from_tuples(cls, ratings, n_users, n_items, name):

@@ -65,6 +65,14 @@ int64_t amf_ratings_nnz(const amf_ratings_t* h);
 int amf_ratings_layout(const amf_ratings_t* h, int side, const int64_t** ptr_d,
                        const int32_t** idx_d, const void** val_d);
 /* sum and count of ratings -> mean_rating (pmf_cy.pyx:63); synchronises. */
+/* Which copy of the list amf_pmf_loss_grad runs on.  AUTO: the tiled copy (item / user tiles of
+ * the factor matrices resident in shared memory, built on first use, +8 or +12 bytes per rating
+ * and side) when nnz >= 2^20 and the padded factor row is 64, 128 or 256 bytes, else the
+ * row-sorted lists; ROWS / TILED force one (TILED fails with AMF_ERR_UNSUPPORTED if it cannot). */
+#define AMF_LAYOUT_AUTO 0
+#define AMF_LAYOUT_ROWS 1
+#define AMF_LAYOUT_TILED 2
+int amf_ratings_set_layout(amf_ratings_t* h, int mode);
 int amf_ratings_mean(const amf_ratings_t* h, double* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 // chunk, every group of four lanes walks TILED_RUN*4 CONSECUTIVE sorted entries while each
 // batch of 32 is one coalesced 128-byte read.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tile_stream.cuh"
@@ -216,6 +217,16 @@ __device__ __forceinline__ void axpy_slices(double2 (&acc)[C], double w, const d
 #pragma unroll
   for (int t = 0; t < C; ++t) vfma(acc[t], w, b[t]);
 }
+// fire-and-forget vector reduction into global memory
+__device__ __forceinline__ void red_add(float* p, const float4& v) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red_add(double* p, const double2& v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v.x) : "memory");
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(v.y) : "memory");
+}
 __device__ __forceinline__ void ld4(const float* p, float (&out)[4]) {
   const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
   out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
@@ -305,9 +316,11 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
       const bool check = nvalid < TILED_CHUNK;        // warp-uniform
       const uint4* wp = reinterpret_cast<const uint4*>(cw + cb) + g;
       const T* rp = rv + cb + g * 4;
-      uint4 wn = __ldcs(wp);
-      T rn[4];
-      ld4(rp, rn);
+      // index words and ratings two batches ahead (HBM latency)
+      uint4 w1 = __ldcs(wp), w2 = __ldcs(wp + 8);
+      T r1[4], r2[4];
+      ld4(rp, r1);
+      ld4(rp + 32, r2);
       V a[CPL], acc[CPL];
 #pragma unroll
       for (int t = 0; t < CPL; ++t) { a[t] = vzero(V()); acc[t] = vzero(V()); }
@@ -316,11 +329,14 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
 #pragma unroll 1
       for (int r = 0; r < TILED_RUN; ++r) {
         T sq = 0;
-        uint32_t w[4] = {wn.x, wn.y, wn.z, wn.w};
-        T rs[4] = {rn[0], rn[1], rn[2], rn[3]};
-        if (r + 1 < TILED_RUN) {
-          wn = __ldcs(wp + (r + 1) * 8);
-          ld4(rp + (r + 1) * 32, rn);
+        const uint32_t w[4] = {w1.x, w1.y, w1.z, w1.w};
+        const T rs[4] = {r1[0], r1[1], r1[2], r1[3]};
+        w1 = w2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r1[q] = r2[q];
+        if (r + 2 < TILED_RUN) {
+          w2 = __ldcs(wp + (r + 2) * 8);
+          ld4(rp + (r + 2) * 32, r2);
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -336,7 +352,7 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
               const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
 #pragma unroll
               for (int t = 0; t < CPL; ++t)
-                vred_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
+                red_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
             }
             prev_i = i;
             const uint64_t up = own0 + (uint64_t)i * ROW_BYTES;
@@ -359,7 +375,7 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
       if (GRAD && prev_i != NONE && have) {
         const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
 #pragma unroll
-        for (int t = 0; t < CPL; ++t) vred_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
+        for (int t = 0; t < CPL; ++t) red_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
       }
       if (l == 0) local_sq += chunk_sq;
     }
@@ -371,6 +387,11 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
   }
 }
 
+static int tiled_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <typename T, bool GRAD>
 static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, const T* Tile,
                         T inv_sigma, T mean_offset, T* dOwn, double* sq_err, cudaStream_t s) {
@@ -380,7 +401,9 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
   int64_t grid64 = (int64_t)num_sms();
   if (grid64 > t->n_chunks) grid64 = t->n_chunks > 0 ? t->n_chunks : 1;
   const int grid = (int)grid64;
-  constexpr int THREADS = sizeof(T) == 4 ? 768 : 512;
+  // 64 registers per thread (fp32) keep 32 warps on the SM: the pass is bound by the latency of
+  // the row fetch at every (row, tile) visit, so resident warps are what hides it
+  constexpr int THREADS = sizeof(T) == 4 ? 1024 : 512;
 #define TILED(NVEC_)                                                                              \
   do {                                                                                            \
     AMF_CUDA(cudaFuncSetAttribute(tiled_side_kernel<T, NVEC_, THREADS, GRAD>,                     \
@@ -421,7 +444,7 @@ int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V
   }
   if (h->tiled_mode == AMF_LAYOUT_AUTO && h->nnz < TILED_AUTO_MIN_NNZ) return AMF_OK;
   if (h->tiled_row_bytes != (int)row_bytes) {
-    const int tile_rows = (int)((224 * 1024) / row_bytes);
+    const int tile_rows = (int)(((size_t)tiled_env("AMF_TILED_KB", 224) * 1024) / row_bytes);
     int rc = AMF_OK;
     for (int side = 0; side < 2 && rc == AMF_OK; ++side) {
       const int32_t tile_side_rows = side == 0 ? h->n_items : h->n_users;

@@ -1,0 +1,40 @@
+"""Times the tiled fused loss+gradient (tiled_side_kernel x2 + prior x2) on the C5 rating list
+for experiment settings given as FLAGS:TILE_KB pairs (AMF_TILED_FLAGS / AMF_TILED_KB), each in
+a child process; 'rows' times the row-sorted kernels."""
+import os, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1 and sys.argv[1] == "--child":
+    import ctypes as C, types
+    import torch
+    import bench
+    from active_matrix_factorization_b200 import _native as N, device as D
+    a = types.SimpleNamespace(users=200_000, items=50_000, latent_d=32, nnz=50_000_000, ncand=1_000_000, dtype="f32")
+    torch.cuda.set_device(0)
+    p = bench.make_problem(a, 0, torch)
+    rat = D.Ratings(a.users, a.items, p["ri"], p["rj"], p["r"], "f32")
+    rat.set_layout(sys.argv[2])
+    lib = N.require_device()
+    U, V = p["U"], p["V"]
+    dU, dV = torch.empty_like(U), torch.empty_like(V)
+    sums = torch.zeros(3, dtype=torch.float64, device="cuda")
+    params = D.pmf_params(1.0, 10.0, 10.0, 0.0)
+    def run():
+        N.check(lib.amf_pmf_loss_grad(rat.handle, N.F32, 32, 32, D.ptr(U), D.ptr(V), C.byref(params),
+                                      D.ptr(dU), D.ptr(dV), D.ptr(sums), D.stream_ptr()))
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): run()
+    e1.record(); torch.cuda.synchronize()
+    print("%s flags=%s tile_kb=%s: %.4f ms  sums=%s |dU|=%.6e |dV|=%.6e" % (
+        sys.argv[2], os.environ.get("AMF_TILED_FLAGS"), os.environ.get("AMF_TILED_KB"), e0.elapsed_time(e1) / 20,
+        sums.cpu().numpy(), dU.double().norm().item(), dV.double().norm().item()))
+else:
+    for spec in sys.argv[1:] or ["1:224"]:
+        if spec == "rows":
+            subprocess.run([sys.executable, __file__, "--child", "rows"], check=True)
+            continue
+        flags, _, kb = spec.partition(":")
+        env = dict(os.environ, AMF_TILED_FLAGS=flags, AMF_TILED_KB=kb or "224")
+        subprocess.run([sys.executable, __file__, "--child", "tiled"], env=env, check=True)

@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--pool", default="tiled", choices=["tiled", "flat"],
                     help="candidate pool layout for the device-resident scoring phase")
+    ap.add_argument("--layout", default="auto", choices=["auto", "rows", "tiled"],
+                    help="rating-list copy the fused loss+gradient runs on (amf_ratings_set_layout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     return ap.parse_args()
@@ -56,9 +58,9 @@ def workload_name(a):
 def measured_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
     kernels, from the committed `ncu --set full` capture of this same command
-    (profiles/r01d_final_ncu_full_raw.csv); None if the summary file is missing."""
+    (profiles/r01e_tiled_ncu_full_raw.csv); None if the summary file is missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return {}
@@ -319,7 +321,9 @@ def run_ours(a):
     es = 4 if name == "f32" else 8
     prob = make_problem(a, rank, torch)
     rat = D.Ratings(n, m, prob["ri"], prob["rj"], prob["r"], name)
+    rat.set_layout(a.layout)
     nnz, ncand = rat.nnz, int(prob["ci"].numel())
+    tiled_grad = a.layout == "tiled" or (a.layout == "auto" and nnz >= (1 << 20) and d * es in (64, 128, 256))
     U, V, ci, cj = prob["U"], prob["V"], prob["ci"], prob["cj"]
     ld = D.padded_ld(d, name)
     assert ld == d, "bench uses an unpadded rank"
@@ -437,21 +441,22 @@ def run_ours(a):
         "vs_baseline": None, "dtype": name, "data": "synthetic",
         "config": {"workload": workload_name(a), "criterion": "pred (MAP prediction) with fused arg-max, winner only", "pool_layout": a.pool,
                    "parallelism": "candidates and ratings sharded per GPU (weak), NCCL all-reduce of dU/dV/sums + all-gather of winners" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (rating list %.0f MB x2 layouts, candidates %.0f MB per GPU)" % (nnz * 8 / 1e6, ncand * 8 / 1e6),
+                   "l2": "inputs larger than L2 (rating list %.0f MB per side, packed candidate pool %.0f MB per GPU)" % (nnz * 8 / 1e6, ncand * 4 / 1e6),
+                   "rating_layout": "tiled" if tiled_grad else "rows",
                    "value_is": "candidates / scoring-phase time; ms_per_step covers gradient + scoring"},
         "phases": {
             "pmf_loss_grad": {"ms": grad_ms / a.steps, "ratings_per_sec_iter": nnz_all / (grad_ms / a.steps * 1e-3), "nnz_total": nnz_all},
             "score_pred": {"ms": score_ms / a.steps, "candidates_per_sec": ncand_all / (score_ms / a.steps * 1e-3), "ncand_total": ncand_all},
         },
-        "roofline": {"kernel": "pool_pred_kernel (V tile in shared memory via TMA)" if a.pool == "tiled" else "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
+        "roofline": {"kernel": "pool_pred_kernel (V tile in shared memory via TMA, U row in registers)" if a.pool == "tiled" else "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
                      "peak_source": peak_kind, "unit": "GB/s", "frac": score_gbs / hbm_peak,
                      "algorithmic_bytes": score_bytes, "kernel_ms": scorek_ms,
                      "traffic": traffic.get("pool_pred_kernel" if a.pool == "tiled" else "score_pred_kernel"),
                      "flat_kernel_ms": score_flat_ms, "pool_build_ms": pool_ms},
-        "roofline_gradient": {"kernel": "side_pass_kernel x2 + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
+        "roofline_gradient": {"kernel": ("tiled_side_kernel x2" if tiled_grad else "side_pass_kernel x2") + " + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
                               "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": grad_gbs / hbm_peak,
                               "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms,
-                              "traffic": traffic.get("side_pass_kernel_x2")},
+                              "traffic": traffic.get("tiled_side_kernel_x2" if tiled_grad else "side_pass_kernel_x2")},
         "e2e": {"value": ncand_all / e2e_score_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(ncand * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
                 "pmf_ratings_per_sec_iter": nnz_all / e2e_grad_s,

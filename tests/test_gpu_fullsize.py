@@ -82,7 +82,9 @@ def test_scoring_invariants_full_size(problem):
     # (3) the bucketed (TMA-tiled) pool reproduces scores and winner, in the caller's order
     pool = S.Pool(ci, cj, n, m, "f32", d)
     sc2, best2 = pool.score_pred(U, V, want_scores=True)
-    assert S.unpack_best(best2) == (bv, bi)
+    bv2, bi2 = S.unpack_best(best2)
+    # same winner; the value may differ in the last bits (fp32 sums taken in a different order)
+    assert bi2 == bi and bv2 == pytest.approx(bv, rel=1e-6) and bv2 == sc2[bi].item()
     assert (sc2 - sc).abs().max().item() <= 1e-5 * sc.abs().max().item()
     # (4) permutation invariance: a shuffled pool selects the same (i, j) with the same value
     perm = torch.randperm(nc, device=ci.device)

@@ -275,6 +275,18 @@ using namespace amf;
 extern "C" {
 #pragma GCC visibility push(default)
 
+int amf_best_reduce(const amf_best_t* recs_d, int n, int maximize, amf_best_t* out_d,
+                    void* stream) {
+  AMF_REQUIRE(recs_d && out_d && n >= 0, "amf_best_reduce: bad arguments");
+  static_assert(sizeof(Best) == sizeof(amf_best_t), "record layouts must agree");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Best* part = reinterpret_cast<const Best*>(recs_d);
+  if (maximize) best_final_kernel<true><<<1, 256, 0, s>>>(part, n, out_d);
+  else best_final_kernel<false><<<1, 256, 0, s>>>(part, n, out_d);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
+}
+
 int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t* ci_d,
                          const int32_t* cj_d, int d, int ld, const void* U_d, const void* V_d,
                          const amf_normal_view_t* nvp, double cutoff, void* scores_d,

@@ -151,7 +151,8 @@ class ShardedStep:
         self._rec = None
         self.pool = None          # optional scoring.Pool (tiled layout) for the pred criterion
         # kernels launched by one step: 2 prior + 2 side passes; scoring + winner reduction
-        self.launches_per_step = 6
+        # (+ the reduction of the gathered winners on multi-GPU runs)
+        self.launches_per_step = 6 + (1 if world > 1 else 0)
 
     def set_candidate_offset(self, ncand_local):
         """global index = offset of this rank's shard + local index"""
@@ -185,18 +186,11 @@ class ShardedStep:
                 C.byref(view) if view is not None else None, float(cutoff), None,
                 1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
         if self.world > 1:
+            # 16-byte all-gather of the per-rank winners, then one launch applies the same
+            # tie-break on every rank; no host sync inside the step
             rec = gather_winner(best, self.world)
-            vals = rec[:, 0].contiguous().view(torch.float64)
-            idx = rec[:, 1].contiguous()
-            # device-side reduction with the same tie-break; no host sync inside the step
-            valid = (idx >= 0) & ~torch.isnan(vals)
-            fill = -math.inf if maximize else math.inf
-            v = torch.where(valid, vals, torch.full_like(vals, fill))
-            top = v.max() if maximize else v.min()
-            tie = valid & (v == top)
-            win = torch.where(tie, idx, torch.full_like(idx, torch.iinfo(torch.int64).max)).min()
-            best[0] = top.view(torch.int64)
-            best[1] = torch.where(valid.any(), win, torch.full_like(win, -1))
+            N.check(lib.amf_best_reduce(D.ptr(rec), self.world, 1 if maximize else 0, D.ptr(best),
+                                        D.stream_ptr()))
 
     def kernel_times(self, U, V, params, dU, dV, sums, ci, cj, best, reps=5):
         """Average device time of the two dominant kernels, timed alone on the current stream

@@ -158,6 +158,11 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
                          const amf_normal_view_t* nv, double cutoff, void* scores_d,
                          int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
 
+/* Reduces n winner records (e.g. the all-gathered per-GPU winners of a sharded pool) to one with
+ * the rule of amf_score_candidates: best value, lowest index on ties, records with index < 0 or a
+ * NaN value never win; out = {0, -1} if none does.  recs_d and out_d may not alias. */
+int amf_best_reduce(const amf_best_t* recs_d, int n, int maximize, amf_best_t* out_d, void* stream);
+
 /* Candidate pool handle: the pool bucketed once by item tile (tile_rows items),
  * each candidate packed into 4 bytes (i << ceil(log2(tile_rows)) | j % tile_rows; needs
  * bits(n_users) + ceil(log2(tile_rows)) <= 32), sorted by user inside a tile.  The scoring kernel keeps

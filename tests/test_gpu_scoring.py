@@ -168,3 +168,28 @@ def test_pool_remove_matches_shrinking_set(S):
     alive = np.ones(nc, bool); alive[order[:20]] = False
     np.testing.assert_allclose(sc.cpu().numpy()[alive], ref[alive], rtol=1e-11, atol=1e-12)
     pool.close()
+
+
+def test_best_reduce_matches_host_rule(S):
+    """amf_best_reduce (the reduction of all-gathered per-GPU winners) applies the rule of
+    parallel.reduce_winners: best value, lowest index on ties, index < 0 and NaN never win"""
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D, parallel as P
+    lib = N.require_device()
+    cases = [([1.0, 3.0, 3.0, 2.0], [7, 9, 4, 1]),
+             ([float("nan"), -1.0, 5.0, 5.0], [0, 3, -1, 8]),
+             ([float("nan")], [2]),
+             ([2.5, 2.5], [-1, -1])]
+    for vals, idx in cases:
+        rec = torch.empty((len(vals), 2), dtype=torch.int64, device="cuda")
+        rec[:, 0] = torch.tensor(vals, dtype=torch.float64, device="cuda").view(torch.int64)
+        rec[:, 1] = torch.tensor(idx, dtype=torch.int64, device="cuda")
+        for maximize in (True, False):
+            out = torch.zeros(2, dtype=torch.int64, device="cuda")
+            N.check(lib.amf_best_reduce(D.ptr(rec), len(vals), 1 if maximize else 0, D.ptr(out),
+                                        D.stream_ptr()))
+            v, i = S.unpack_best(out)
+            hv, hi = P.reduce_winners(torch.tensor(vals, dtype=torch.float64), torch.tensor(idx), maximize)
+            assert i == hi
+            if i >= 0:
+                assert v == hv

@@ -304,7 +304,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -318,6 +318,11 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL's version
+    # banner) are sent to stderr until the line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
@@ -490,7 +495,9 @@ def run_ours(a):
         # parity spot check of the sample against the device path
         cb.pop("_best", None)
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

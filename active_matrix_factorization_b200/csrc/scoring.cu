@@ -272,6 +272,18 @@ int acquire_partials(Best** out, cudaStream_t s) {
 
 using namespace amf;
 
+namespace amf {
+// ci[p] = row of candidate p for a pool given by row offsets (warp per row)
+__global__ void expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
+                                   int32_t* __restrict__ ci) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) ci[p] = (int32_t)r;
+}
+}  // namespace amf
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -338,21 +350,26 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
   return launch_best_final(part, grid, maximize != 0, best_d, s);
 }
 
-int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,
-                        int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
-                        void* scores_h, int maximize, amf_best_t* best_h) {
+constexpr int HOST_CHUNKS = 8;   // pieces the candidate arrays cross PCIe in (large pools)
+
+// shared body of the host-buffer scoring calls: the candidate users come either as an array
+// (ci_h) or as row offsets into cj_h (ptr_h, n+1 entries), expanded on the device
+static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int64_t* ptr_h,
+                           const int32_t* cj_h, int32_t n, int32_t m, int d, const void* U_h,
+                           const void* V_h, void* scores_h, int maximize, amf_best_t* best_h) {
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_score_pred_host: bad dtype");
   AMF_REQUIRE(best_h && U_h && V_h, "amf_score_pred_host: NULL argument");
+  AMF_REQUIRE(ncand == 0 || (cj_h && (ci_h || ptr_h)), "amf_score_pred_host: NULL candidate arrays");
   const size_t es = dtype == AMF_F32 ? 4 : 8;
   const int vecn = dtype == AMF_F32 ? 4 : 2;
   const int ld = (d + vecn - 1) / vecn * vecn;
   // grow-only staging buffers, one set per host thread and device (freed at process exit)
-  struct Stage { void* p[6]; size_t n[6]; int dev; };
+  struct Stage { void* p[7]; size_t n[7]; int dev; };
   static thread_local Stage st = {{nullptr}, {0}, -1};
   int dev = 0;
   AMF_CUDA(cudaGetDevice(&dev));
   if (st.dev != dev) {
-    for (int q = 0; q < 6; ++q) { if (st.p[q]) cudaFree(st.p[q]); st.p[q] = nullptr; st.n[q] = 0; }
+    for (int q = 0; q < 7; ++q) { if (st.p[q]) cudaFree(st.p[q]); st.p[q] = nullptr; st.n[q] = 0; }
     st.dev = dev;
   }
   auto need = [&](int q, size_t bytes) -> int {
@@ -366,32 +383,78 @@ int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int
   const size_t nc = ncand > 0 ? (size_t)ncand : 1;
   int rc;
   if ((rc = need(0, (size_t)n * ld * es)) || (rc = need(1, (size_t)m * ld * es)) ||
-      (rc = need(2, 4 * nc)) || (rc = need(3, 4 * nc)) || (rc = need(4, sizeof(amf_best_t))) ||
-      (scores_h && (rc = need(5, es * nc))))
+      (rc = need(2, 4 * nc)) || (rc = need(3, 4 * nc)) ||
+      (rc = need(4, sizeof(amf_best_t) * (HOST_CHUNKS + 1))) ||
+      (scores_h && (rc = need(5, es * nc))) || (ptr_h && (rc = need(6, 8 * ((size_t)n + 1)))))
     return rc;
   void *U_d = st.p[0], *V_d = st.p[1], *sc_d = scores_h ? st.p[5] : nullptr;
   int32_t *ci_d = (int32_t*)st.p[2], *cj_d = (int32_t*)st.p[3];
-  amf_best_t* best_d = (amf_best_t*)st.p[4];
-  cudaStream_t s = nullptr;
+  amf_best_t* best_d = (amf_best_t*)st.p[4];          // [HOST_CHUNKS] per-chunk winners + result
+  // copy stream + compute stream: the candidate arrays cross PCIe in HOST_CHUNKS pieces and
+  // every piece is scored while the next one is still in flight
+  static thread_local cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  static thread_local cudaEvent_t ev[HOST_CHUNKS + 1] = {nullptr};
+  if (!s_copy) {
+    AMF_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    AMF_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    for (int k = 0; k <= HOST_CHUNKS; ++k)
+      AMF_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+  }
   if (ld != d) {
-    AMF_CUDA(cudaMemsetAsync(U_d, 0, (size_t)n * ld * es, s));
-    AMF_CUDA(cudaMemsetAsync(V_d, 0, (size_t)m * ld * es, s));
+    AMF_CUDA(cudaMemsetAsync(U_d, 0, (size_t)n * ld * es, s_copy));
+    AMF_CUDA(cudaMemsetAsync(V_d, 0, (size_t)m * ld * es, s_copy));
   }
-  AMF_CUDA(cudaMemcpy2DAsync(U_d, ld * es, U_h, d * es, d * es, n, cudaMemcpyHostToDevice, s));
-  AMF_CUDA(cudaMemcpy2DAsync(V_d, ld * es, V_h, d * es, d * es, m, cudaMemcpyHostToDevice, s));
-  if (ncand > 0) {
-    AMF_CUDA(cudaMemcpyAsync(ci_d, ci_h, 4 * ncand, cudaMemcpyHostToDevice, s));
-    AMF_CUDA(cudaMemcpyAsync(cj_d, cj_h, 4 * ncand, cudaMemcpyHostToDevice, s));
+  AMF_CUDA(cudaMemcpy2DAsync(U_d, ld * es, U_h, d * es, d * es, n, cudaMemcpyHostToDevice, s_copy));
+  AMF_CUDA(cudaMemcpy2DAsync(V_d, ld * es, V_h, d * es, d * es, m, cudaMemcpyHostToDevice, s_copy));
+  if (ncand > 0 && ptr_h) {
+    AMF_REQUIRE(ptr_h[0] == 0 && ptr_h[n] == ncand, "amf_score_pred_host_csr: row offsets must "
+                "run from 0 to ncand");
+    AMF_CUDA(cudaMemcpyAsync(st.p[6], ptr_h, 8 * ((size_t)n + 1), cudaMemcpyHostToDevice, s_copy));
   }
-  rc = amf_score_candidates(AMF_CRIT_PRED, dtype, ncand, ci_d, cj_d, d, ld, U_d, V_d, nullptr,
-                            0.0, sc_d, maximize, 0, best_d, s);
+  AMF_CUDA(cudaEventRecord(ev[HOST_CHUNKS], s_copy));
+  AMF_CUDA(cudaStreamWaitEvent(s_comp, ev[HOST_CHUNKS], 0));
+  if (ncand > 0 && ptr_h) {
+    expand_rows_kernel<<<num_sms() * 8, 256, 0, s_comp>>>((const int64_t*)st.p[6], n, ci_d);
+    AMF_LAUNCH_CHECK();
+  }
+  const int nchunks = ncand >= (int64_t)HOST_CHUNKS * (1 << 20) ? HOST_CHUNKS : 1;
+  for (int k = 0; k < nchunks; ++k) {
+    const int64_t lo = ncand * k / nchunks, hi = ncand * (k + 1) / nchunks;
+    if (hi > lo) {
+      if (!ptr_h)
+        AMF_CUDA(cudaMemcpyAsync(ci_d + lo, ci_h + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
+      AMF_CUDA(cudaMemcpyAsync(cj_d + lo, cj_h + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
+    }
+    AMF_CUDA(cudaEventRecord(ev[k], s_copy));
+    AMF_CUDA(cudaStreamWaitEvent(s_comp, ev[k], 0));
+    rc = amf_score_candidates(AMF_CRIT_PRED, dtype, hi - lo, ci_d + lo, cj_d + lo, d, ld, U_d, V_d,
+                              nullptr, 0.0, sc_d ? (char*)sc_d + es * lo : nullptr, maximize, lo,
+                              best_d + 1 + k, s_comp);
+    if (rc != AMF_OK) return rc;
+  }
+  rc = amf_best_reduce(best_d + 1, nchunks, maximize, best_d, s_comp);
   if (rc == AMF_OK) {
     if (scores_h && ncand > 0)
-      AMF_CUDA(cudaMemcpyAsync(scores_h, sc_d, es * ncand, cudaMemcpyDeviceToHost, s));
-    AMF_CUDA(cudaMemcpyAsync(best_h, best_d, sizeof(amf_best_t), cudaMemcpyDeviceToHost, s));
-    AMF_CUDA(cudaStreamSynchronize(s));
+      AMF_CUDA(cudaMemcpyAsync(scores_h, sc_d, es * ncand, cudaMemcpyDeviceToHost, s_comp));
+    AMF_CUDA(cudaMemcpyAsync(best_h, best_d, sizeof(amf_best_t), cudaMemcpyDeviceToHost, s_comp));
+    AMF_CUDA(cudaStreamSynchronize(s_comp));
   }
   return rc;
+}
+
+int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,
+                        int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
+                        void* scores_h, int maximize, amf_best_t* best_h) {
+  return score_pred_host(dtype, ncand, ci_h, nullptr, cj_h, n, m, d, U_h, V_h, scores_h, maximize,
+                         best_h);
+}
+
+int amf_score_pred_host_csr(int dtype, const int64_t* cand_ptr_h, const int32_t* cj_h, int32_t n,
+                            int32_t m, int d, const void* U_h, const void* V_h, void* scores_h,
+                            int maximize, amf_best_t* best_h) {
+  AMF_REQUIRE(cand_ptr_h && n > 0, "amf_score_pred_host_csr: NULL row offsets");
+  return score_pred_host(dtype, cand_ptr_h[n], nullptr, cand_ptr_h, cj_h, n, m, d, U_h, V_h,
+                         scores_h, maximize, best_h);
 }
 
 #pragma GCC visibility pop

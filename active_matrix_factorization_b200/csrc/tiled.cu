@@ -32,8 +32,8 @@ static int bits_for_u64(uint64_t x) {
 }
 
 // own[p] = row of entry p of the row-sorted list (warp per row)
-__global__ void expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
-                                   int32_t* __restrict__ own) {
+__global__ void tiled_expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
+                                         int32_t* __restrict__ own) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -147,7 +147,7 @@ static int build_tiled_side(amf_ratings* h, int side, int tile_rows, cudaStream_
   TILED_CUDA(cudaMalloc(&keys_out, 8 * (size_t)nnz));
   TILED_CUDA(cudaMalloc(&vals, 4 * (size_t)nnz));
   TILED_CUDA(cudaMalloc(&perm, 4 * (size_t)nnz));
-  expand_rows_kernel<<<grid, 256, 0, s>>>(h->ptr[side], own_rows, own);
+  tiled_expand_rows_kernel<<<grid, 256, 0, s>>>(h->ptr[side], own_rows, own);
   TILED_CUDA(cudaGetLastError());
   tiled_keys_kernel<<<grid, 256, 0, s>>>(own, h->idx[side], nnz, tile_rows, jbits, ibits, keys, vals);
   TILED_CUDA(cudaGetLastError());

@@ -411,20 +411,34 @@ def run_ours(a):
     sums_h = np.zeros(3)
     best_h = N.Best()
 
-    def e2e_step():
+    # the pool is sorted by user: the host call takes it as row offsets + item ids (CSR), which
+    # halves the PCIe bytes of the (i, j) pair form; both forms are timed
+    ptr_h = torch.zeros(n + 1, dtype=torch.int64).pin_memory()
+    ptr_h[1:].copy_(torch.cumsum(torch.bincount(ci.long(), minlength=n), 0))
+
+    def e2e_step(csr=True):
         t0 = time.perf_counter()
         N.check(lib.amf_pmf_loss_grad_host(rat.handle, D.code(name), d, C.c_void_p(U_h.data_ptr()),
                                            C.c_void_p(V_h.data_ptr()), C.byref(params),
                                            C.c_void_p(dU_h.data_ptr()), C.c_void_p(dV_h.data_ptr()),
                                            N.host_ptr(sums_h)))
         t1 = time.perf_counter()
-        N.check(lib.amf_score_pred_host(D.code(name), ncand, C.c_void_p(ci_h.data_ptr()),
-                                        C.c_void_p(cj_h.data_ptr()), n, m, d,
-                                        C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
-                                        None, 1, C.byref(best_h)))
+        if csr:
+            N.check(lib.amf_score_pred_host_csr(D.code(name), C.c_void_p(ptr_h.data_ptr()),
+                                                C.c_void_p(cj_h.data_ptr()), n, m, d,
+                                                C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
+                                                None, 1, C.byref(best_h)))
+        else:
+            N.check(lib.amf_score_pred_host(D.code(name), ncand, C.c_void_p(ci_h.data_ptr()),
+                                            C.c_void_p(cj_h.data_ptr()), n, m, d,
+                                            C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
+                                            None, 1, C.byref(best_h)))
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
 
+    e2e_step(csr=False)
+    sync()
+    e2e_pairs_s = float(np.mean([e2e_step(csr=False)[1] for _ in range(a.e2e_steps)]))
     e2e_step()
     sync()
     e2e = [e2e_step() for _ in range(a.e2e_steps)]
@@ -480,9 +494,11 @@ def run_ours(a):
                               "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms,
                               "traffic": traffic.get("tiled_side_kernel_x2" if tiled_grad else "side_pass_kernel_x2")},
         "e2e": {"value": ncand_all / e2e_score_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(ncand * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
+                "h2d_bytes_per_step": int(ncand * 4 + (n + 1) * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
                 "pmf_ratings_per_sec_iter": nnz_all / e2e_grad_s,
-                "note": "amf_pmf_loss_grad_host + amf_score_pred_host with pinned host buffers; rating list resident"},
+                "pairs_form_value": ncand / e2e_pairs_s if world == 1 else None,
+                "note": "amf_pmf_loss_grad_host + amf_score_pred_host_csr (pool as row offsets + item ids) with pinned host buffers; "
+                        "rating list resident; pairs_form_value = amf_score_pred_host with (i, j) arrays, 8 bytes per candidate"},
         "gpu_launches": a.steps * step.launches_per_step,
         "clocks": clocks,
         "selected": {"value": float(bv), "index": bi},

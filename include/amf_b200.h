@@ -192,6 +192,13 @@ int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int
                         int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
                         void* scores_h, int maximize, amf_best_t* best_h);
 
+/* Same, for a pool sorted by user and given as row offsets: the candidates of user i are
+ * cj_h[cand_ptr_h[i] .. cand_ptr_h[i+1]) (n+1 offsets, cand_ptr_h[0] = 0, cand_ptr_h[n] = ncand),
+ * candidate index = position in cj_h.  Half the host->device bytes of the (ci, cj) form. */
+int amf_score_pred_host_csr(int dtype, const int64_t* cand_ptr_h, const int32_t* cj_h, int32_t n,
+                            int32_t m, int d, const void* U_h, const void* V_h, void* scores_h,
+                            int maximize, amf_best_t* best_h);
+
 /* ------------------------------------------------------------------------------------------
  * Bayesian PMF (bayes_pmf.py:189-216 sample_feature inside the sweeps of :283-300;
  * :433-455 predict / pred_variance / :528-538 prob_ge_cutoff over a list of samples).

@@ -193,3 +193,28 @@ def test_best_reduce_matches_host_rule(S):
             assert i == hi
             if i >= 0:
                 assert v == hv
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 1e-5)])
+def test_host_csr_pool_matches_pairs(S, dtype, tol):
+    """amf_score_pred_host_csr: a pool given as row offsets scores like the (i, j) form; users
+    without candidates and an empty pool are fine"""
+    rng = np.random.RandomState(4)
+    n, m, d, nc = 300, 500, 10, 20_000
+    U, V = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    ii = np.sort(rng.randint(0, n // 2, nc) * 2)            # odd users have no candidates
+    jj = rng.randint(0, m, nc)
+    ptr = np.zeros(n + 1, np.int64)
+    np.add.at(ptr, ii + 1, 1)
+    ptr = np.cumsum(ptr)
+    ref = np.einsum("nd,nd->n", U[ii], V[jj])
+    for maximize in (True, False):
+        sc, (bv, bi) = S.score_pred_host_csr(U, V, ptr, jj, dtype, want_scores=True, maximize=maximize)
+        np.testing.assert_allclose(sc, ref, rtol=tol, atol=tol * np.abs(ref).max())
+        assert bi == int(np.argmax(sc) if maximize else np.argmin(sc)) and bv == sc[bi]
+    _, (bv, bi) = S.score_pred_host_csr(U, V, ptr, jj, dtype)
+    assert bi == int(np.argmax(sc if False else ref.astype(sc.dtype))) or abs(ref[bi] - ref.max()) <= tol * abs(ref.max())
+    _, (bv, bi) = S.score_pred_host_csr(U, V, np.zeros(n + 1, np.int64), jj[:0], dtype)
+    assert bi == -1
+    with pytest.raises(ValueError):
+        S.score_pred_host_csr(U, V, ptr[:-1], jj, dtype)

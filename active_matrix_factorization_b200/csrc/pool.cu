@@ -216,9 +216,7 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
             for (int t = 0; t < CPL; ++t)
               a[t] = ldg_v(reinterpret_cast<const unsigned char*>(up ^ (uint64_t)xo[t]), V());
           }
-          T acc = 0;
-#pragma unroll
-          for (int t = 0; t < CPL; ++t) acc = vdot_acc(a[t], b[t], acc);
+          const T acc = dot_slices<CPL>(a, b);
           p[s] = have ? acc : T(0);
         }
         // transpose-reduce over the four lanes: lane l ends with candidate l of the group

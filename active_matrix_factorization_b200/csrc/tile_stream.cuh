@@ -77,4 +77,24 @@ __device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const f
   return *reinterpret_cast<float2*>(&rd);
 }
 
+
+// dot product of the C 16-byte slices a lane holds of two rows (packed FFMA2 for fp32)
+template <int C>
+__device__ __forceinline__ float dot_slices(const float4 (&a)[C], const float4 (&b)[C]) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < C; ++t) {
+    acc = fma2(make_float2(a[t].x, a[t].y), make_float2(b[t].x, b[t].y), acc);
+    acc = fma2(make_float2(a[t].z, a[t].w), make_float2(b[t].z, b[t].w), acc);
+  }
+  return acc.x + acc.y;
+}
+template <int C>
+__device__ __forceinline__ double dot_slices(const double2 (&a)[C], const double2 (&b)[C]) {
+  double acc = 0;
+#pragma unroll
+  for (int t = 0; t < C; ++t) acc = fma(a[t].x, b[t].x, fma(a[t].y, b[t].y, acc));
+  return acc;
+}
+
 }  // namespace amf

@@ -184,24 +184,7 @@ done:
   return rc;
 }
 
-// ---- per-type arithmetic of one 4-lane dot product / accumulator update ----------------------
-template <int C>
-__device__ __forceinline__ float dot_slices(const float4 (&a)[C], const float4 (&b)[C]) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int t = 0; t < C; ++t) {
-    acc = fma2(make_float2(a[t].x, a[t].y), make_float2(b[t].x, b[t].y), acc);
-    acc = fma2(make_float2(a[t].z, a[t].w), make_float2(b[t].z, b[t].w), acc);
-  }
-  return acc.x + acc.y;
-}
-template <int C>
-__device__ __forceinline__ double dot_slices(const double2 (&a)[C], const double2 (&b)[C]) {
-  double acc = 0;
-#pragma unroll
-  for (int t = 0; t < C; ++t) acc = fma(a[t].x, b[t].x, fma(a[t].y, b[t].y, acc));
-  return acc;
-}
+// ---- accumulator update of one 4-lane group ---------------------------------------------------
 template <int C>
 __device__ __forceinline__ void axpy_slices(float4 (&acc)[C], float w, const float4 (&b)[C]) {
   const float2 w2 = make_float2(w, w);

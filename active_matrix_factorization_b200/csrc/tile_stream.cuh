@@ -59,6 +59,63 @@ __device__ __forceinline__ float4 ldg_v(const unsigned char* p, float4) {
 __device__ __forceinline__ double2 ldg_v(const unsigned char* p, double2) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
+// read-only 32-byte load of two adjacent slices (one LDG.256 on sm_100a)
+__device__ __forceinline__ void ldg_v2(const unsigned char* p, float4& lo, float4& hi) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y),
+                 "=f"(hi.z), "=f"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg_v2(const unsigned char* p, double2& lo, double2& hi) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y)
+               : "l"(p));
+}
+__device__ __forceinline__ float4 vsel(bool c, const float4& a, const float4& b) {
+  return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
+__device__ __forceinline__ double2 vsel(bool c, const double2& a, const double2& b) {
+  return make_double2(c ? a.x : b.x, c ? a.y : b.y);
+}
+
+// Which 16-byte slices of a row a lane owns, for rows of NVEC slices shared by four lanes
+// (CPL = NVEC / 4 per lane), and in which order it visits them.  The two lane groups that share
+// a shared-memory wavefront (group parity gq) visit their slices in a different order, so the
+// eight lanes of a wavefront always touch eight different 16-byte bank groups.
+//   ADJ (CPL == 2 only): lane l owns the adjacent slices 2l, 2l+1 (one 256-bit global load
+//             fetches both, at the price of 8 selects) and visits 2l+gq first;
+//   else    : lane l owns l, l+4, l+8, ... and starts at slice l + 4*(gq mod CPL).
+// off0 = byte offset of the first slice visited, xo[t] = XOR that turns it into the t-th.
+template <int CPL, bool ADJ>
+__device__ __forceinline__ void slice_order(int l, int gq, bool have, uint32_t& off0,
+                                            uint32_t (&xo)[CPL]) {
+  static_assert(!ADJ || CPL == 2, "adjacent ownership is for two slices per lane");
+  const int ll = have ? l : 0;
+  if constexpr (ADJ) {
+    off0 = (uint32_t)(2 * ll + gq) * 16u;
+    xo[0] = 0; xo[1] = 16u;
+  } else {
+    off0 = (uint32_t)(ll + 4 * (gq % CPL)) * 16u;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) xo[t] = off0 ^ ((uint32_t)(ll + 4 * ((t + gq) % CPL)) * 16u);
+  }
+}
+// the lane's slices of the row at `row` (global, row-aligned), in visiting order
+template <typename V, int CPL, bool ADJ>
+__device__ __forceinline__ void load_row_slices(uint64_t row, int l, int gq, uint32_t off0,
+                                                const uint32_t (&xo)[CPL], V (&a)[CPL]) {
+  if constexpr (ADJ) {
+    V n0, n1;
+    ldg_v2(reinterpret_cast<const unsigned char*>(row + 32u * (uint32_t)l), n0, n1);
+    a[0] = vsel(gq != 0, n1, n0);
+    a[1] = vsel(gq != 0, n0, n1);
+  } else {
+#pragma unroll
+    for (int t = 0; t < CPL; ++t)
+      a[t] = ldg_v(reinterpret_cast<const unsigned char*>((row + off0) ^ (uint64_t)xo[t]), V());
+  }
+}
+
 __device__ __forceinline__ float vdot_acc(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }

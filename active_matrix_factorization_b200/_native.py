@@ -75,6 +75,8 @@ PROTOTYPES = {
     "amf_normal_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
                            _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],
     "amf_ratings_set_layout": [_P, _INT],
+    "amf_ratings_append": [_P, _I64, _P, _P, _P, _P],
+    "amf_ratings_compact": [_P, _P],
     "amf_best_reduce": [_P, _INT, _INT, _P, _P],
     "amf_pool_create": [C.POINTER(_P), _I64, _P, _P, _I32, _I32, _INT, _P],
     "amf_pool_destroy": [_P],

@@ -169,6 +169,16 @@ struct amf_ratings {
   amf_tiled_side tiled[2];
   int tiled_row_bytes;    // padded factor-row size the tiles were cut for (0 = not built)
   int tiled_mode;         // AMF_LAYOUT_AUTO / _ROWS / _TILED
+  // ratings appended since the sorted lists were built (amf_ratings_append): plain COO, folded
+  // into the sorted lists by ratings_compact() once the tail is large or a consumer needs them
+  int32_t *tail_i, *tail_j;
+  void* tail_r;
+  int64_t tail_n, tail_cap;
 };
+
+namespace amf {
+// merges the appended tail into the sorted lists (no-op if there is none)
+int ratings_compact(amf_ratings* h, cudaStream_t s);
+}  // namespace amf
 
 #define AMF_SUB 32

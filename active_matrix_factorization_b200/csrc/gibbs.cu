@@ -290,6 +290,10 @@ int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d
   AMF_REQUIRE(d >= 1 && d <= GIBBS_MAXD, "amf_gibbs_half_sweep: latent_d=%d unsupported (max %d)", d,
               GIBBS_MAXD);
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = ratings_compact(const_cast<amf_ratings*>(h), s);
+    if (rc != AMF_OK) return rc;
+  }
   if (dtype == AMF_F32)
     return gibbs_launch<float>(h, side, d, (const float*)other_d, (const float*)alpha_d,
                                (const float*)mu_d, beta, mean_offset, (const float*)z_d,

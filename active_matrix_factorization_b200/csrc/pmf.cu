@@ -341,6 +341,21 @@ static int launch_side(const amf_ratings* h, int side, const T* Self, const T* O
 }
 
 template <typename T>
+static int grad_coo(int64_t nnz, const int32_t* i_d, const int32_t* j_d, const T* r_d, int d,
+                    int ld, const T* U, const T* V, const amf_pmf_params_t* p, T* dU, T* dV,
+                    double* sums, cudaStream_t s, bool reset_sums = true);
+
+// the data terms of the ratings appended since the sorted lists were built (amf_ratings_append):
+// COO kernel with atomics into both sides, on top of what the sorted passes wrote
+template <typename T>
+static int tail_terms(const amf_ratings* h, int d, int ld, const T* U, const T* V,
+                      const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s) {
+  if (h->tail_n == 0) return AMF_OK;
+  return grad_coo<T>(h->tail_n, h->tail_i, h->tail_j, (const T*)h->tail_r, d, ld, U, V, p, dU, dV,
+                     sums, s, false);
+}
+
+template <typename T>
 static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V,
                      const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s) {
   constexpr int N = Vec<T>::N;
@@ -353,30 +368,32 @@ static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V
   AMF_LAUNCH_CHECK();
   prior_kernel<T><<<gv, 256, 0, s>>>(V, cv, (T)(-1.0 / p->sigma_v_sq), dV, sums + 2);
   AMF_LAUNCH_CHECK();
-  if (h->nnz == 0) return AMF_OK;
+  if (h->nnz == 0) return tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
   const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
   int rc;
   bool tiled = false;
   rc = tiled_prepare(const_cast<amf_ratings*>(h), (size_t)ld * sizeof(T), U, V, dU, dV, &tiled, s);
   if (rc != AMF_OK) return rc;
-  if (tiled) return tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s);
-  if (dU) {
+  if (tiled) {
+    rc = tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s);
+  } else if (dU) {
     rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
     if (rc != AMF_OK) return rc;
     rc = launch_side<T, true>(h, 1, V, U, ld, inv_sigma, mo, dV, nullptr, s);
   } else {
     rc = launch_side<T, false>(h, 0, U, V, ld, inv_sigma, mo, nullptr, sums, s);
   }
-  return rc;
+  if (rc != AMF_OK) return rc;
+  return tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
 }
 
 template <typename T>
 static int grad_coo(int64_t nnz, const int32_t* i_d, const int32_t* j_d, const T* r_d, int d,
                     int ld, const T* U, const T* V, const amf_pmf_params_t* p, T* dU, T* dV,
-                    double* sums, cudaStream_t s) {
+                    double* sums, cudaStream_t s, bool reset_sums) {
   constexpr int N = Vec<T>::N;
   AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
-  if (sums) AMF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double), s));
+  if (sums && reset_sums) AMF_CUDA(cudaMemsetAsync(sums, 0, sizeof(double), s));
   if (nnz == 0) return AMF_OK;
   const int nvec = ld / N;
   int lpr = pow2_ceil(nvec), vpl = 1;

@@ -133,6 +133,63 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
                       cudaStream_t s);
 void tiled_free(amf_ratings* h);
 
+// row[p] = row of entry p of a row-sorted list (warp per row)
+__global__ void ratings_expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
+                                           int32_t* __restrict__ row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) row[p] = (int32_t)r;
+}
+
+static void free_sides(amf_ratings* h) {
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(h->ptr[s]); cudaFree(h->idx[s]); cudaFree(h->val[s]); cudaFree(h->sub_row[s]);
+    h->ptr[s] = nullptr; h->idx[s] = nullptr; h->val[s] = nullptr; h->sub_row[s] = nullptr;
+  }
+}
+
+// Sorted lists + tail -> sorted lists of everything.  The user-major list keeps the order of
+// arrival inside a row and the tail is placed after it, so the stable sorts give the lists a
+// fresh amf_ratings_create of the whole rating list (in order of arrival) would give.
+int ratings_compact(amf_ratings* h, cudaStream_t s) {
+  if (h->tail_n == 0) return AMF_OK;
+  const int64_t n0 = h->nnz, n1 = h->tail_n, total = n0 + n1;
+  AMF_REQUIRE(total < (1ll << 32), "rating list would exceed 2^32 entries");
+  const size_t es = h->dtype == AMF_F32 ? 4 : 8;
+  int32_t *i_d = nullptr, *j_d = nullptr;
+  void* r_d = nullptr;
+  AMF_CUDA(cudaMalloc(&i_d, 4 * (size_t)total));
+  AMF_CUDA(cudaMalloc(&j_d, 4 * (size_t)total));
+  AMF_CUDA(cudaMalloc(&r_d, es * (size_t)total));
+  if (n0 > 0) {
+    ratings_expand_rows_kernel<<<num_sms() * 8, 256, 0, s>>>(h->ptr[0], h->n_users, i_d);
+    AMF_LAUNCH_CHECK();
+    AMF_CUDA(cudaMemcpyAsync(j_d, h->idx[0], 4 * (size_t)n0, cudaMemcpyDeviceToDevice, s));
+    AMF_CUDA(cudaMemcpyAsync(r_d, h->val[0], es * (size_t)n0, cudaMemcpyDeviceToDevice, s));
+  }
+  AMF_CUDA(cudaMemcpyAsync(i_d + n0, h->tail_i, 4 * (size_t)n1, cudaMemcpyDeviceToDevice, s));
+  AMF_CUDA(cudaMemcpyAsync(j_d + n0, h->tail_j, 4 * (size_t)n1, cudaMemcpyDeviceToDevice, s));
+  AMF_CUDA(cudaMemcpyAsync((char*)r_d + es * n0, h->tail_r, es * (size_t)n1, cudaMemcpyDeviceToDevice, s));
+  AMF_CUDA(cudaStreamSynchronize(s));
+  free_sides(h);
+  tiled_free(h);
+  h->nnz = total;
+  h->n_sub = (total + AMF_SUB - 1) / AMF_SUB;
+  h->tail_n = 0;
+  int rc;
+  if (h->dtype == AMF_F32) {
+    rc = build_side<float>(h, 0, i_d, j_d, (const float*)r_d, s);
+    if (rc == AMF_OK) rc = build_side<float>(h, 1, j_d, i_d, (const float*)r_d, s);
+  } else {
+    rc = build_side<double>(h, 0, i_d, j_d, (const double*)r_d, s);
+    if (rc == AMF_OK) rc = build_side<double>(h, 1, j_d, i_d, (const double*)r_d, s);
+  }
+  cudaFree(i_d); cudaFree(j_d); cudaFree(r_d);
+  return rc;
+}
+
 }  // namespace amf
 
 using namespace amf;
@@ -207,11 +264,52 @@ int amf_ratings_create_host(amf_ratings_t** out, int32_t n_users, int32_t n_item
   return rc;
 }
 
+int amf_ratings_append(amf_ratings_t* h, int64_t n_new, const int32_t* i_d, const int32_t* j_d,
+                       const void* r_d, void* stream) {
+  AMF_REQUIRE(h && n_new >= 0 && (n_new == 0 || (i_d && j_d && r_d)), "amf_ratings_append: bad arguments");
+  if (n_new == 0) return AMF_OK;
+  AMF_REQUIRE(h->nnz + h->tail_n + n_new < (1ll << 32), "amf_ratings_append: list would exceed 2^32 entries");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t es = h->dtype == AMF_F32 ? 4 : 8;
+  if (h->tail_n + n_new > h->tail_cap) {
+    int64_t cap = h->tail_cap > 0 ? h->tail_cap : 4096;
+    while (cap < h->tail_n + n_new) cap *= 2;
+    int32_t *ni = nullptr, *nj = nullptr;
+    void* nr = nullptr;
+    AMF_CUDA(cudaMalloc(&ni, 4 * (size_t)cap));
+    AMF_CUDA(cudaMalloc(&nj, 4 * (size_t)cap));
+    AMF_CUDA(cudaMalloc(&nr, es * (size_t)cap));
+    if (h->tail_n > 0) {
+      AMF_CUDA(cudaMemcpyAsync(ni, h->tail_i, 4 * (size_t)h->tail_n, cudaMemcpyDeviceToDevice, s));
+      AMF_CUDA(cudaMemcpyAsync(nj, h->tail_j, 4 * (size_t)h->tail_n, cudaMemcpyDeviceToDevice, s));
+      AMF_CUDA(cudaMemcpyAsync(nr, h->tail_r, es * (size_t)h->tail_n, cudaMemcpyDeviceToDevice, s));
+      AMF_CUDA(cudaStreamSynchronize(s));
+    }
+    cudaFree(h->tail_i); cudaFree(h->tail_j); cudaFree(h->tail_r);
+    h->tail_i = ni; h->tail_j = nj; h->tail_r = nr; h->tail_cap = cap;
+  }
+  AMF_CUDA(cudaMemcpyAsync(h->tail_i + h->tail_n, i_d, 4 * (size_t)n_new, cudaMemcpyDeviceToDevice, s));
+  AMF_CUDA(cudaMemcpyAsync(h->tail_j + h->tail_n, j_d, 4 * (size_t)n_new, cudaMemcpyDeviceToDevice, s));
+  AMF_CUDA(cudaMemcpyAsync((char*)h->tail_r + es * h->tail_n, r_d, es * (size_t)n_new,
+                           cudaMemcpyDeviceToDevice, s));
+  h->tail_n += n_new;
+  // keep the unsorted tail a small fraction of the list: it is walked with atomics into both sides
+  const int64_t limit = h->nnz / 32 > 65536 ? h->nnz / 32 : 65536;
+  if (h->tail_n > limit) return amf::ratings_compact(h, s);
+  return AMF_OK;
+}
+
+int amf_ratings_compact(amf_ratings_t* h, void* stream) {
+  AMF_REQUIRE(h, "amf_ratings_compact: NULL handle");
+  return amf::ratings_compact(h, (cudaStream_t)stream);
+}
+
 int amf_ratings_destroy(amf_ratings_t* h) {
   if (!h) return AMF_OK;
   for (int s = 0; s < 2; ++s) {
     cudaFree(h->ptr[s]); cudaFree(h->idx[s]); cudaFree(h->val[s]); cudaFree(h->sub_row[s]);
   }
+  cudaFree(h->tail_i); cudaFree(h->tail_j); cudaFree(h->tail_r);
   for (int k = 0; k < 8; ++k) cudaFree(h->stage[k]);
   cudaFree(h->sums_d);
   amf::tiled_free(h);
@@ -219,11 +317,13 @@ int amf_ratings_destroy(amf_ratings_t* h) {
   return AMF_OK;
 }
 
-int64_t amf_ratings_nnz(const amf_ratings_t* h) { return h ? h->nnz : -1; }
+int64_t amf_ratings_nnz(const amf_ratings_t* h) { return h ? h->nnz + h->tail_n : -1; }
 
 int amf_ratings_layout(const amf_ratings_t* h, int side, const int64_t** ptr_d,
                        const int32_t** idx_d, const void** val_d) {
   AMF_REQUIRE(h && (side == 0 || side == 1), "amf_ratings_layout: bad arguments");
+  int rc = amf::ratings_compact(const_cast<amf_ratings*>(h), nullptr);
+  if (rc != AMF_OK) return rc;
   if (ptr_d) *ptr_d = h->ptr[side];
   if (idx_d) *idx_d = h->idx[side];
   if (val_d) *val_d = h->val[side];
@@ -233,6 +333,10 @@ int amf_ratings_layout(const amf_ratings_t* h, int side, const int64_t** ptr_d,
 int amf_ratings_mean(const amf_ratings_t* h, double* mean_out, void* stream) {
   AMF_REQUIRE(h && mean_out, "amf_ratings_mean: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = amf::ratings_compact(const_cast<amf_ratings*>(h), s);
+    if (rc != AMF_OK) return rc;
+  }
   AMF_CUDA(cudaMemsetAsync(h->sums_d + 4, 0, sizeof(double), s));
   if (h->nnz > 0) {
     if (h->dtype == AMF_F32)

@@ -102,6 +102,25 @@ class Ratings:
         if layout != "auto":
             self.set_layout(layout)
 
+    def append(self, i, j, r):
+        """Add ratings to the device-resident list without re-sorting it (amf_ratings_append);
+        i, j, r: numpy arrays or CUDA tensors."""
+        if isinstance(i, torch.Tensor):
+            ti, tj, tr = i.to(torch.int32).contiguous(), j.to(torch.int32).contiguous(), \
+                r.to(torch_dtype(self.name)).contiguous()
+        else:
+            ti, tj = to_device(np.atleast_1d(i), np.int32), to_device(np.atleast_1d(j), np.int32)
+            tr = to_device(np.atleast_1d(r), np_dtype(self.name))
+        torch.cuda.current_stream().synchronize()
+        N.check(N.load().amf_ratings_append(self.handle, int(ti.numel()), ptr(ti), ptr(tj), ptr(tr),
+                                            stream_ptr()))
+        torch.cuda.current_stream().synchronize()      # the inputs may be freed by the caller
+        self.nnz += int(ti.numel())
+
+    def compact(self):
+        """Fold appended ratings into the sorted lists now (amf_ratings_compact)."""
+        N.check(N.load().amf_ratings_compact(self.handle, stream_ptr()))
+
     def set_layout(self, mode):
         """'auto' | 'rows' | 'tiled': which copy of the list the fused loss+gradient runs on
         (amf_ratings_set_layout)."""

@@ -252,7 +252,7 @@ class ProbabilisticMatrixFactorization(object):
         self.add_ratings([int(i), int(j), float(rating)])
 
     def add_ratings(self, extra):
-        cols = self.ratings.shape[1]
+        cols = 3 if self._ratings is None else self._ratings.shape[1]
         extra = np.array(extra, ndmin=2)
         if len(extra.shape) != 2 or extra.shape[1] != cols:
             raise TypeError("bad shape for extra")
@@ -270,8 +270,35 @@ class ProbabilisticMatrixFactorization(object):
         self.rated.update(new_items)
         self.unrated.difference_update(new_items)
 
-        self.ratings = np.append(self.ratings, extra, 0)
-        self.mean_rating = float(np.mean(self.ratings[:, 2]))
+        # active-loop residency: a rating list that already lives on the device
+        # takes the new ratings as an appended tail instead of being re-uploaded and re-sorted
+        rat = self.__dict__.get('_dev', {}).get('rat')
+        key = self._dev.get('rat_key') if rat is not None else None
+        coo = self.__dict__.get('_coo')
+        if coo is not None and self._ratings is None:
+            # from_coo() model: no host (nnz, 3) array is kept; the device list is the list
+            import torch
+            ti = torch.as_tensor(extra[:, 0].astype(np.int32)).to(coo[0].device)
+            tj = torch.as_tensor(extra[:, 1].astype(np.int32)).to(coo[0].device)
+            tr = torch.as_tensor(extra[:, 2]).to(coo[2].dtype).to(coo[0].device)
+            total = float(self.mean_rating) * int(coo[0].numel()) + float(extra[:, 2].sum())
+            self._coo = (torch.cat((coo[0], ti)), torch.cat((coo[1], tj)), torch.cat((coo[2], tr)))
+            if rat is not None and key is not None and key[0] == self.dtype_name:
+                rat.append(ti, tj, tr)
+                self._dev['rat_key'] = (key[0], 'coo', rat.nnz)
+            else:
+                self._drop_device('rat')
+            self.mean_rating = total / int(self._coo[0].numel())
+            return
+        old = self._ratings
+        new_ratings = np.append(old, extra, 0)
+        if rat is not None and key == (self.dtype_name, id(old), old.shape[0]):
+            rat.append(extra[:, 0].astype(np.int32), extra[:, 1].astype(np.int32), extra[:, 2])
+            self._ratings = new_ratings            # not through the setter: the handle stays
+            self._dev['rat_key'] = (self.dtype_name, id(new_ratings), new_ratings.shape[0])
+        else:
+            self.ratings = new_ratings
+        self.mean_rating = float(np.mean(self._ratings[:, 2]))
 
     # ---- numerics ------------------------------------------------------------------------
     def prediction_for(self, i, j, users=None, items=None):

@@ -65,6 +65,17 @@ int64_t amf_ratings_nnz(const amf_ratings_t* h);
 int amf_ratings_layout(const amf_ratings_t* h, int side, const int64_t** ptr_d,
                        const int32_t** idx_d, const void** val_d);
 /* sum and count of ratings -> mean_rating (pmf_cy.pyx:63); synchronises. */
+/* Appends ratings (device arrays, same value type as the list) without re-sorting: they are kept
+ * as an unsorted tail that amf_pmf_loss_grad adds on top of the sorted passes, and are merged
+ * into the sorted lists (as if the whole list had been created in order of arrival) when the
+ * tail exceeds max(65536, nnz/32) entries, by amf_ratings_compact, or by any other consumer of
+ * the sorted lists (amf_ratings_layout, amf_ratings_mean, amf_gibbs_half_sweep).  This is
+ * add_rating / add_ratings (pmf_cy.pyx:128-156) for a device-resident list: an active-learning
+ * step costs O(new ratings), not a re-upload and two sorts of everything. */
+int amf_ratings_append(amf_ratings_t* h, int64_t n_new, const int32_t* i_d, const int32_t* j_d,
+                       const void* r_d, void* stream);
+int amf_ratings_compact(amf_ratings_t* h, void* stream);
+
 /* Which copy of the list amf_pmf_loss_grad runs on.  AUTO: the tiled copy (item / user tiles of
  * the factor matrices resident in shared memory, built on first use, +8 or +12 bytes per rating
  * and side) when nnz >= 2^20 and the padded factor row is 64, 128 or 256 bytes, else the

@@ -74,6 +74,37 @@ __device__ void tri_inverse_lower(const double* L, double* Linv, int d, int lda)
   __syncthreads();
 }
 
+// Given Lambda (A, d x d in shared memory) and rhs: cov = Lambda^-1 via Cholesky
+// (Lambda = R R', cov = R^-T R^-1), mean = cov rhs, L = chol(cov), out = L z + mean
+// (bayes_pmf.py:205-216: the reference inverts and factors the covariance, not Lambda).
+template <typename T>
+__device__ bool solve_and_sample(double* A, double* Bm, double* rhs, double* mean, int d, int lda,
+                                 int* flag, const T* __restrict__ z, T* __restrict__ out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  bool ok = chol_lower(A, d, lda, flag);
+  tri_inverse_lower(A, Bm, d, lda);            // Bm = R^-1
+  for (int t = tid; t < d * d; t += nt) {
+    const int k = t / d, l = t % d;
+    double s = 0;
+    for (int q = max(k, l); q < d; ++q) s += Bm[q * lda + k] * Bm[q * lda + l];
+    A[k * lda + l] = s;                        // cov
+  }
+  __syncthreads();
+  if (tid < d) {
+    double s = 0;
+    for (int l = 0; l < d; ++l) s += A[tid * lda + l] * rhs[l];
+    mean[tid] = s;
+  }
+  __syncthreads();
+  ok = chol_lower(A, d, lda, flag) && ok;      // A = lower chol of cov
+  if (tid < d) {
+    double s = mean[tid];
+    for (int l = 0; l <= tid; ++l) s += A[tid * lda + l] * (double)z[l];
+    out[tid] = (T)s;
+  }
+  return ok;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GIBBS_THREADS)
 gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -168,28 +199,133 @@ gibbs_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
       rhs[tid] = s;
     }
     __syncthreads();
-    // ---- cov = Lambda^-1 via Cholesky: Lambda = R R', cov = R^-T R^-1 ---------------------
-    bool ok = chol_lower(A, d, lda, &flag);
-    tri_inverse_lower(A, Bm, d, lda);            // Bm = R^-1
-    for (int t = tid; t < d * d; t += GIBBS_THREADS) {
-      const int k = t / d, l = t % d;
-      double s = 0;
-      for (int q = max(k, l); q < d; ++q) s += Bm[q * lda + k] * Bm[q * lda + l];
-      A[k * lda + l] = s;                        // cov
+    const bool ok = solve_and_sample<T>(A, Bm, rhs, mean, d, lda, &flag, z + (int64_t)row * d,
+                                        out + (int64_t)row * d);
+    if (!ok && tid == 0) atomicExch(fail, 1);
+    __syncthreads();
+  }
+}
+
+// ---- fp32, d = 32 or 64: the Gram matrix F'F on the tensor cores ----------------------------
+// F'F over the rated rows is a dense (d x n_i) x (n_i x d) contraction; with d >= 32 it fills
+// whole m16n8k8 TF32 MMA tiles.  fp32 accuracy is kept with the 3xTF32 split
+// (x = hi + lo; hi*hi + hi*lo + lo*hi, fp32 accumulate).  The four warps of the CTA take the
+// 8-rating k-steps of a staged tile in turn and keep the upper-triangle tiles of the Gram
+// matrix in registers for the whole row; partial sums meet in shared memory once per row.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int GIBBS_TC_TILE = 64;   // rated rows staged per tile (8 k-steps)
+
+template <int D>
+__global__ void __launch_bounds__(GIBBS_THREADS)
+gibbs_rows_tc_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                     const float* __restrict__ val, int row_begin, int rows,
+                     const float* __restrict__ other, const float* __restrict__ alpha,
+                     const float* __restrict__ mu, double beta, double mean_offset,
+                     const float* __restrict__ z, float* __restrict__ out, int* __restrict__ fail) {
+  constexpr int d = D, lda = D + 1;
+  constexpr int LDT = D + 8;               // == 8 (mod 32): the fragment loads hit 32 banks
+  constexpr int MT = D / 16, NT8 = D / 8;  // 16-row and 8-column tiles per side
+  constexpr int NTILES = MT * (MT + 1);    // tiles (M, N >= 2M) covering the upper triangle
+  constexpr int NW = GIBBS_THREADS / 32;
+  extern __shared__ double smem[];
+  double* A = smem;                        // d x lda
+  double* Bm = A + d * lda;                // d x lda
+  double* rhs = Bm + d * lda;              // d
+  double* mean = rhs + d;                  // d
+  float* tile_r = reinterpret_cast<float*>(mean + d);   // GIBBS_TC_TILE
+  float* tile = tile_r + GIBBS_TC_TILE;                   // GIBBS_TC_TILE x LDT (16-byte aligned)
+  float* part = tile;        // NW x NTILES x 128 partial Gram tiles, after the last staged tile
+  __shared__ int flag;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+
+  for (int row = row_begin + blockIdx.x; row < rows; row += gridDim.x) {
+    const int64_t p0 = ptr[row], p1 = ptr[row + 1];
+    float c[NTILES][4];
+#pragma unroll
+    for (int t = 0; t < NTILES; ++t) c[t][0] = c[t][1] = c[t][2] = c[t][3] = 0.f;
+    float racc = 0.f;
+    for (int64_t base = p0; base < p1; base += GIBBS_TC_TILE) {
+      const int cnt = (int)min((int64_t)GIBBS_TC_TILE, p1 - base);
+      const int cnt8 = (cnt + 7) & ~7;     // rows staged: whole k-steps, zero-filled past cnt
+      for (int t = tid; t < cnt8 * (D / 4); t += GIBBS_THREADS) {
+        const int e = t / (D / 4), q = t - e * (D / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < cnt) v = __ldg(reinterpret_cast<const float4*>(other + (int64_t)idx[base + e] * D) + q);
+        *reinterpret_cast<float4*>(tile + e * LDT + 4 * q) = v;
+      }
+      for (int t = tid; t < cnt; t += GIBBS_THREADS)
+        tile_r[t] = (float)((double)val[base + t] - mean_offset);
+      __syncthreads();
+      for (int e0 = w * 8; e0 < cnt8; e0 += NW * 8) {
+        uint32_t xh[NT8], xl[NT8], yh[NT8], yl[NT8];
+#pragma unroll
+        for (int j = 0; j < NT8; ++j) {
+          const float x = tile[(e0 + tig) * LDT + 8 * j + g];
+          const float y = tile[(e0 + tig + 4) * LDT + 8 * j + g];
+          xh[j] = to_tf32(x); xl[j] = to_tf32(x - __uint_as_float(xh[j]));
+          yh[j] = to_tf32(y); yl[j] = to_tf32(y - __uint_as_float(yh[j]));
+        }
+        int t = 0;
+#pragma unroll
+        for (int M = 0; M < MT; ++M) {
+          const uint32_t ah[4] = {xh[2 * M], xh[2 * M + 1], yh[2 * M], yh[2 * M + 1]};
+          const uint32_t al[4] = {xl[2 * M], xl[2 * M + 1], yl[2 * M], yl[2 * M + 1]};
+#pragma unroll
+          for (int N = 2 * M; N < NT8; ++N, ++t) {
+            mma_tf32(c[t], al, xh[N], yh[N]);
+            mma_tf32(c[t], ah, xl[N], yl[N]);
+            mma_tf32(c[t], ah, xh[N], yh[N]);
+          }
+        }
+      }
+      if (tid < d) {
+        float s = racc;
+        for (int e = 0; e < cnt; ++e) s = fmaf(tile[e * LDT + tid], tile_r[e], s);
+        racc = s;
+      }
+      __syncthreads();
+    }
+    // ---- partial Gram tiles of the four warps -> Lambda = alpha + beta F'F ------------------
+#pragma unroll
+    for (int t = 0; t < NTILES; ++t)
+      *reinterpret_cast<float4*>(part + ((w * NTILES + t) * 32 + lane) * 4) =
+          make_float4(c[t][0], c[t][1], c[t][2], c[t][3]);
+    __syncthreads();
+    for (int e = tid; e < d * d; e += GIBBS_THREADS) {
+      const int k = e / d, l = e - k * d;
+      if (k > l) continue;
+      const int M = k >> 4, N = l >> 3;                     // N >= 2M because l >= k
+      const int t = M * NT8 - M * (M - 1) + (N - 2 * M);    // tiles before row M: sum (NT8 - 2m)
+      const int rr = k & 15, cc = l & 7;
+      const int src = ((rr & 7) * 4 + (cc >> 1)) * 4 + 2 * (rr >> 3) + (cc & 1);
+      float gsum = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) gsum += part[(ww * NTILES + t) * 128 + src];
+      A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)gsum;
+      if (k != l) A[l * lda + k] = (double)alpha[l * d + k] + beta * (double)gsum;
+    }
+    if (tid < d) {
+      double s = beta * (double)racc;
+      for (int l = 0; l < d; ++l) s += (double)alpha[tid * d + l] * (double)mu[l];
+      rhs[tid] = s;
     }
     __syncthreads();
-    if (tid < d) {
-      double s = 0;
-      for (int l = 0; l < d; ++l) s += A[tid * lda + l] * rhs[l];
-      mean[tid] = s;
-    }
-    __syncthreads();
-    ok = chol_lower(A, d, lda, &flag) && ok;     // A = lower chol of cov
-    if (tid < d) {
-      double s = mean[tid];
-      for (int l = 0; l <= tid; ++l) s += A[tid * lda + l] * (double)z[(int64_t)row * d + l];
-      out[(int64_t)row * d + tid] = (T)s;
-    }
+    const bool ok = solve_and_sample<float>(A, Bm, rhs, mean, d, lda, &flag, z + (int64_t)row * d,
+                                            out + (int64_t)row * d);
     if (!ok && tid == 0) atomicExch(fail, 1);
     __syncthreads();
   }
@@ -245,14 +381,37 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
   if (row_begin < 0) row_begin = 0;
   if (row_begin >= row_end) return AMF_OK;
   const int rows = row_end;
-  const size_t smem = sizeof(double) * (2 * d * (d + 1) + 2 * d + GIBBS_TILE) +
-                      sizeof(T) * GIBBS_TILE * (((d + 1) & ~1) + 2);
-  AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);
   AMF_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
   const int span = row_end - row_begin;
   const int grid = span < num_sms() * 8 ? span : num_sms() * 8;
+  if constexpr (sizeof(T) == 4) {
+    if (d == 32 || d == 64) {            // dense enough for whole MMA tiles: tensor-core Gram
+      const int mt = d / 16, ntiles = mt * (mt + 1);
+      const size_t stage = (size_t)GIBBS_TC_TILE * (d + 8), parts = (size_t)(GIBBS_THREADS / 32) * ntiles * 128;
+      const size_t smem_tc = sizeof(double) * (2 * d * (d + 1) + 2 * d) +
+                             sizeof(float) * (GIBBS_TC_TILE + (stage > parts ? stage : parts));
+      if (d == 32) {
+        AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_tc_kernel<32>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        gibbs_rows_tc_kernel<32><<<grid, GIBBS_THREADS, smem_tc, s>>>(
+            h->ptr[side], h->idx[side], (const float*)h->val[side], row_begin, rows, other, alpha,
+            mu, beta, mean_offset, z, out, fail);
+      } else {
+        AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_tc_kernel<64>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        gibbs_rows_tc_kernel<64><<<grid, GIBBS_THREADS, smem_tc, s>>>(
+            h->ptr[side], h->idx[side], (const float*)h->val[side], row_begin, rows, other, alpha,
+            mu, beta, mean_offset, z, out, fail);
+      }
+      AMF_LAUNCH_CHECK();
+      return AMF_OK;
+    }
+  }
+  const size_t smem = sizeof(double) * (2 * d * (d + 1) + 2 * d + GIBBS_TILE) +
+                      sizeof(T) * GIBBS_TILE * (((d + 1) & ~1) + 2);
+  AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
   gibbs_rows_kernel<T><<<grid, GIBBS_THREADS, smem, s>>>(h->ptr[side], h->idx[side],
                                                          (const T*)h->val[side], row_begin, rows,
                                                          d, other, alpha, mu, beta, mean_offset,

@@ -129,16 +129,28 @@ def prior_once_params(params, rank):
     return type(params)(params.sigma_sq, math.inf, math.inf, params.mean_offset)
 
 
-def combine_loss_grad(dU, dV, sums, world, rank, group=None):
-    """All-reduce of the per-shard data terms; |U|^2, |V|^2 are counted once (rank 0)."""
+def combine_loss_grad(dU, dV, sums, world, rank, group=None, grads_flat=None):
+    """All-reduce of the per-shard data terms; |U|^2, |V|^2 are counted once (rank 0).
+    grads_flat: one tensor whose storage holds dU followed by dV (see alloc_grads): the two
+    gradients then travel in one collective instead of two."""
     if world == 1:
         return
     if rank != 0:
         sums[1:].zero_()
     if dU is not None:
-        dist.all_reduce(dU, group=group)
-        dist.all_reduce(dV, group=group)
+        if grads_flat is not None:
+            dist.all_reduce(grads_flat, group=group)
+        else:
+            dist.all_reduce(dU, group=group)
+            dist.all_reduce(dV, group=group)
     dist.all_reduce(sums, group=group)
+
+
+def alloc_grads(U, V):
+    """(dU, dV, flat): gradient buffers shaped like U and V that share one allocation, so that a
+    sharded step can all-reduce both with one collective."""
+    flat = torch.empty(U.numel() + V.numel(), dtype=U.dtype, device=U.device)
+    return flat[:U.numel()].view_as(U), flat[U.numel():].view_as(V), flat
 
 
 class ShardedStep:
@@ -164,10 +176,10 @@ class ShardedStep:
         dist.all_gather_into_tensor(allc, cnt)
         self.index_base = int(allc[:self.rank].sum().item())
 
-    def loss_grad(self, U, V, params, dU, dV, sums):
+    def loss_grad(self, U, V, params, dU, dV, sums, grads_flat=None):
         from . import device as D
         D.loss_grad(self.rat, self.d, U, V, prior_once_params(params, self.rank), dU, dV, sums)
-        combine_loss_grad(dU, dV, sums, self.world, self.rank)
+        combine_loss_grad(dU, dV, sums, self.world, self.rank, grads_flat=grads_flat)
 
     def select(self, criterion, ci, cj, U, V, view, cutoff, maximize, best):
         from . import device as D

@@ -349,7 +349,7 @@ def run_ours(a):
     U, V, ci, cj = prob["U"], prob["V"], prob["ci"], prob["cj"]
     ld = D.padded_ld(d, name)
     assert ld == d, "bench uses an unpadded rank"
-    dU, dV = torch.empty_like(U), torch.empty_like(V)
+    dU, dV, grads_flat = P.alloc_grads(U, V)       # one allocation: one all-reduce for both
     sums = torch.zeros(3, dtype=torch.float64, device=U.device)
     best = torch.zeros(2, dtype=torch.int64, device=U.device)
     params = D.pmf_params(1.0, 10.0, 10.0, 0.0)
@@ -365,7 +365,7 @@ def run_ours(a):
 
     def one_step(ev=None):
         if ev: ev[0].record()
-        step.loss_grad(U, V, params, dU, dV, sums)
+        step.loss_grad(U, V, params, dU, dV, sums, grads_flat)
         if ev: ev[1].record()
         step.select(N.CRIT_PRED, ci, cj, U, V, None, 0.0, True, best)
         if ev: ev[2].record()

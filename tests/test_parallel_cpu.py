@@ -49,6 +49,15 @@ def _worker(rank, world, port, out):
         assert np.allclose(dU.numpy(), fu, rtol=1e-12, atol=1e-12)
         assert np.allclose(dV.numpy(), fv, rtol=1e-12, atol=1e-12)
         assert np.allclose(sums.numpy(), [full @ full, (U * U).sum(), (V * V).sum()], rtol=1e-12)
+        # same with both gradients in one allocation: a single collective carries dU and dV
+        fU, fV, flat = P.alloc_grads(torch.from_numpy(U), torch.from_numpy(V))
+        fU.copy_(torch.from_numpy(gu)); fV.copy_(torch.from_numpy(gv))
+        s2 = torch.tensor([float(resid @ resid), float((U * U).sum()), float((V * V).sum())],
+                          dtype=torch.float64)
+        P.combine_loss_grad(fU, fV, s2, world, rank, grads_flat=flat)
+        assert np.allclose(fU.numpy(), fu, rtol=1e-12, atol=1e-12)
+        assert np.allclose(fV.numpy(), fv, rtol=1e-12, atol=1e-12)
+        assert torch.equal(s2, sums)
 
         # ---- scoring: candidate shards, winner all-gather --------------------------------------
         lo, hi = P.shard_bounds(ncand, world, rank)

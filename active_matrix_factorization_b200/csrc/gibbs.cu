@@ -2,7 +2,8 @@
 // statistics over posterior samples.
 //
 //   amf_gibbs_half_sweep : bayes_pmf.py:189-216 sample_feature for every row of one side
-//                          (the loops at :286-292 / :294-300), one CTA per row.
+//                          (the loops at :286-292 / :294-300): one warp per row for d <= 32,
+//                          one CTA per row above.
 //   amf_bayes_sample_stats : bayes_pmf.py:433-455 predict / pred_variance and :528-538
 //                          prob_ge_cutoff without materialising S dense N x M matrices.
 //
@@ -10,6 +11,8 @@
 // passes those draws in (z_d) so a seeded chain reproduces the reference's samples.  As in the
 // reference the sample is  chol(inv(Lambda)) z + mean  (lower factor of the COVARIANCE), not the
 // cheaper  Lambda = R R', x = mean + R^-T z, which has the same law but different values.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace amf {
@@ -21,8 +24,9 @@ constexpr int GIBBS_MAXD = 64;
 // (d/2)(d/2+1)/2 blocks, GIBBS_MAXBLK per thread at the largest d
 constexpr int GIBBS_MAXBLK = ((GIBBS_MAXD / 2) * (GIBBS_MAXD / 2 + 1) / 2 + GIBBS_THREADS - 1) / GIBBS_THREADS;
 
+// ---- CTA-wide dense helpers (d > 32: one CTA per row, matrices in shared memory) -------------
 // in-place lower Cholesky of the d x d matrix A (leading dimension lda) in shared memory.
-// Returns false (to all threads) if a pivot is not positive.
+// Returns false (to all threads of the group) if a pivot is not positive.
 __device__ bool chol_lower(double* A, int d, int lda, int* flag) {
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) *flag = 1;
@@ -82,7 +86,7 @@ __device__ bool solve_and_sample(double* A, double* Bm, double* rhs, double* mea
                                  int* flag, const T* __restrict__ z, T* __restrict__ out) {
   const int tid = threadIdx.x, nt = blockDim.x;
   bool ok = chol_lower(A, d, lda, flag);
-  tri_inverse_lower(A, Bm, d, lda);            // Bm = R^-1
+  tri_inverse_lower(A, Bm, d, lda);      // Bm = R^-1
   for (int t = tid; t < d * d; t += nt) {
     const int k = t / d, l = t % d;
     double s = 0;
@@ -96,7 +100,7 @@ __device__ bool solve_and_sample(double* A, double* Bm, double* rhs, double* mea
     mean[tid] = s;
   }
   __syncthreads();
-  ok = chol_lower(A, d, lda, flag) && ok;      // A = lower chol of cov
+  ok = chol_lower(A, d, lda, flag) && ok;   // A = lower chol of cov
   if (tid < d) {
     double s = mean[tid];
     for (int l = 0; l <= tid; ++l) s += A[tid * lda + l] * (double)z[l];
@@ -331,6 +335,284 @@ gibbs_rows_tc_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict_
   }
 }
 
+// ---- register-resident warp solve (d <= 32, padded to 32 with the identity) -----------------
+// Run by one warp, shared-memory formulations of the solve spend ~36k instructions per row on
+// index arithmetic and predicated read-modify-write loops.  Here a lane keeps ITS row (Cholesky) or column (inverse)
+// of the 32 x 32 matrix in registers; the one vector every lane needs per step (the current
+// Cholesky column, a row of L, a row of L^-1) goes through shared memory as a broadcast read.
+// All loops are fully unrolled (static register indices): ~4k instructions per row.
+constexpr int S32 = 34;                     // row stride of the 32 x 32 scratch (16-byte aligned rows)
+
+// fp64 sqrt / divide expand to ~40 instructions each; the unrolled solve needs 128 of them, so
+// they are kept out of line (scalar arguments: no register arrays are forced to memory)
+__device__ __noinline__ double sqrt_then_inv(double pv, double* inv) {
+  const double r = sqrt(pv);
+  *inv = 1.0 / r;
+  return r;
+}
+__device__ __noinline__ double div_f64(double a, double b) { return a / b; }
+
+// in-place lower Cholesky; lane i holds row i in a[0..31] (entries right of the diagonal are
+// don't-care on entry and junk on exit).  col: 2 x 32 doubles of shared memory.
+__device__ __forceinline__ bool chol32_rows(double (&a)[32], double* col, int lane) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double pv = __shfl_sync(0xffffffffu, a[j], j);
+    ok = ok & (pv > 0.0);                             // no short circuit: straight-line code
+    double inv;
+    const double r = sqrt_then_inv(pv, &inv);
+    double lij = lane == j ? r : a[j] * inv;
+    if (lane < j) lij = 0.0;
+    a[j] = lij;
+    double* cb = col + (j & 1) * 32;                  // double-buffered: one sync per column
+    cb[lane] = lij;
+    __syncwarp();
+#pragma unroll
+    for (int k = j + 1; k < 32; ++k) a[k] = fma(-lij, cb[k], a[k]);   // rows above k: junk, unused
+  }
+  return ok;
+}
+
+// out = chol(inv(Lambda)) z + inv(Lambda) rhs for the row whose Lambda (d x d, leading dimension
+// lda) sits in shared memory at Lam.  scr: 32 x S32 doubles (may alias Lam), col: 2 x 32, vec: 32.
+template <typename T>
+__device__ bool warp_solve32(const double* Lam, int d, int lda, double* scr, double* col, double* vec,
+                             double rhs_lane, const T* __restrict__ z, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = (lane < d && k < d) ? Lam[lane * lda + k] : (k == lane ? 1.0 : 0.0);
+  __syncwarp();                                        // Lam may be overwritten from here on
+  bool ok = chol32_rows(a, col, lane);                 // Lambda = R R'
+  // R (row per lane) -> scratch, then R^-1 by forward substitution, lane c owning column c
+#pragma unroll
+  for (int k = 0; k < 32; ++k) scr[lane * S32 + k] = k <= lane ? a[k] : 0.0;
+  __syncwarp();
+  double x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < i; k += 2) {
+      const double2 l2 = *reinterpret_cast<const double2*>(scr + i * S32 + k);
+      s0 = fma(l2.x, x[k], s0);
+      s1 = fma(l2.y, x[k + 1], s1);
+    }
+    if (i & 1) s0 = fma(scr[i * S32 + i - 1], x[i - 1], s0);
+    x[i] = div_f64((i == lane ? 1.0 : 0.0) - (s0 + s1), scr[i * S32 + i]);   // 0 above the diagonal
+  }
+  __syncwarp();
+  // R^-1 (column per lane) -> scratch rows; cov = R^-T R^-1, lane k owning row k
+#pragma unroll
+  for (int q = 0; q < 32; ++q) scr[q * S32 + lane] = x[q];
+  vec[lane] = rhs_lane;
+  __syncwarp();
+  double c[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) c[l] = 0.0;
+#pragma unroll
+  for (int l = 0; l < 32; l += 2) {
+#pragma unroll
+    for (int q = l; q < 32; ++q) {                     // terms with q < max(k, l) are zeros
+      const double2 b2 = *reinterpret_cast<const double2*>(scr + q * S32 + l);
+      c[l] = fma(x[q], b2.x, c[l]);
+      c[l + 1] = fma(x[q], b2.y, c[l + 1]);            // b2.y = 0 at q == l
+    }
+  }
+  double mean = 0;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) mean = fma(c[l], vec[l], mean);
+  __syncwarp();
+  vec[lane] = lane < d ? (double)z[lane] : 0.0;
+  ok = chol32_rows(c, col, lane) & ok;                 // cov = L L'
+  __syncwarp();
+  double sres = mean;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) sres = fma(l <= lane ? c[l] : 0.0, vec[l], sres);
+  if (lane < d) out[lane] = (T)sres;
+  return ok;
+}
+
+// ---- d <= 32: one WARP per row ---------------------------------------------------------------
+// The per-row work after the Gram matrix is a chain of ~100 short dependent steps (two Cholesky
+// factorisations, a triangular inverse) on a matrix of at most 32 x 32: with a CTA per row the
+// time goes to block barriers.  Here every warp owns a row, solves it in registers
+// (warp_solve32) and synchronises with __syncwarp only; the four warps of a CTA never meet.
+//   TC (fp32, d == 32): Gram matrix on the tensor cores as in gibbs_rows_tc_kernel, all k-steps
+//   of the row taken by the one warp; otherwise 2 x 2 register blocks spread over the 32 lanes.
+constexpr int GIBBS_WARP_MAXBLK = (16 * 17 / 2 + 31) / 32;   // 2 x 2 blocks per lane at d = 32
+
+template <typename T, bool TC>
+__global__ void __launch_bounds__(GIBBS_THREADS)
+gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                       const T* __restrict__ val, int row_begin, int rows, int d,
+                       const T* __restrict__ other, const T* __restrict__ alpha,
+                       const T* __restrict__ mu, double beta, double mean_offset,
+                       const T* __restrict__ z, T* __restrict__ out, int* __restrict__ fail,
+                       int a_doubles, int warp_doubles) {
+  extern __shared__ double smem[];
+  constexpr int NW = GIBBS_THREADS / 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lda = d + 1;
+  // per warp: [ staged tile | Lambda (d x lda) | 32 x S32 scratch of the solve ] share one region
+  // (each is dead before the next is written), then the column / vector buffers of the solve
+  double* A = smem + (size_t)w * warp_doubles;
+  double* col = A + a_doubles;                      // 2 x 32
+  double* vec = col + 64;                           // 32
+  T* tile = reinterpret_cast<T*>(A);
+  const int dp = (d + 1) & ~1;
+  const int ldt = TC ? 40 : dp + 2;                 // TC: == 8 (mod 32), conflict-free fragments
+  const int hb = dp / 2, nblk = hb * (hb + 1) / 2;
+  const int g = lane >> 2, tig = lane & 3;
+
+  int bks[GIBBS_WARP_MAXBLK], bls[GIBBS_WARP_MAXBLK];
+  if (!TC) {
+#pragma unroll
+    for (int a = 0; a < GIBBS_WARP_MAXBLK; ++a) {
+      int blk = lane + a * 32, bk = 0;
+      if (blk < nblk) {
+        while (blk >= hb - bk) { blk -= hb - bk; ++bk; }
+        bks[a] = bk; bls[a] = bk + blk;
+      } else {
+        bks[a] = -1; bls[a] = 0;
+      }
+    }
+  }
+
+#pragma unroll 1
+  for (int row = row_begin + blockIdx.x * NW + w; row < rows; row += gridDim.x * NW) {
+    const int64_t p0 = ptr[row], p1 = ptr[row + 1];
+    T acc[GIBBS_WARP_MAXBLK][4];
+    float c[6][4];
+#pragma unroll
+    for (int a = 0; a < GIBBS_WARP_MAXBLK; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) c[t][0] = c[t][1] = c[t][2] = c[t][3] = 0.f;
+    T racc = 0;                                      // lane k < d accumulates rhs[k]
+#pragma unroll 1
+    for (int64_t base = p0; base < p1; base += 32) {
+      const int cnt = (int)min((int64_t)32, p1 - base);
+      // lane e holds index and centred rating of the tile's e-th entry
+      const int32_t jreg = lane < cnt ? idx[base + lane] : 0;
+      const T rreg = lane < cnt ? (T)((double)val[base + lane] - mean_offset) : T(0);
+      if (TC) {
+        const int cnt8 = (cnt + 7) & ~7;             // whole k-steps, zero-filled past cnt
+        // a lane stages the q-th 16-byte slice of rows e = it*4 + lane/8: all eight gathers are
+        // issued before the first store (one L2 round trip per tile, not eight)
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int e = it * 4 + (lane >> 3);
+          const int32_t j = __shfl_sync(0xffffffffu, jreg, e);
+          v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < cnt) v[it] = __ldg(reinterpret_cast<const float4*>(other + (int64_t)j * 32) + (lane & 7));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int e = it * 4 + (lane >> 3);
+          if (e < cnt8)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(tile) + e * 40 + 4 * (lane & 7)) = v[it];
+        }
+        __syncwarp();
+        const float* tf = reinterpret_cast<const float*>(tile);
+        for (int e0 = 0; e0 < cnt8; e0 += 8) {
+          uint32_t xh[4], xl[4], yh[4], yl[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = tf[(e0 + tig) * 40 + 8 * j + g];
+            const float y = tf[(e0 + tig + 4) * 40 + 8 * j + g];
+            xh[j] = to_tf32(x); xl[j] = to_tf32(x - __uint_as_float(xh[j]));
+            yh[j] = to_tf32(y); yl[j] = to_tf32(y - __uint_as_float(yh[j]));
+          }
+          int t = 0;
+#pragma unroll
+          for (int M = 0; M < 2; ++M) {
+            const uint32_t ah[4] = {xh[2 * M], xh[2 * M + 1], yh[2 * M], yh[2 * M + 1]};
+            const uint32_t al[4] = {xl[2 * M], xl[2 * M + 1], yl[2 * M], yl[2 * M + 1]};
+#pragma unroll
+            for (int N = 2 * M; N < 4; ++N, ++t) {
+              mma_tf32(c[t], al, xh[N], yh[N]);
+              mma_tf32(c[t], ah, xl[N], yl[N]);
+              mma_tf32(c[t], ah, xh[N], yh[N]);
+            }
+          }
+        }
+      } else {
+        for (int t = lane; t < cnt * dp; t += 32) {
+          const int e = t / dp, k = t - e * dp;
+          tile[e * ldt + k] = k < d ? other[(int64_t)idx[base + e] * d + k] : T(0);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < GIBBS_WARP_MAXBLK; ++a) {
+          if (bks[a] >= 0) {
+            const T* pa = tile + 2 * bks[a];
+            const T* pb = tile + 2 * bls[a];
+            T s00 = acc[a][0], s01 = acc[a][1], s10 = acc[a][2], s11 = acc[a][3];
+            for (int e = 0; e < cnt; ++e) {
+              const T a0 = pa[e * ldt], a1 = pa[e * ldt + 1];
+              const T b0 = pb[e * ldt], b1 = pb[e * ldt + 1];
+              s00 = fma(a0, b0, s00); s01 = fma(a0, b1, s01);
+              s10 = fma(a1, b0, s10); s11 = fma(a1, b1, s11);
+            }
+            acc[a][0] = s00; acc[a][1] = s01; acc[a][2] = s10; acc[a][3] = s11;
+          }
+        }
+      }
+      {
+        T sres = racc;
+        for (int e = 0; e < cnt; ++e) {
+          const T re = __shfl_sync(0xffffffffu, rreg, e);
+          if (lane < d) sres = fma(tile[e * ldt + lane], re, sres);
+        }
+        racc = sres;
+      }
+      __syncwarp();
+    }
+    // ---- Lambda = alpha + beta F'F ; rhs = beta F'r + alpha mu ---------------------------
+    if (TC) {
+#pragma unroll
+      for (int M = 0, t = 0; M < 2; ++M)
+#pragma unroll
+        for (int N = 2 * M; N < 4; ++N, ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = 16 * M + g + 8 * (q >> 1), l = 8 * N + 2 * tig + (q & 1);
+            if (k <= l) {
+              A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)c[t][q];
+              if (k != l) A[l * lda + k] = (double)alpha[l * d + k] + beta * (double)c[t][q];
+            }
+          }
+    } else {
+#pragma unroll
+      for (int a = 0; a < GIBBS_WARP_MAXBLK; ++a) {
+        if (bks[a] >= 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = 2 * bks[a] + (q >> 1), l = 2 * bls[a] + (q & 1);
+            if (k < d && l < d) {
+              A[k * lda + l] = (double)alpha[k * d + l] + beta * (double)acc[a][q];
+              if (k != l && bks[a] != bls[a])
+                A[l * lda + k] = (double)alpha[l * d + k] + beta * (double)acc[a][q];
+            }
+          }
+        }
+      }
+    }
+    double rhs_lane = 0;
+    if (lane < d) {
+      rhs_lane = beta * (double)racc;
+      for (int l = 0; l < d; ++l) rhs_lane += (double)alpha[lane * d + l] * (double)mu[l];
+    }
+    __syncwarp();
+    const bool ok = warp_solve32<T>(A, d, lda, A, col, vec, rhs_lane, z + (int64_t)row * d,
+                                    out + (int64_t)row * d);
+    if (!ok && lane == 0) atomicExch(fail, 1);
+    __syncwarp();
+  }
+}
+
 // mean / population variance / exceedance frequency of U_s[i].V_s[j] + offset over S samples
 template <typename T, bool MAX>
 __global__ void __launch_bounds__(128)
@@ -385,25 +667,43 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
   AMF_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
   const int span = row_end - row_begin;
   const int grid = span < num_sms() * 8 ? span : num_sms() * 8;
+  if (d <= 32) {
+    // one warp per row; per-warp shared memory: A, Bm (or the staged tile), rhs, mean, flag
+    const bool tc = sizeof(T) == 4 && d == 32;
+    const size_t tile_bytes = tc ? 32 * 40 * sizeof(float) : 32 * (size_t)(((d + 1) & ~1) + 2) * sizeof(T);
+    const int a_doubles = (int)std::max({(size_t)d * (d + 1), (tile_bytes + 7) / 8, (size_t)32 * 34});
+    const int warp_doubles = (a_doubles + 64 + 32 + 1) & ~1;                    // 16-byte multiple
+    const size_t smem_w = sizeof(double) * (size_t)warp_doubles * (GIBBS_THREADS / 32);
+    const int nwarp_rows = (span + GIBBS_THREADS / 32 - 1) / (GIBBS_THREADS / 32);
+    const int grid_w = nwarp_rows < num_sms() * 8 ? nwarp_rows : num_sms() * 8;
+#define GIBBS_WARP(TC_)                                                                          \
+  do {                                                                                           \
+    AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));    \
+    gibbs_rows_warp_kernel<T, TC_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(                        \
+        h->ptr[side], h->idx[side], (const T*)h->val[side], row_begin, rows, d, other, alpha, mu, \
+        beta, mean_offset, z, out, fail, a_doubles, warp_doubles);                               \
+  } while (0)
+    if constexpr (sizeof(T) == 4) {
+      if (tc) GIBBS_WARP(true); else GIBBS_WARP(false);
+    } else {
+      GIBBS_WARP(false);
+    }
+#undef GIBBS_WARP
+    AMF_LAUNCH_CHECK();
+    return AMF_OK;
+  }
   if constexpr (sizeof(T) == 4) {
-    if (d == 32 || d == 64) {            // dense enough for whole MMA tiles: tensor-core Gram
+    if (d == 64) {                       // dense enough for whole MMA tiles: tensor-core Gram
       const int mt = d / 16, ntiles = mt * (mt + 1);
       const size_t stage = (size_t)GIBBS_TC_TILE * (d + 8), parts = (size_t)(GIBBS_THREADS / 32) * ntiles * 128;
       const size_t smem_tc = sizeof(double) * (2 * d * (d + 1) + 2 * d) +
                              sizeof(float) * (GIBBS_TC_TILE + (stage > parts ? stage : parts));
-      if (d == 32) {
-        AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_tc_kernel<32>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-        gibbs_rows_tc_kernel<32><<<grid, GIBBS_THREADS, smem_tc, s>>>(
-            h->ptr[side], h->idx[side], (const float*)h->val[side], row_begin, rows, other, alpha,
-            mu, beta, mean_offset, z, out, fail);
-      } else {
-        AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_tc_kernel<64>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-        gibbs_rows_tc_kernel<64><<<grid, GIBBS_THREADS, smem_tc, s>>>(
-            h->ptr[side], h->idx[side], (const float*)h->val[side], row_begin, rows, other, alpha,
-            mu, beta, mean_offset, z, out, fail);
-      }
+      AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_tc_kernel<64>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      gibbs_rows_tc_kernel<64><<<grid, GIBBS_THREADS, smem_tc, s>>>(
+          h->ptr[side], h->idx[side], (const float*)h->val[side], row_begin, rows, other, alpha,
+          mu, beta, mean_offset, z, out, fail);
       AMF_LAUNCH_CHECK();
       return AMF_OK;
     }

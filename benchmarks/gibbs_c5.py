@@ -26,5 +26,5 @@ for side, rows, other in ((0, n, p["V"]), (1, m, p["U"])):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     flops = rat.nnz * (2 * d * d + 2 * d)
-    print("side %d: %d rows, %.2f ms per half-sweep, %.2e rows/s, Gram %.1f TFLOP/s, finite=%s" % (
+    print("side %d: %d rows, %.2f ms per half-sweep, %.2e rows/s, %.1f TFLOP/s counting only the Gram flops, finite=%s" % (
         side, rows, ms, rows / ms * 1e3, flops / ms / 1e9, bool(torch.isfinite(out).all())))

@@ -444,7 +444,7 @@ __device__ bool warp_solve32(const double* Lam, int d, int lda, double* scr, dou
 constexpr int GIBBS_WARP_MAXBLK = (16 * 17 / 2 + 31) / 32;   // 2 x 2 blocks per lane at d = 32
 
 template <typename T, bool TC>
-__global__ void __launch_bounds__(GIBBS_THREADS)
+__global__ void __launch_bounds__(GIBBS_THREADS, 3)   // <= 168 registers: 12 warps per SM
 gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const T* __restrict__ val, int row_begin, int rows, int d,
                        const T* __restrict__ other, const T* __restrict__ alpha,

@@ -366,9 +366,12 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
   }
 }
 
-static int tiled_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+// tuning knob for benchmarks/tiled_variants.py: AMF_TILED_KB = shared memory given to the tile
+// (default 224 KB, the most that fits next to the static buffers); clamped to [16, 224]
+static int tiled_tile_kb() {
+  const char* e = getenv("AMF_TILED_KB");
+  const int kb = e ? atoi(e) : 224;
+  return kb < 16 ? 16 : (kb > 224 ? 224 : kb);
 }
 
 template <typename T, bool GRAD>
@@ -423,7 +426,7 @@ int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V
   }
   if (h->tiled_mode == AMF_LAYOUT_AUTO && h->nnz < TILED_AUTO_MIN_NNZ) return AMF_OK;
   if (h->tiled_row_bytes != (int)row_bytes) {
-    const int tile_rows = (int)(((size_t)tiled_env("AMF_TILED_KB", 224) * 1024) / row_bytes);
+    const int tile_rows = (int)(((size_t)tiled_tile_kb() * 1024) / row_bytes);
     int rc = AMF_OK;
     for (int side = 0; side < 2 && rc == AMF_OK; ++side) {
       const int32_t tile_side_rows = side == 0 ? h->n_items : h->n_users;

@@ -1,6 +1,6 @@
 """Times the tiled fused loss+gradient (tiled_side_kernel x2 + prior x2) on the C5 rating list
-for experiment settings given as FLAGS:TILE_KB pairs (AMF_TILED_FLAGS / AMF_TILED_KB), each in
-a child process; 'rows' times the row-sorted kernels."""
+for the tile sizes (KB of shared memory, AMF_TILED_KB) given on the command line, each in a
+child process; 'rows' times the row-sorted kernels."""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
@@ -27,14 +27,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     e0.record()
     for _ in range(20): run()
     e1.record(); torch.cuda.synchronize()
-    print("%s flags=%s tile_kb=%s: %.4f ms  sums=%s |dU|=%.6e |dV|=%.6e" % (
-        sys.argv[2], os.environ.get("AMF_TILED_FLAGS"), os.environ.get("AMF_TILED_KB"), e0.elapsed_time(e1) / 20,
+    print("%s tile_kb=%s: %.4f ms  sums=%s |dU|=%.6e |dV|=%.6e" % (
+        sys.argv[2], os.environ.get("AMF_TILED_KB"), e0.elapsed_time(e1) / 20,
         sums.cpu().numpy(), dU.double().norm().item(), dV.double().norm().item()))
 else:
-    for spec in sys.argv[1:] or ["1:224"]:
+    for spec in sys.argv[1:] or ["224"]:
         if spec == "rows":
             subprocess.run([sys.executable, __file__, "--child", "rows"], check=True)
             continue
-        flags, _, kb = spec.partition(":")
-        env = dict(os.environ, AMF_TILED_FLAGS=flags, AMF_TILED_KB=kb or "224")
+        env = dict(os.environ, AMF_TILED_KB=spec)
         subprocess.run([sys.executable, __file__, "--child", "tiled"], env=env, check=True)

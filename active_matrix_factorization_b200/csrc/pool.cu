@@ -136,9 +136,8 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
   const int g = lane >> 2, l = lane & 3;
   const uint32_t jmask = (1u << jbits) - 1;
   const bool have = l < NVEC;                         // rows narrower than four slices
-  uint32_t off0, xo[CPL];
   constexpr bool ADJ = CPL == 2;                      // measured: -3 % time at d=32 fp32
-  slice_order<CPL, ADJ>(l, g & 1, have, off0, xo);
+  const uint32_t off0 = slice_off0<CPL, ADJ>(l, g & 1, have);
   const uint32_t vrow0 = smem0 + off0;                // tile base is 1024-byte aligned
   const uint64_t urow = (uint64_t)reinterpret_cast<uintptr_t>(U);
 
@@ -199,16 +198,15 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
         T p[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          // slice t of a row sits at  off[0] ^ xo[t]  (rows are ROW_BYTES-aligned): one address
-          // per row, the other slices by XOR
+          // slice t of a row sits at  off0 ^ slice_xor(t)  (rows are ROW_BYTES-aligned)
           const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
           V b[CPL];
 #pragma unroll
-          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ xo[t], V());
+          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ slice_xor<CPL, ADJ>(t), V());
           const uint32_t i = w[s] >> jbits;
           if (i != prev_i) {                          // next user of this lane group's run
             prev_i = i;
-            load_row_slices<V, CPL, ADJ>(urow + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, xo, a);
+            load_row_slices<V, CPL, ADJ>(urow + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, a);
           }
           const T acc = dot_slices<CPL>(a, b);
           p[s] = have ? acc : T(0);

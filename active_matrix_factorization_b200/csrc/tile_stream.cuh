@@ -84,26 +84,26 @@ __device__ __forceinline__ double2 vsel(bool c, const double2& a, const double2&
 // eight lanes of a wavefront always touch eight different 16-byte bank groups.
 //   ADJ (CPL == 2 only): lane l owns the adjacent slices 2l, 2l+1 (one 256-bit global load
 //             fetches both, at the price of 8 selects) and visits 2l+gq first;
-//   else    : lane l owns l, l+4, l+8, ... and starts at slice l + 4*(gq mod CPL).
-// off0 = byte offset of the first slice visited, xo[t] = XOR that turns it into the t-th.
+//   else    : lane l owns l, l+4, l+8, ... and visits l + 4*(t ^ gq) at step t.
+// Either way the t-th slice is at  off0 ^ slice_xor(t)  with off0 = slice_off0(...) the byte
+// offset of the first one and slice_xor a compile-time constant (16*t or 64*t): one address per
+// row, the other slices by XOR with an immediate.
 template <int CPL, bool ADJ>
-__device__ __forceinline__ void slice_order(int l, int gq, bool have, uint32_t& off0,
-                                            uint32_t (&xo)[CPL]) {
+__device__ __forceinline__ uint32_t slice_off0(int l, int gq, bool have) {
   static_assert(!ADJ || CPL == 2, "adjacent ownership is for two slices per lane");
+  static_assert((CPL & (CPL - 1)) == 0, "slices per lane must be a power of two");
   const int ll = have ? l : 0;
-  if constexpr (ADJ) {
-    off0 = (uint32_t)(2 * ll + gq) * 16u;
-    xo[0] = 0; xo[1] = 16u;
-  } else {
-    off0 = (uint32_t)(ll + 4 * (gq % CPL)) * 16u;
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) xo[t] = off0 ^ ((uint32_t)(ll + 4 * ((t + gq) % CPL)) * 16u);
-  }
+  if constexpr (ADJ) return (uint32_t)(2 * ll + gq) * 16u;
+  return (uint32_t)(ll + 4 * (CPL > 1 ? gq : 0)) * 16u;
+}
+template <int CPL, bool ADJ>
+__device__ __forceinline__ constexpr uint32_t slice_xor(int t) {
+  return ADJ ? 16u * (uint32_t)t : 64u * (uint32_t)t;
 }
 // the lane's slices of the row at `row` (global, row-aligned), in visiting order
 template <typename V, int CPL, bool ADJ>
 __device__ __forceinline__ void load_row_slices(uint64_t row, int l, int gq, uint32_t off0,
-                                                const uint32_t (&xo)[CPL], V (&a)[CPL]) {
+                                                V (&a)[CPL]) {
   if constexpr (ADJ) {
     V n0, n1;
     ldg_v2(reinterpret_cast<const unsigned char*>(row + 32u * (uint32_t)l), n0, n1);
@@ -112,7 +112,7 @@ __device__ __forceinline__ void load_row_slices(uint64_t row, int l, int gq, uin
   } else {
 #pragma unroll
     for (int t = 0; t < CPL; ++t)
-      a[t] = ldg_v(reinterpret_cast<const unsigned char*>((row + off0) ^ (uint64_t)xo[t]), V());
+      a[t] = ldg_v(reinterpret_cast<const unsigned char*>((row + off0) ^ (uint64_t)slice_xor<CPL, ADJ>(t)), V());
   }
 }
 

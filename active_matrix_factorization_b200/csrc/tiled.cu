@@ -242,10 +242,10 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
   const int g = lane >> 2, l = lane & 3;
   const uint32_t jmask = (1u << jbits) - 1;
   const bool have = l < NVEC;
-  uint32_t off0, xo[CPL];
   // interleaved ownership: the 256-bit row load costs this kernel registers it does not have
   // (measured +6 % time)
-  slice_order<CPL, false>(l, g & 1, have, off0, xo);
+  constexpr bool ADJ = false;
+  const uint32_t off0 = slice_off0<CPL, ADJ>(l, g & 1, have);
   const uint32_t vrow0 = smem0 + off0;
   const uint64_t own_base = (uint64_t)reinterpret_cast<uintptr_t>(Own);
   const uint64_t down0 = (uint64_t)reinterpret_cast<uintptr_t>(dOwn) + off0;
@@ -327,17 +327,17 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
           const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
           V b[CPL];
 #pragma unroll
-          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ xo[t], V());
+          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ slice_xor<CPL, ADJ>(t), V());
           const uint32_t i = w[s] >> jbits;
           if (i != prev_i) {                          // next row of this lane group's run
             if (GRAD && prev_i != NONE && have) {
               const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
 #pragma unroll
               for (int t = 0; t < CPL; ++t)
-                red_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
+                red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
             }
             prev_i = i;
-            load_row_slices<V, CPL, false>(own_base + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, xo, a);
+            load_row_slices<V, CPL, ADJ>(own_base + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, a);
 #pragma unroll
             for (int t = 0; t < CPL; ++t) acc[t] = vzero(V());
           }
@@ -354,7 +354,7 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
       if (GRAD && prev_i != NONE && have) {
         const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
 #pragma unroll
-        for (int t = 0; t < CPL; ++t) red_add(reinterpret_cast<T*>(dp ^ (uint64_t)xo[t]), acc[t]);
+        for (int t = 0; t < CPL; ++t) red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
       }
       if (l == 0) local_sq += chunk_sq;
     }

@@ -26,7 +26,8 @@ int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V
                   const void* dV, bool* use, cudaStream_t s);
 template <typename T>
 int tiled_loss_grad(const amf_ratings* h, int ld, const T* U, const T* V, T inv_sigma,
-                    T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s);
+                    T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s,
+                    cudaEvent_t dU_done);
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -355,9 +356,12 @@ static int tail_terms(const amf_ratings* h, int d, int ld, const T* U, const T* 
                      sums, s, false);
 }
 
+// dU_done (optional): recorded on s as soon as dU holds its final value (before the pass that
+// produces dV), so a host-buffer caller can start copying dU back while dV is computed
 template <typename T>
 static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V,
-                     const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s) {
+                     const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s,
+                     cudaEvent_t dU_done = nullptr) {
   constexpr int N = Vec<T>::N;
   AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
   AMF_REQUIRE((dU == nullptr) == (dV == nullptr), "dU and dV must both be given or both NULL");
@@ -368,23 +372,32 @@ static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V
   AMF_LAUNCH_CHECK();
   prior_kernel<T><<<gv, 256, 0, s>>>(V, cv, (T)(-1.0 / p->sigma_v_sq), dV, sums + 2);
   AMF_LAUNCH_CHECK();
-  if (h->nnz == 0) return tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
+  // the appended tail (if any) touches dU last: then dU is final only at the very end
+  cudaEvent_t early = h->tail_n > 0 ? nullptr : dU_done;
+  if (h->nnz == 0) {
+    int rc0 = tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
+    if (rc0 == AMF_OK && dU_done) AMF_CUDA(cudaEventRecord(dU_done, s));
+    return rc0;
+  }
   const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
   int rc;
   bool tiled = false;
   rc = tiled_prepare(const_cast<amf_ratings*>(h), (size_t)ld * sizeof(T), U, V, dU, dV, &tiled, s);
   if (rc != AMF_OK) return rc;
   if (tiled) {
-    rc = tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s);
+    rc = tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s, early);
   } else if (dU) {
     rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
     if (rc != AMF_OK) return rc;
+    if (early) AMF_CUDA(cudaEventRecord(early, s));
     rc = launch_side<T, true>(h, 1, V, U, ld, inv_sigma, mo, dV, nullptr, s);
   } else {
     rc = launch_side<T, false>(h, 0, U, V, ld, inv_sigma, mo, nullptr, sums, s);
   }
   if (rc != AMF_OK) return rc;
-  return tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
+  rc = tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
+  if (rc == AMF_OK && dU_done && (!early || !dU)) AMF_CUDA(cudaEventRecord(dU_done, s));
+  return rc;
 }
 
 template <typename T>
@@ -537,7 +550,15 @@ int amf_pmf_loss_grad_host(const amf_ratings_t* hc, int dtype, int d, const void
   int rc;
   if ((rc = ensure_stage(h, 0, bu)) || (rc = ensure_stage(h, 1, bv))) return rc;
   if (dU_h && ((rc = ensure_stage(h, 2, bu)) || (rc = ensure_stage(h, 3, bv)))) return rc;
-  cudaStream_t s = nullptr;
+  // two streams: dU goes back to the host while the second pass is still producing dV
+  static thread_local cudaStream_t s = nullptr, s_copy = nullptr;
+  static thread_local cudaEvent_t ev_dU = nullptr, ev_copied = nullptr;
+  if (!s) {
+    AMF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    AMF_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    AMF_CUDA(cudaEventCreateWithFlags(&ev_dU, cudaEventDisableTiming));
+    AMF_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+  }
   if (ld != d) {
     AMF_CUDA(cudaMemsetAsync(h->stage[0], 0, bu, s));
     AMF_CUDA(cudaMemsetAsync(h->stage[1], 0, bv, s));
@@ -546,14 +567,23 @@ int amf_pmf_loss_grad_host(const amf_ratings_t* hc, int dtype, int d, const void
                              cudaMemcpyHostToDevice, s));
   AMF_CUDA(cudaMemcpy2DAsync(h->stage[1], ld * es, V_h, d * es, d * es, h->n_items,
                              cudaMemcpyHostToDevice, s));
-  rc = amf_pmf_loss_grad(h, dtype, d, ld, h->stage[0], h->stage[1], p,
-                         dU_h ? h->stage[2] : nullptr, dU_h ? h->stage[3] : nullptr, h->sums_d, s);
+  void* dU_d = dU_h ? h->stage[2] : nullptr;
+  void* dV_d = dU_h ? h->stage[3] : nullptr;
+  if (dtype == AMF_F32)
+    rc = loss_grad<float>(h, d, ld, (const float*)h->stage[0], (const float*)h->stage[1], p,
+                          (float*)dU_d, (float*)dV_d, h->sums_d, s, dU_h ? ev_dU : nullptr);
+  else
+    rc = loss_grad<double>(h, d, ld, (const double*)h->stage[0], (const double*)h->stage[1], p,
+                           (double*)dU_d, (double*)dV_d, h->sums_d, s, dU_h ? ev_dU : nullptr);
   if (rc != AMF_OK) return rc;
   if (dU_h) {
+    AMF_CUDA(cudaStreamWaitEvent(s_copy, ev_dU, 0));
     AMF_CUDA(cudaMemcpy2DAsync(dU_h, d * es, h->stage[2], ld * es, d * es, h->n_users,
-                               cudaMemcpyDeviceToHost, s));
+                               cudaMemcpyDeviceToHost, s_copy));
+    AMF_CUDA(cudaEventRecord(ev_copied, s_copy));
     AMF_CUDA(cudaMemcpy2DAsync(dV_h, d * es, h->stage[3], ld * es, d * es, h->n_items,
                                cudaMemcpyDeviceToHost, s));
+    AMF_CUDA(cudaStreamWaitEvent(s, ev_copied, 0));
   }
   AMF_CUDA(cudaMemcpyAsync(sums_h, h->sums_d, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   AMF_CUDA(cudaStreamSynchronize(s));

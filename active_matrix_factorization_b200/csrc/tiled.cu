@@ -453,20 +453,22 @@ void tiled_free(amf_ratings* h) {
 
 template <typename T>
 int tiled_loss_grad(const amf_ratings* h, int ld, const T* U, const T* V, T inv_sigma,
-                    T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s) {
+                    T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s,
+                    cudaEvent_t dU_done) {
   const int nvec = ld / Vec<T>::N;
   int rc;
   if (dU) {
     rc = launch_tiled<T, true>(h, 0, nvec, U, V, inv_sigma, mean_offset, dU, sq_err, s);
     if (rc != AMF_OK) return rc;
+    if (dU_done) AMF_CUDA(cudaEventRecord(dU_done, s));   // dU is final: the caller may read it
     return launch_tiled<T, true>(h, 1, nvec, V, U, inv_sigma, mean_offset, dV, nullptr, s);
   }
   return launch_tiled<T, false>(h, 0, nvec, U, V, inv_sigma, mean_offset, nullptr, sq_err, s);
 }
 template int tiled_loss_grad<float>(const amf_ratings*, int, const float*, const float*, float,
-                                    float, float*, float*, double*, cudaStream_t);
+                                    float, float*, float*, double*, cudaStream_t, cudaEvent_t);
 template int tiled_loss_grad<double>(const amf_ratings*, int, const double*, const double*, double,
-                                     double, double*, double*, double*, cudaStream_t);
+                                     double, double*, double*, double*, cudaStream_t, cudaEvent_t);
 
 }  // namespace amf
 

@@ -104,6 +104,20 @@ def _criterion(name, normal_fit, spawn, chooser):
 ################################################################################
 ### Main code
 
+def _pool_arrays(pool):
+    """(i, j) int32 arrays of a list of index pairs; one pass over a flattened iterator is the
+    cheapest way through the per-tuple Python cost that dominates scoring of large pools."""
+    import itertools
+    n = len(pool)
+    try:
+        flat = np.fromiter(itertools.chain.from_iterable(pool), dtype=np.int64, count=2 * n)
+    except (TypeError, ValueError):          # pairs that are not plain integer 2-tuples
+        ii, jj = zip(*pool)
+        return np.asarray(ii, dtype=np.int32), np.asarray(jj, dtype=np.int32)
+    flat = flat.reshape(n, 2)
+    return flat[:, 0].astype(np.int32), flat[:, 1].astype(np.int32)
+
+
 class ActivePMF(ProbabilisticMatrixFactorization):
     verbose_lookahead = False   # the reference prints one line per lookahead (active_pmf.py:702-703)
     max_normal_steps = 0        # > 0 caps the accepted steps of one fit_normal (0: to convergence)
@@ -542,7 +556,7 @@ class ActivePMF(ProbabilisticMatrixFactorization):
             pool = list(pool)
             if not pool:
                 return []
-            ii, jj = zip(*pool) if name != 'random_weighting' else ((), ())
+            ii, jj = _pool_arrays(pool) if name != 'random_weighting' else ((), ())
         if name == 'random_weighting':
             return [random.random() for _ in range(len(pool))]
         if name == 'pred':

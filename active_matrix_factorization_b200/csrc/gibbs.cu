@@ -490,12 +490,19 @@ gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
 #pragma unroll
     for (int t = 0; t < 6; ++t) c[t][0] = c[t][1] = c[t][2] = c[t][3] = 0.f;
     T racc = 0;                                      // lane k < d accumulates rhs[k]
+    // lane e holds index and rating of the tile's e-th entry; the next tile's are loaded one
+    // tile ahead so that only the gather of the rated rows waits on memory inside a tile
+    int32_t jnext = p0 + lane < p1 ? idx[p0 + lane] : 0;
+    T vnext = p0 + lane < p1 ? val[p0 + lane] : T(0);
 #pragma unroll 1
     for (int64_t base = p0; base < p1; base += 32) {
       const int cnt = (int)min((int64_t)32, p1 - base);
-      // lane e holds index and centred rating of the tile's e-th entry
-      const int32_t jreg = lane < cnt ? idx[base + lane] : 0;
-      const T rreg = lane < cnt ? (T)((double)val[base + lane] - mean_offset) : T(0);
+      const int32_t jreg = jnext;
+      const T rreg = lane < cnt ? (T)((double)vnext - mean_offset) : T(0);
+      if (base + 32 + lane < p1) {
+        jnext = idx[base + 32 + lane];
+        vnext = val[base + 32 + lane];
+      }
       if (TC) {
         const int cnt8 = (cnt + 7) & ~7;             // whole k-steps, zero-filled past cnt
         // a lane stages the q-th 16-byte slice of rows e = it*4 + lane/8: all eight gathers are

@@ -437,7 +437,10 @@ int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V
     if (rc != AMF_OK) {
       free_tiled_side(&h->tiled[0]); free_tiled_side(&h->tiled[1]);
       h->tiled_row_bytes = 0;
-      if (rc == AMF_ERR_UNSUPPORTED && h->tiled_mode == AMF_LAYOUT_AUTO) return AMF_OK;
+      if (rc == AMF_ERR_UNSUPPORTED && h->tiled_mode == AMF_LAYOUT_AUTO) {
+        h->tiled_mode = AMF_LAYOUT_ROWS;     // do not try again at every call
+        return AMF_OK;
+      }
       return rc;
     }
     h->tiled_row_bytes = (int)row_bytes;

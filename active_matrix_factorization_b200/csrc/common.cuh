@@ -133,6 +133,18 @@ __device__ __forceinline__ Best block_best(Best b) {
   return b;
 }
 
+// row[p] = row of entry p of a list given by row offsets ptr[0..rows] (warp per row).  A template
+// only so that every translation unit that launches it gets its own copy without -rdc.
+template <typename Index>
+__global__ void expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
+                                   Index* __restrict__ row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) row[p] = (Index)r;
+}
+
 // final reduction of per-block partial winners (launch with one block)
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);

@@ -133,16 +133,6 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
                       cudaStream_t s);
 void tiled_free(amf_ratings* h);
 
-// row[p] = row of entry p of a row-sorted list (warp per row)
-__global__ void ratings_expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
-                                           int32_t* __restrict__ row) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < rows; r += nwarps)
-    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) row[p] = (int32_t)r;
-}
-
 static void free_sides(amf_ratings* h) {
   for (int s = 0; s < 2; ++s) {
     cudaFree(h->ptr[s]); cudaFree(h->idx[s]); cudaFree(h->val[s]); cudaFree(h->sub_row[s]);
@@ -164,7 +154,7 @@ int ratings_compact(amf_ratings* h, cudaStream_t s) {
   AMF_CUDA(cudaMalloc(&j_d, 4 * (size_t)total));
   AMF_CUDA(cudaMalloc(&r_d, es * (size_t)total));
   if (n0 > 0) {
-    ratings_expand_rows_kernel<<<num_sms() * 8, 256, 0, s>>>(h->ptr[0], h->n_users, i_d);
+    expand_rows_kernel<int32_t><<<num_sms() * 8, 256, 0, s>>>(h->ptr[0], h->n_users, i_d);
     AMF_LAUNCH_CHECK();
     AMF_CUDA(cudaMemcpyAsync(j_d, h->idx[0], 4 * (size_t)n0, cudaMemcpyDeviceToDevice, s));
     AMF_CUDA(cudaMemcpyAsync(r_d, h->val[0], es * (size_t)n0, cudaMemcpyDeviceToDevice, s));

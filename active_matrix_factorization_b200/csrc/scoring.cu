@@ -272,18 +272,6 @@ int acquire_partials(Best** out, cudaStream_t s) {
 
 using namespace amf;
 
-namespace amf {
-// ci[p] = row of candidate p for a pool given by row offsets (warp per row)
-__global__ void expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
-                                   int32_t* __restrict__ ci) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < rows; r += nwarps)
-    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) ci[p] = (int32_t)r;
-}
-}  // namespace amf
-
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -414,7 +402,7 @@ static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const 
   AMF_CUDA(cudaEventRecord(ev[HOST_CHUNKS], s_copy));
   AMF_CUDA(cudaStreamWaitEvent(s_comp, ev[HOST_CHUNKS], 0));
   if (ncand > 0 && ptr_h) {
-    expand_rows_kernel<<<num_sms() * 8, 256, 0, s_comp>>>((const int64_t*)st.p[6], n, ci_d);
+    expand_rows_kernel<int32_t><<<num_sms() * 8, 256, 0, s_comp>>>((const int64_t*)st.p[6], n, ci_d);
     AMF_LAUNCH_CHECK();
   }
   const int nchunks = ncand >= (int64_t)HOST_CHUNKS * (1 << 20) ? HOST_CHUNKS : 1;

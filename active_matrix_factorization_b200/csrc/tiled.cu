@@ -31,16 +31,6 @@ static int bits_for_u64(uint64_t x) {
   return b;
 }
 
-// own[p] = row of entry p of the row-sorted list (warp per row)
-__global__ void tiled_expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows,
-                                         int32_t* __restrict__ own) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < rows; r += nwarps)
-    for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) own[p] = (int32_t)r;
-}
-
 __global__ void tiled_keys_kernel(const int32_t* __restrict__ own, const int32_t* __restrict__ other,
                                   int64_t n, int tile_rows, int jbits, int ibits,
                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
@@ -147,7 +137,7 @@ static int build_tiled_side(amf_ratings* h, int side, int tile_rows, cudaStream_
   TILED_CUDA(cudaMalloc(&keys_out, 8 * (size_t)nnz));
   TILED_CUDA(cudaMalloc(&vals, 4 * (size_t)nnz));
   TILED_CUDA(cudaMalloc(&perm, 4 * (size_t)nnz));
-  tiled_expand_rows_kernel<<<grid, 256, 0, s>>>(h->ptr[side], own_rows, own);
+  expand_rows_kernel<int32_t><<<grid, 256, 0, s>>>(h->ptr[side], own_rows, own);
   TILED_CUDA(cudaGetLastError());
   tiled_keys_kernel<<<grid, 256, 0, s>>>(own, h->idx[side], nnz, tile_rows, jbits, ibits, keys, vals);
   TILED_CUDA(cudaGetLastError());

@@ -16,6 +16,8 @@
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tile_stream.cuh"
 
@@ -285,68 +287,73 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
       // entries of this chunk that are real (the last chunk of a tile is padded)
       const int64_t left = t_count - (chunk - t_first) * TILED_CHUNK;
       const int nvalid = left >= TILED_CHUNK ? TILED_CHUNK : (int)left;
-      const bool check = nvalid < TILED_CHUNK;        // warp-uniform
-      const uint4* wp = reinterpret_cast<const uint4*>(cw + cb) + g;
-      const T* rp = rv + cb + g * 4;
-      // index words and ratings two batches ahead (HBM latency)
-      uint4 w1 = __ldcs(wp), w2 = __ldcs(wp + 8);
-      T r1[4], r2[4];
-      ld4(rp, r1);
-      ld4(rp + 32, r2);
-      V a[CPL], acc[CPL];
-#pragma unroll
-      for (int t = 0; t < CPL; ++t) { a[t] = vzero(V()); acc[t] = vzero(V()); }
-      uint32_t prev_i = NONE;
-      double chunk_sq = 0;
-#pragma unroll 1
-      for (int r = 0; r < TILED_RUN; ++r) {
-        T sq = 0;
-        const uint32_t w[4] = {w1.x, w1.y, w1.z, w1.w};
-        const T rs[4] = {r1[0], r1[1], r1[2], r1[3]};
-        w1 = w2;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) r1[q] = r2[q];
-        if (r + 2 < TILED_RUN) {
-          w2 = __ldcs(wp + (r + 2) * 8);
-          ld4(rp + (r + 2) * 32, r2);
-        }
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          // sorted offset of this entry inside the chunk: group run, batch, slot
-          const bool valid = !check || (g * (4 * TILED_RUN) + r * 4 + s < nvalid);
-          const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
-          V b[CPL];
-#pragma unroll
-          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ slice_xor<CPL, ADJ>(t), V());
-          const uint32_t i = w[s] >> jbits;
-          if (i != prev_i) {                          // next row of this lane group's run
-            if (GRAD && prev_i != NONE && have) {
-              const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
-#pragma unroll
-              for (int t = 0; t < CPL; ++t)
-                red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
-            }
-            prev_i = i;
-            load_row_slices<V, CPL, ADJ>(own_base + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, a);
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) acc[t] = vzero(V());
+      // the bounds check of padded chunks (the last chunk of a tile) is compiled out of the
+      // path every other chunk takes
+      auto process = [&](auto check_tag) {
+        constexpr bool CHECK = decltype(check_tag)::value;
+        const uint4* wp = reinterpret_cast<const uint4*>(cw + cb) + g;
+        const T* rp = rv + cb + g * 4;
+        // index words and ratings two batches ahead (HBM latency)
+        uint4 w1 = __ldcs(wp), w2 = __ldcs(wp + 8);
+        T r1[4], r2[4];
+        ld4(rp, r1);
+        ld4(rp + 32, r2);
+        V a[CPL], acc[CPL];
+  #pragma unroll
+        for (int t = 0; t < CPL; ++t) { a[t] = vzero(V()); acc[t] = vzero(V()); }
+        uint32_t prev_i = NONE;
+        double chunk_sq = 0;
+  #pragma unroll 1
+        for (int r = 0; r < TILED_RUN; ++r) {
+          T sq = 0;
+          const uint32_t w[4] = {w1.x, w1.y, w1.z, w1.w};
+          const T rs[4] = {r1[0], r1[1], r1[2], r1[3]};
+          w1 = w2;
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) r1[q] = r2[q];
+          if (r + 2 < TILED_RUN) {
+            w2 = __ldcs(wp + (r + 2) * 8);
+            ld4(rp + (r + 2) * 32, r2);
           }
-          T dot = have ? dot_slices<CPL>(a, b) : T(0);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-          T e = (rs[s] - mean_offset) - dot;
-          if (check) e = valid ? e : T(0);
-          sq = fma(e, e, sq);
-          if (GRAD) axpy_slices<CPL>(acc, e * inv_sigma, b);
+  #pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            // sorted offset of this entry inside the chunk: group run, batch, slot
+            const bool valid = !CHECK || (g * (4 * TILED_RUN) + r * 4 + s < nvalid);
+            const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
+            V b[CPL];
+  #pragma unroll
+            for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ slice_xor<CPL, ADJ>(t), V());
+            const uint32_t i = w[s] >> jbits;
+            if (i != prev_i) {                          // next row of this lane group's run
+              if (GRAD && prev_i != NONE && have) {
+                const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
+  #pragma unroll
+                for (int t = 0; t < CPL; ++t)
+                  red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
+              }
+              prev_i = i;
+              load_row_slices<V, CPL, ADJ>(own_base + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, a);
+  #pragma unroll
+              for (int t = 0; t < CPL; ++t) acc[t] = vzero(V());
+            }
+            T dot = have ? dot_slices<CPL>(a, b) : T(0);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            T e = (rs[s] - mean_offset) - dot;
+            if (CHECK) e = valid ? e : T(0);
+            sq = fma(e, e, sq);
+            if (GRAD) axpy_slices<CPL>(acc, e * inv_sigma, b);
+          }
+          chunk_sq += (double)sq;
         }
-        chunk_sq += (double)sq;
-      }
-      if (GRAD && prev_i != NONE && have) {
-        const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
-#pragma unroll
-        for (int t = 0; t < CPL; ++t) red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
-      }
-      if (l == 0) local_sq += chunk_sq;
+        if (GRAD && prev_i != NONE && have) {
+          const uint64_t dp = down0 + (uint64_t)prev_i * ROW_BYTES;
+  #pragma unroll
+          for (int t = 0; t < CPL; ++t) red_add(reinterpret_cast<T*>(dp ^ (uint64_t)slice_xor<CPL, ADJ>(t)), acc[t]);
+        }
+        if (l == 0) local_sq += chunk_sq;
+      };
+      if (nvalid < TILED_CHUNK) process(std::true_type{}); else process(std::false_type{});
     }
     c = seg_end;
   }

@@ -74,6 +74,9 @@ PROTOTYPES = {
     "amf_normal_workspace_doubles": [_I32, _I32, _INT],
     "amf_normal_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
                            _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],
+    "amf_pmf_fit_workspace_bytes": [_P, _INT, _INT],
+    "amf_pmf_fit_lls": [_P, _INT, _INT, _INT, _P, _P, C.POINTER(PmfParams), _F64, _F64, _F64, _INT, _P,
+                        _INT, _P, _P, _I64, _P],
     "amf_ratings_set_layout": [_P, _INT],
     "amf_ratings_append": [_P, _I64, _P, _P, _P, _P],
     "amf_ratings_compact": [_P, _P],
@@ -116,6 +119,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.argtypes = argtypes
         fn.restype = _I64 if name in ("amf_ratings_nnz", "amf_normal_workspace_doubles", "amf_pool_size",
+                                    "amf_pmf_fit_workspace_bytes",
                                    "amf_mn_workspace_doubles") else _INT
     _lib = lib
     return lib

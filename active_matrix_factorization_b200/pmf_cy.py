@@ -15,6 +15,8 @@ import random
 import warnings
 from copy import deepcopy
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -460,9 +462,36 @@ class ProbabilisticMatrixFactorization(object):
                         break
         self._pull()
 
+    # problems up to this size run the whole line search in one launch (csrc/fit.cu)
+    _DEVICE_FIT_MAX_NNZ = 200_000
+    _DEVICE_FIT_MAX_TABLE = 2_000_000
+
     def fit(self):
-        for _ll in self.fit_lls():
-            pass
+        """(pmf_cy.pyx:293-295) run fit_lls to convergence.  Small problems (the reference's own
+        sizes) do the entire line search on the device in one launch -- same control flow, no
+        host round trip per trial (amf_pmf_fit_lls); larger ones drive the fused pass per trial."""
+        name = self.dtype_name
+        ld = D.padded_ld(self.latent_d, name)
+        if (self._num_ratings() > self._DEVICE_FIT_MAX_NNZ or
+                (self.num_users + self.num_items) * ld > self._DEVICE_FIT_MAX_TABLE):
+            for _ll in self.fit_lls():
+                pass
+            return
+        lib = N.require_device()
+        rat = self._rating_handle()
+        self._check_factors(self._users, self._items)
+        U, V = D.to_padded(self._users, name), D.to_padded(self._items, name)
+        nbytes = int(lib.amf_pmf_fit_workspace_bytes(rat.handle, D.code(name), ld))
+        work = torch.empty(nbytes, dtype=torch.uint8, device=U.device)
+        result = torch.zeros(4, dtype=torch.float64, device=U.device)       # amf_fit_result_t
+        params = self._params()
+        N.check(lib.amf_pmf_fit_lls(rat.handle, D.code(name), self.latent_d, ld, D.ptr(U), D.ptr(V),
+                                    C.byref(params), float(self.learning_rate),
+                                    float(self.min_learning_rate), float(self.stop_thresh), 0,
+                                    None, 0, D.ptr(result), D.ptr(work), nbytes, D.stream_ptr()))
+        self._dev.pop('host_set', None)
+        self._dev['U'], self._dev['V'], self._dev['host_stale'] = U, V, True
+        self._pull()
 
     def do_fit(self):
         kind, *args = self.fit_type

@@ -104,6 +104,22 @@ int amf_pmf_loss_grad(const amf_ratings_t* h, int dtype, int d, int ld, const vo
                       const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
                       double* sums_d, void* stream);
 
+/* The whole line-search fit (pmf_cy.pyx:257-305 fit_lls consumed by fit) in ONE launch, for small
+ * problems: one cooperative launch (CTAs meet at a grid barrier three times per trial) runs
+ * trial point, fused objective + gradient, accept / reject, step-size update (x1.25 / x0.5 in
+ * fp64) and the convergence tests (gain < stop_thresh, lr < min_lr) with the reference's control
+ * flow; U_d / V_d (rows x ld, padding zero) are updated in place.
+ * trace_d[0 .. min(steps, trace_cap)) receives the objective of every accepted step.  max_steps
+ * <= 0: no cap.  Uses scalar gathers and atomics: meant for lists up to a few 1e5 ratings, where a
+ * trial is launch-bound; larger lists should drive amf_pmf_loss_grad + amf_axpy from the host.
+ * workspace_d: 256-byte aligned.  Merges an appended tail first. */
+typedef struct { double lr; double ll; int32_t steps; int32_t trials; int32_t converged; int32_t pad_; } amf_fit_result_t;
+int64_t amf_pmf_fit_workspace_bytes(const amf_ratings_t* h, int dtype, int ld);
+int amf_pmf_fit_lls(const amf_ratings_t* h, int dtype, int d, int ld, void* U_d, void* V_d,
+                    const amf_pmf_params_t* p, double lr, double min_lr, double stop_thresh,
+                    int max_steps, double* trace_d, int trace_cap, amf_fit_result_t* result_d,
+                    void* workspace_d, int64_t workspace_bytes, void* stream);
+
 /* Line-search trial point of fit_lls (pmf_cy.pyx:271-272): X_new = X + lr * G, elementwise
  * over `count` elements (the padded (rows, ld) block). */
 int amf_axpy(int dtype, int64_t count, const void* X_d, const void* G_d, double lr,

@@ -204,3 +204,53 @@ def test_from_coo_matches_tuple_constructor(amf):
     assert len(la) == len(lb)
     np.testing.assert_allclose(lb, la, rtol=1e-9)
     np.testing.assert_allclose(b.users, a2.users, rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("sm", [False, True])
+def test_device_fit_matches_reference_trajectory(amf, golden, sm):
+    """amf_pmf_fit_lls: the whole line search in one launch takes the reference's accepted steps
+    (same count, objectives to 1e-9) and ends at the reference's factors; fit() uses it"""
+    import ctypes as C
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D
+    g = golden("fit_30x40_d4")
+    tag = "_sm" if sm else ""
+    p = make_model(amf, g["ratings"], g["users0"], g["items0"], 4, "f64", sm)
+    lib = N.require_device()
+    rat = p._rating_handle()
+    ld = D.padded_ld(4, "f64")
+    U, V = D.to_padded(g["users0"], "f64"), D.to_padded(g["items0"], "f64")
+    nbytes = int(lib.amf_pmf_fit_workspace_bytes(rat.handle, N.F64, ld))
+    work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    trace = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    res = torch.zeros(4, dtype=torch.float64, device="cuda")
+    params = p._params()
+    N.check(lib.amf_pmf_fit_lls(rat.handle, N.F64, 4, ld, D.ptr(U), D.ptr(V), C.byref(params),
+                                p.learning_rate, p.min_learning_rate, p.stop_thresh, 0, D.ptr(trace),
+                                4096, D.ptr(res), D.ptr(work), nbytes, D.stream_ptr()))
+    steps = int(res[2:3].view(torch.int32)[0].item())
+    ref = g["lls" + tag]
+    assert steps == len(ref)
+    np.testing.assert_allclose(trace[:steps].cpu().numpy(), ref, rtol=1e-9)
+    np.testing.assert_allclose(D.from_padded(U, 4), g["users_fit" + tag], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(D.from_padded(V, 4), g["items_fit" + tag], rtol=1e-6, atol=1e-8)
+    assert res[1].item() == pytest.approx(ref[-1], rel=1e-9)
+    # the class method takes the same path
+    p.fit()
+    np.testing.assert_allclose(p.users, g["users_fit" + tag], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(p.items, g["items_fit" + tag], rtol=1e-6, atol=1e-8)
+    # a step cap stops early with the same prefix
+    U2, V2 = D.to_padded(g["users0"], "f64"), D.to_padded(g["items0"], "f64")
+    N.check(lib.amf_pmf_fit_lls(rat.handle, N.F64, 4, ld, D.ptr(U2), D.ptr(V2), C.byref(params),
+                                p.learning_rate, p.min_learning_rate, p.stop_thresh, 5, D.ptr(trace),
+                                4096, D.ptr(res), D.ptr(work), nbytes, D.stream_ptr()))
+    assert int(res[2:3].view(torch.int32)[0].item()) == 5
+    np.testing.assert_allclose(trace[:5].cpu().numpy(), ref[:5], rtol=1e-9)
+
+
+def test_device_fit_fast_mode(amf, golden):
+    """f32: the one-launch fit ends within stop_thresh of the fp64 reference objective"""
+    g = golden("fit_30x40_d4")
+    p = make_model(amf, g["ratings"], g["users0"], g["items0"], 4, "f32")
+    p.fit()
+    assert p.log_likelihood() == pytest.approx(float(g["lls"][-1]), rel=1e-4, abs=2e-2)

@@ -103,6 +103,9 @@ def test_lookahead_criteria_golden(A, golden):
                      (A.ActivePMF.exp_approx_entropy_byapprox, "uv_entropy_approx"),
                      (A.ActivePMF.exp_total_variance, "total_variance")):
         vals = np.array(a._get_key_vals(pool, key, None, None))
+        # the re-fit amplifies rounding (a 1e-16 perturbation of the reference's own state moves
+        # these criteria by up to 7e-5, benchmarks/ref_sensitivity.py); short rating lists are
+        # accumulated in list order by one warp, so the result is reproducible: worst 9.1e-6
         np.testing.assert_allclose(vals, g[ref], rtol=1e-5, err_msg=ref)
         got = a.pick_query_point(pool, key)
         want = pool[int(np.argmin(g[ref]))]

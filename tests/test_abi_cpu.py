@@ -142,3 +142,33 @@ def test_error_conventions_of_the_active_classes():
     assert b.beta == 2 and b.subtract_mean and b.u_hyperparams[2] == 3
     st = b.__getstate__()
     assert {'discrete_expectations', 'rating_values', 'beta', 'u_hyperparams', 'v_hyperparams'} <= set(st)
+
+
+def test_pool_arrays_conversion():
+    """host logic: a list of (i, j) pairs becomes two int32 arrays in iteration order whatever
+    the pair type (tuples, numpy integers, lists of floats holding integers)"""
+    from active_matrix_factorization_b200 import active_pmf as A
+    ii, jj = A._pool_arrays([(1, 2), (3, 4), (0, 9)])
+    assert ii.dtype == np.int32 and ii.tolist() == [1, 3, 0] and jj.tolist() == [2, 4, 9]
+    ii, jj = A._pool_arrays([(np.int64(5), np.int32(6))])
+    assert (ii.tolist(), jj.tolist()) == ([5], [6])
+    ii, jj = A._pool_arrays([[7.0, 8.0], [1.0, 0.0]])
+    assert (ii.tolist(), jj.tolist()) == ([7, 1], [8, 0])
+    s = {(2, 3), (4, 5), (6, 7)}
+    ii, jj = A._pool_arrays(list(s))
+    assert list(zip(ii.tolist(), jj.tolist())) == list(s)
+
+
+def test_ratings_append_bookkeeping_without_device():
+    """host logic of add_ratings: duplicate cells and bad values are rejected before any device
+    work, rated / unrated sets and the mean follow the reference (pmf_cy.pyx:128-156)"""
+    from active_matrix_factorization_b200 import pmf_cy as P
+    R = np.array([[0, 0, 1.], [1, 2, 3.], [2, 1, 5.]])
+    p = P.ProbabilisticMatrixFactorization(R, 2)
+    with pytest.raises(ValueError, match="already rated"):
+        p.add_rating(1, 2, 4.)
+    with pytest.raises(TypeError):
+        p.add_ratings([[0, 1]])
+    p.add_ratings([[0, 1, 2.], [2, 2, 4.]])        # no device handle exists yet: host arrays only
+    assert p.ratings.shape == (5, 3) and (0, 1) in p.rated and (0, 1) not in p.unrated
+    assert p.mean_rating == pytest.approx(3.0)

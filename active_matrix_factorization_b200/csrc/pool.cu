@@ -6,7 +6,7 @@
 // sorted by (j / TJ, i, j), so a CTA keeps a TJ-row tile of V in shared memory (TMA bulk
 // copies) and reads every item row from there; the user row lives in registers and is fetched
 // from L2 only when the user changes (about once per TJ * density candidates).  Each candidate
-// costs 4 bytes of HBM: one packed word  i << log2(TJ) | (j % TJ).
+// costs 4 bytes of HBM: one packed word  i << ceil(log2(TJ)) | (j % TJ).
 //
 // Memory order inside a tile.  The sorted list of a tile is cut into chunks of POOL_CHUNK
 // candidates; a warp scores one chunk at a time in POOL_RUN batches of 32.  A group of four
@@ -20,7 +20,6 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
-#include <vector>
 
 #include "common.cuh"
 #include "tile_stream.cuh"

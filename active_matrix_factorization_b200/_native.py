@@ -58,6 +58,8 @@ PROTOTYPES = {
     "amf_ratings_layout": [_P, _INT, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)],
     "amf_ratings_mean": [_P, C.POINTER(_F64), _P],
     "amf_pmf_loss_grad": [_P, _INT, _INT, _INT, _P, _P, C.POINTER(PmfParams), _P, _P, _P, _P],
+    "amf_pmf_loss_grad_part": [_P, _INT, _INT, _INT, _P, _P, C.POINTER(PmfParams), _P, _P, _P, _INT,
+                               _INT, _P],
     "amf_axpy": [_INT, _I64, _P, _P, _F64, _P, _P],
     "amf_pmf_grad_coo": [_INT, _I64, _P, _P, _P, _INT, _INT, _P, _P, C.POINTER(PmfParams),
                          _P, _P, _P, _P],

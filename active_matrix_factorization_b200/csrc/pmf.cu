@@ -27,7 +27,7 @@ int tiled_prepare(amf_ratings* h, size_t row_bytes, const void* U, const void* V
 template <typename T>
 int tiled_loss_grad(const amf_ratings* h, int ld, const T* U, const T* V, T inv_sigma,
                     T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s,
-                    cudaEvent_t dU_done);
+                    cudaEvent_t dU_done, int sides, int max_ctas);
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -357,46 +357,52 @@ static int tail_terms(const amf_ratings* h, int d, int ld, const T* U, const T* 
 }
 
 // dU_done (optional): recorded on s as soon as dU holds its final value (before the pass that
-// produces dV), so a host-buffer caller can start copying dU back while dV is computed
+// produces dV), so a host-buffer caller can start copying dU back while dV is computed.
+// parts: bit 0 = prior terms of both sides + the pass that completes dU and the squared error
+// (+ the appended tail), bit 1 = the pass that completes dV; a caller that runs them as two
+// calls can put a collective on dU in between.  max_ctas > 0 caps the grid of the tiled passes.
 template <typename T>
 static int loss_grad(const amf_ratings* h, int d, int ld, const T* U, const T* V,
                      const amf_pmf_params_t* p, T* dU, T* dV, double* sums, cudaStream_t s,
-                     cudaEvent_t dU_done = nullptr) {
+                     cudaEvent_t dU_done = nullptr, int parts = 3, int max_ctas = 0) {
   constexpr int N = Vec<T>::N;
   AMF_REQUIRE(ld >= d && ld % N == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, N);
   AMF_REQUIRE((dU == nullptr) == (dV == nullptr), "dU and dV must both be given or both NULL");
-  AMF_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
-  const int64_t cu = (int64_t)h->n_users * ld, cv = (int64_t)h->n_items * ld;
-  const int gu = grid_for((cu / N + 255) / 256, 8), gv = grid_for((cv / N + 255) / 256, 8);
-  prior_kernel<T><<<gu, 256, 0, s>>>(U, cu, (T)(-1.0 / p->sigma_u_sq), dU, sums + 1);
-  AMF_LAUNCH_CHECK();
-  prior_kernel<T><<<gv, 256, 0, s>>>(V, cv, (T)(-1.0 / p->sigma_v_sq), dV, sums + 2);
-  AMF_LAUNCH_CHECK();
+  AMF_REQUIRE(parts >= 1 && parts <= 3, "parts must be 1, 2 or 3");
+  if (parts & 1) {
+    AMF_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+    const int64_t cu = (int64_t)h->n_users * ld, cv = (int64_t)h->n_items * ld;
+    const int gu = grid_for((cu / N + 255) / 256, 8), gv = grid_for((cv / N + 255) / 256, 8);
+    prior_kernel<T><<<gu, 256, 0, s>>>(U, cu, (T)(-1.0 / p->sigma_u_sq), dU, sums + 1);
+    AMF_LAUNCH_CHECK();
+    prior_kernel<T><<<gv, 256, 0, s>>>(V, cv, (T)(-1.0 / p->sigma_v_sq), dV, sums + 2);
+    AMF_LAUNCH_CHECK();
+  }
   // the appended tail (if any) touches dU last: then dU is final only at the very end
   cudaEvent_t early = h->tail_n > 0 ? nullptr : dU_done;
-  if (h->nnz == 0) {
-    int rc0 = tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
-    if (rc0 == AMF_OK && dU_done) AMF_CUDA(cudaEventRecord(dU_done, s));
-    return rc0;
-  }
-  const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
-  int rc;
-  bool tiled = false;
-  rc = tiled_prepare(const_cast<amf_ratings*>(h), (size_t)ld * sizeof(T), U, V, dU, dV, &tiled, s);
-  if (rc != AMF_OK) return rc;
-  if (tiled) {
-    rc = tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s, early);
-  } else if (dU) {
-    rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
+  int rc = AMF_OK;
+  if (h->nnz > 0) {
+    const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
+    bool tiled = false;
+    rc = tiled_prepare(const_cast<amf_ratings*>(h), (size_t)ld * sizeof(T), U, V, dU, dV, &tiled, s);
     if (rc != AMF_OK) return rc;
-    if (early) AMF_CUDA(cudaEventRecord(early, s));
-    rc = launch_side<T, true>(h, 1, V, U, ld, inv_sigma, mo, dV, nullptr, s);
-  } else {
-    rc = launch_side<T, false>(h, 0, U, V, ld, inv_sigma, mo, nullptr, sums, s);
+    if (tiled) {
+      rc = tiled_loss_grad<T>(h, ld, U, V, inv_sigma, mo, dU, dV, sums, s, early, parts, max_ctas);
+    } else if (dU) {
+      if (parts & 1) {
+        rc = launch_side<T, true>(h, 0, U, V, ld, inv_sigma, mo, dU, sums, s);
+        if (rc != AMF_OK) return rc;
+        if (early) AMF_CUDA(cudaEventRecord(early, s));
+      }
+      if (parts & 2) rc = launch_side<T, true>(h, 1, V, U, ld, inv_sigma, mo, dV, nullptr, s);
+    } else if (parts & 1) {
+      rc = launch_side<T, false>(h, 0, U, V, ld, inv_sigma, mo, nullptr, sums, s);
+    }
+    if (rc != AMF_OK) return rc;
   }
-  if (rc != AMF_OK) return rc;
-  rc = tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
-  if (rc == AMF_OK && dU_done && (!early || !dU)) AMF_CUDA(cudaEventRecord(dU_done, s));
+  if (parts & 1) rc = tail_terms<T>(h, d, ld, U, V, p, dU, dV, sums, s);
+  if (rc == AMF_OK && dU_done && (parts & 1) && (!early || !dU || h->nnz == 0))
+    AMF_CUDA(cudaEventRecord(dU_done, s));
   return rc;
 }
 
@@ -467,6 +473,20 @@ int amf_pmf_loss_grad(const amf_ratings_t* h, int dtype, int d, int ld, const vo
                             (float*)dV_d, sums_d, s);
   return loss_grad<double>(h, d, ld, (const double*)U_d, (const double*)V_d, p, (double*)dU_d,
                            (double*)dV_d, sums_d, s);
+}
+
+int amf_pmf_loss_grad_part(const amf_ratings_t* h, int dtype, int d, int ld, const void* U_d,
+                           const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
+                           double* sums_d, int part, int max_ctas, void* stream) {
+  AMF_REQUIRE(h && U_d && V_d && p && sums_d && dU_d && dV_d, "amf_pmf_loss_grad_part: NULL argument");
+  AMF_REQUIRE(dtype == h->dtype, "amf_pmf_loss_grad_part: dtype does not match the rating list");
+  AMF_REQUIRE(part == 0 || part == 1, "amf_pmf_loss_grad_part: part must be 0 or 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == AMF_F32)
+    return loss_grad<float>(h, d, ld, (const float*)U_d, (const float*)V_d, p, (float*)dU_d,
+                            (float*)dV_d, sums_d, s, nullptr, 1 << part, max_ctas);
+  return loss_grad<double>(h, d, ld, (const double*)U_d, (const double*)V_d, p, (double*)dU_d,
+                           (double*)dV_d, sums_d, s, nullptr, 1 << part, max_ctas);
 }
 
 int amf_axpy(int dtype, int64_t count, const void* X_d, const void* G_d, double lr, void* Xnew_d,

@@ -373,11 +373,13 @@ static int tiled_tile_kb() {
 
 template <typename T, bool GRAD>
 static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, const T* Tile,
-                        T inv_sigma, T mean_offset, T* dOwn, double* sq_err, cudaStream_t s) {
+                        T inv_sigma, T mean_offset, T* dOwn, double* sq_err, cudaStream_t s,
+                        int max_ctas) {
   const amf_tiled_side* t = &h->tiled[side];
   const int tile_side_rows = side == 0 ? h->n_items : h->n_users;
   const size_t smem = (size_t)t->tile_rows * nvec * 16;
   int64_t grid64 = (int64_t)num_sms();
+  if (max_ctas > 0 && grid64 > max_ctas) grid64 = max_ctas;   // leave SMs to a concurrent collective
   if (grid64 > t->n_chunks) grid64 = t->n_chunks > 0 ? t->n_chunks : 1;
   const int grid = (int)grid64;
   // 64 registers per thread (fp32) keep 32 warps on the SM: the pass is bound by the latency of
@@ -451,24 +453,33 @@ void tiled_free(amf_ratings* h) {
   h->tiled_row_bytes = 0;
 }
 
+// sides: bit 0 = users past item tiles (dU, squared error), bit 1 = items past user tiles (dV)
 template <typename T>
 int tiled_loss_grad(const amf_ratings* h, int ld, const T* U, const T* V, T inv_sigma,
                     T mean_offset, T* dU, T* dV, double* sq_err, cudaStream_t s,
-                    cudaEvent_t dU_done) {
+                    cudaEvent_t dU_done, int sides, int max_ctas) {
   const int nvec = ld / Vec<T>::N;
-  int rc;
+  int rc = AMF_OK;
   if (dU) {
-    rc = launch_tiled<T, true>(h, 0, nvec, U, V, inv_sigma, mean_offset, dU, sq_err, s);
-    if (rc != AMF_OK) return rc;
-    if (dU_done) AMF_CUDA(cudaEventRecord(dU_done, s));   // dU is final: the caller may read it
-    return launch_tiled<T, true>(h, 1, nvec, V, U, inv_sigma, mean_offset, dV, nullptr, s);
+    if (sides & 1) {
+      rc = launch_tiled<T, true>(h, 0, nvec, U, V, inv_sigma, mean_offset, dU, sq_err, s, max_ctas);
+      if (rc != AMF_OK) return rc;
+      if (dU_done) AMF_CUDA(cudaEventRecord(dU_done, s));   // dU is final: the caller may read it
+    }
+    if (sides & 2)
+      rc = launch_tiled<T, true>(h, 1, nvec, V, U, inv_sigma, mean_offset, dV, nullptr, s, max_ctas);
+    return rc;
   }
-  return launch_tiled<T, false>(h, 0, nvec, U, V, inv_sigma, mean_offset, nullptr, sq_err, s);
+  if (sides & 1)
+    rc = launch_tiled<T, false>(h, 0, nvec, U, V, inv_sigma, mean_offset, nullptr, sq_err, s, max_ctas);
+  return rc;
 }
 template int tiled_loss_grad<float>(const amf_ratings*, int, const float*, const float*, float,
-                                    float, float*, float*, double*, cudaStream_t, cudaEvent_t);
+                                    float, float*, float*, double*, cudaStream_t, cudaEvent_t, int,
+                                    int);
 template int tiled_loss_grad<double>(const amf_ratings*, int, const double*, const double*, double,
-                                     double, double*, double*, double*, cudaStream_t, cudaEvent_t);
+                                     double, double*, double*, double*, cudaStream_t, cudaEvent_t,
+                                     int, int);
 
 }  // namespace amf
 

@@ -169,6 +169,14 @@ def loss_grad(rat, d, U, V, params, dU=None, dV=None, sums=None):
     return sums
 
 
+def loss_grad_part(rat, d, U, V, params, dU, dV, sums, part, max_ctas=0):
+    """One half of the fused loss+gradient (amf_pmf_loss_grad_part): part 0 completes dU and the
+    sums, part 1 completes dV."""
+    N.check(N.require_device().amf_pmf_loss_grad_part(
+        rat.handle, code(rat.name), d, U.shape[1], ptr(U), ptr(V), C.byref(params), ptr(dU), ptr(dV),
+        ptr(sums), int(part), int(max_ctas), stream_ptr()))
+
+
 def axpy(X, G, lr, out, name):
     N.check(N.require_device().amf_axpy(code(name), X.numel(), ptr(X), ptr(G), float(lr), ptr(out),
                                         stream_ptr()))

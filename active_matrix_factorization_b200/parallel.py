@@ -176,10 +176,35 @@ class ShardedStep:
         dist.all_gather_into_tensor(allc, cnt)
         self.index_base = int(allc[:self.rank].sum().item())
 
-    def loss_grad(self, U, V, params, dU, dV, sums, grads_flat=None):
+    # SMs left to NCCL while the second gradient pass runs (its CTAs otherwise fill every SM)
+    SMS_FOR_COLLECTIVE = 8
+
+    def loss_grad(self, U, V, params, dU, dV, sums, grads_flat=None, overlap=False):
+        """Fused loss+gradient over this rank's rating block, all-reduced.  overlap=True runs
+        the pass that completes dU first, starts its all-reduce (and that of the sums)
+        asynchronously and lets it travel while the second pass computes dV on all but a few
+        SMs; measured on 2 and 8 B200s it does not pay (0.764 vs 0.780 ms and 1.412 vs 1.386 ms,
+        benchmarks/check_sharded_grad.py), so one all-reduce after both passes is the default."""
         from . import device as D
-        D.loss_grad(self.rat, self.d, U, V, prior_once_params(params, self.rank), dU, dV, sums)
-        combine_loss_grad(dU, dV, sums, self.world, self.rank, grads_flat=grads_flat)
+        prm = prior_once_params(params, self.rank)
+        if self.world == 1:
+            D.loss_grad(self.rat, self.d, U, V, prm, dU, dV, sums)
+            return
+        if not overlap:
+            D.loss_grad(self.rat, self.d, U, V, prm, dU, dV, sums)
+            combine_loss_grad(dU, dV, sums, self.world, self.rank, grads_flat=grads_flat)
+            return
+        n_sms = torch.cuda.get_device_properties(U.device).multi_processor_count
+        D.loss_grad_part(self.rat, self.d, U, V, prm, dU, dV, sums, 0)
+        if self.rank != 0:
+            sums[1:].zero_()
+        w_u = dist.all_reduce(dU, async_op=True)
+        w_s = dist.all_reduce(sums, async_op=True)
+        D.loss_grad_part(self.rat, self.d, U, V, prm, dU, dV, sums, 1,
+                         max_ctas=max(1, n_sms - self.SMS_FOR_COLLECTIVE))
+        dist.all_reduce(dV)
+        w_u.wait()
+        w_s.wait()
 
     def select(self, criterion, ci, cj, U, V, view, cutoff, maximize, best):
         from . import device as D

@@ -104,6 +104,15 @@ int amf_pmf_loss_grad(const amf_ratings_t* h, int dtype, int d, int ld, const vo
                       const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
                       double* sums_d, void* stream);
 
+/* amf_pmf_loss_grad in two calls, for a caller that puts a collective between them (multi-GPU:
+ * all-reduce dU while dV is still being computed).  part 0: prior terms of both sides, the pass
+ * that completes dU_d and sums_d (and the appended tail, which adds to both gradients); part 1:
+ * the pass that completes dV_d.  Both parts must be run, in this order, with the same arguments.
+ * max_ctas > 0 caps the grid of the tiled passes (leaves SMs to the concurrent collective). */
+int amf_pmf_loss_grad_part(const amf_ratings_t* h, int dtype, int d, int ld, const void* U_d,
+                           const void* V_d, const amf_pmf_params_t* p, void* dU_d, void* dV_d,
+                           double* sums_d, int part, int max_ctas, void* stream);
+
 /* The whole line-search fit (pmf_cy.pyx:257-305 fit_lls consumed by fit) in ONE launch, for small
  * problems: one cooperative launch (CTAs meet at a grid barrier three times per trial) runs
  * trial point, fused objective + gradient, accept / reject, step-size update (x1.25 / x0.5 in

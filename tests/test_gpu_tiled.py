@@ -129,3 +129,32 @@ def test_tiled_auto_threshold_and_model_api(env):
     assert out["auto"][0] == pytest.approx(out["rows"][0], rel=1e-5)
     for a, b in zip(out["auto"][1], out["rows"][1]):
         assert rel_err(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("layout", ["rows", "tiled"])
+def test_two_part_pass_equals_one_call(env, layout):
+    """amf_pmf_loss_grad_part: part 0 (priors, dU, sums) then part 1 (dV), with a capped grid,
+    gives what the single call gives"""
+    N, D, torch = env
+    lib = N.require_device()
+    rng = np.random.RandomState(21)
+    n, m, d, nnz = 3000, 2500, 32, 150000
+    cells = rng.permutation(n * m)[:nnz]
+    ii, jj, r = (cells // m).astype(np.int32), (cells % m).astype(np.int32), rng.normal(3, 1, nnz)
+    rat = D.Ratings(n, m, ii, jj, r, "f32")
+    rat.set_layout(layout)
+    U = D.to_padded(rng.normal(0, .5, (n, d)), "f32")
+    V = D.to_padded(rng.normal(0, .5, (m, d)), "f32")
+    params = D.pmf_params(.8, 7., 12., .25)
+    dU, dV = torch.empty_like(U), torch.empty_like(V)
+    sums = D.loss_grad(rat, d, U, V, params, dU, dV)
+    gU, gV = torch.full_like(U, 9.), torch.full_like(V, 9.)
+    s2 = torch.full((3,), 5., dtype=torch.float64, device="cuda")
+    D.loss_grad_part(rat, d, U, V, params, gU, gV, s2, 0)
+    # after part 0: dU and the sums are final, dV holds the prior term only
+    assert rel_err(gU.cpu().numpy(), dU.cpu().numpy()) < 2e-6
+    assert torch.allclose(s2, sums, rtol=1e-9)
+    assert rel_err(gV.cpu().numpy(), (-V / 12.).cpu().numpy()) < 1e-6
+    D.loss_grad_part(rat, d, U, V, params, gU, gV, s2, 1, max_ctas=5)
+    assert rel_err(gV.cpu().numpy(), dV.cpu().numpy()) < 2e-6
+    assert rel_err(gU.cpu().numpy(), dU.cpu().numpy()) < 2e-6

@@ -597,7 +597,8 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         evals = np.empty((self.num_users, self.num_items))
         evals.fill(np.nan)
         if pool:
-            evals[tuple(zip(*pool))] = self._get_key_vals(pool, key, procs, worker_pool)
+            ii, jj = _pool_arrays(pool)
+            evals[ii, jj] = self._get_key_vals(pool, key, procs, worker_pool)
         return evals
 
 

@@ -23,7 +23,7 @@
 
 namespace amf {
 
-constexpr int TILED_RUN = 32;                    // batches of 32 entries per chunk
+constexpr int TILED_RUN = 16;                    // batches of 32 entries per chunk
 constexpr int TILED_CHUNK = 32 * TILED_RUN;      // entries per chunk (one warp, one grab)
 constexpr int64_t TILED_AUTO_MIN_NNZ = 1ll << 20;
 

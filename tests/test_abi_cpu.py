@@ -172,3 +172,25 @@ def test_ratings_append_bookkeeping_without_device():
     p.add_ratings([[0, 1, 2.], [2, 2, 4.]])        # no device handle exists yet: host arrays only
     assert p.ratings.shape == (5, 3) and (0, 1) in p.rated and (0, 1) not in p.unrated
     assert p.mean_rating == pytest.approx(3.0)
+
+
+def test_shims_resolve_to_the_mirror():
+    """drop-in boundary: with shims/ first on sys.path the reference's own import
+    lines (`from pmf_cy import ...`, `import active_pmf`, ...) get the GPU-backed classes"""
+    import importlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from pmf_cy import ProbabilisticMatrixFactorization, rmse, parse_fit_type\n"
+        "import active_pmf, bayes_pmf, mn_active_pmf, normal_exps_cy, matrix_normal_exps_cy\n"
+        "import active_matrix_factorization_b200.pmf_cy as M\n"
+        "assert ProbabilisticMatrixFactorization is M.ProbabilisticMatrixFactorization\n"
+        "assert active_pmf.ActivePMF.__module__.startswith('active_matrix_factorization_b200')\n"
+        "assert len(active_pmf.KEY_FUNCS) == 15 and hasattr(bayes_pmf, 'BayesianPMF')\n"
+        "assert hasattr(mn_active_pmf, 'MNActivePMF') and hasattr(normal_exps_cy, 'exp_dotprod_sq')\n"
+        "print('ok')\n" % (root, os.path.join(root, "shims")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

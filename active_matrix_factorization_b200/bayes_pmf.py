@@ -33,8 +33,10 @@ from .pmf_cy import ProbabilisticMatrixFactorization, rmse, parse_fit_type  # no
 def sample_wishart(sigma, dof):
     '''
     Draw from Wishart(sigma, dof) (bayes_pmf.py:41-59): d x d host algebra on draws from the
-    global numpy stream (direct scheme if dof <= 81+n and integral, else Bartlett).
+    global numpy stream (direct scheme if dof <= 81+n and integral, else Bartlett).  `dof` is a
+    C int in the compiled reference (bayes_pmf.pxd:7), so a fractional value is truncated.
     '''
+    dof = int(dof)
     n = sigma.shape[0]
     chol = np.linalg.cholesky(sigma)
     if dof <= 81 + n and dof == round(dof):
@@ -223,7 +225,7 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         '''(bayes_pmf.py:306-424) the row fan-out is the GPU launch; `pool` is not needed.'''
         if multiproc_mode == 'force' and pool is None:
             raise ValueError("need a process pool if multiproc is forced")
-        return self.samples(num_gibbs=num_gibbs, fit_first=fit_first)
+        yield from self.samples(num_gibbs=num_gibbs, fit_first=fit_first)
 
     ############################################################################
     ### Criteria over samples

@@ -443,7 +443,10 @@ class ProbabilisticMatrixFactorization(object):
                     yield new_ll
                     old_ll = new_ll
                     # the caller may have changed hyper-parameters, factors or ratings between
-                    # steps (fit_with_sigmas_lls does): resynchronise if so
+                    # steps (fit_with_sigmas_lls does).  The reference then takes its next
+                    # gradient from the new state but keeps comparing against the objective it
+                    # yielded (pmf_cy.pyx:265,284-285: old_ll is never re-evaluated), so only
+                    # the gradient is refreshed here
                     changed = dev.get('rat') is not rat
                     if dev.pop('host_set', False):
                         self._pull()
@@ -452,7 +455,6 @@ class ProbabilisticMatrixFactorization(object):
                     if changed or hyper != (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq):
                         rat = self._rating_handle()
                         D.loss_grad(rat, d, U, V, self._params(), gU, gV, sums)
-                        old_ll = ll_of(sums)
                     hyper = (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq)
                     break
                 else:
@@ -532,8 +534,9 @@ class ProbabilisticMatrixFactorization(object):
                 end = min(start + batch_size, num_ratings)
                 n = end - start
                 gu, gv = self._batch_gradient_device(None, U, V, (bi[start:end], bj[start:end], br[start:end]))
-                N.check(lib.amf_momentum_step(code, U.numel(), D.ptr(u_inc), D.ptr(gu), momentum, lr / n, D.ptr(U), st))
-                N.check(lib.amf_momentum_step(code, V.numel(), D.ptr(v_inc), D.ptr(gv), momentum, lr / n, D.ptr(V), st))
+                step = float(np.float32(lr) / np.float32(n))   # C float / C int in the reference
+                N.check(lib.amf_momentum_step(code, U.numel(), D.ptr(u_inc), D.ptr(gu), momentum, step, D.ptr(U), st))
+                N.check(lib.amf_momentum_step(code, V.numel(), D.ptr(v_inc), D.ptr(gv), momentum, step, D.ptr(V), st))
             dev['U'], dev['V'], dev['host_stale'] = U, V, True
             # training error over ALL of self.ratings (pmf_cy.pyx:347-349)
             sums = D.loss_grad(self._rating_handle(), self.latent_d, U, V, self._params())

@@ -245,8 +245,90 @@ def case_matrix_normal():
     save("matrix_normal", **out)
 
 
+# ---- case 7: sigma-learning and mini-batch fits, dense prediction / RMSE, Bayes extras ---
+def case_extras():
+    import random as pyrandom
+    n, m, d = 30, 40, 4
+    rng, R, users, items = random_problem(5, n, m, d, 300, scale=.8)
+    real = rng.normal(0, 1, (n, m))
+    mask = rng.uniform(size=(n, m)) < .3
+    out = dict(ratings=R, users0=users, items0=items, real=real, mask=mask)
+    # (a) fit_with_sigmas_lls (pmf_cy.pyx:384-403), plain and with the log-normal variance prior
+    for tag, sm, prior in (("", False, None), ("_sm", True, None), ("_prior", False, (0.5, 2.0, 1.0, 3.0))):
+        p = PMF(R, d, sm)
+        p.users, p.items = users.copy(), items.copy()
+        if prior:
+            p.sig_u_mean, p.sig_u_var, p.sig_v_mean, p.sig_v_var = prior
+            out["sig_prior"] = np.array(prior)
+        lls, sig = [], []
+        for ll in islice(p.fit_with_sigmas_lls(5, 2), 400):
+            lls.append(ll)
+            sig.append((p.sigma_sq, p.sigma_u_sq, p.sigma_v_sq))
+        out["ws_lls" + tag], out["ws_sigmas" + tag] = np.array(lls), np.array(sig)
+        out["ws_users" + tag], out["ws_items" + tag] = p.users, p.items
+    # (b) mini-batch SGD with a validation split (pmf_cy.pyx:308-381)
+    for tag, sm in (("", False), ("_sm", True)):
+        p = PMF(R.copy(), d, sm)
+        p.users, p.items = users.copy() * .3, items.copy() * .3
+        np.random.seed(3); pyrandom.seed(3)
+        errs = list(islice(p.fit_minibatches_validation(50, 40, lr=.05), 6))
+        out["mb_errs" + tag] = np.array(errs)
+        out["mb_users" + tag], out["mb_items" + tag] = p.users, p.items
+        q = PMF(R.copy(), d, sm)
+        q.users, q.items = users.copy() * .3, items.copy() * .3
+        np.random.seed(3); pyrandom.seed(3)
+        q.fit_minibatches_until_validation(50, 40, lr=.05, stop_thresh=1e-3)
+        out["mbu_users" + tag], out["mbu_items" + tag] = q.users, q.items
+        # (c) dense prediction and RMSE on everything / a mask / an index tuple
+        out["pm" + tag] = p.predicted_matrix()
+        rows = np.array([0, 3, 29, 7])           # `on` is typed ndarray: a mask or row numbers
+        out["rmse3" + tag] = np.array([p.rmse(real), p.rmse(real, mask), p.rmse(real, rows)])
+        out["rmse_rows"] = rows
+    # (d) Wishart draws, both schemes (bayes_pmf.py:41-59)
+    S = rng.normal(size=(3, 3)); S = S @ S.T + np.eye(3)
+    np.random.seed(8)
+    out["wishart_sigma"] = S
+    out["wishart_direct"] = ref.bayes_pmf.sample_wishart(S, 7)
+    out["wishart_bartlett"] = ref.bayes_pmf.sample_wishart(S, 120)
+    out["wishart_bartlett_frac"] = ref.bayes_pmf.sample_wishart(S, 6.5)
+    # (e) bayes_rmse over a short chain (bayes_pmf.py:544-545)
+    b = BayesianPMF(R, d)
+    b.users, b.items = users.copy(), items.copy()
+    np.random.seed(13)
+    s = list(islice(b.samples(num_gibbs=2), 4))
+    out["br_samples_u"] = np.array([x[0] for x in s])
+    out["br_samples_v"] = np.array([x[1] for x in s])
+    out["bayes_rmse"] = np.array([b.bayes_rmse(s, real), b.bayes_rmse(s, real, mask)])
+    save("extras_30x40_d4", **out)
+
+
+# ---- case 8: lookahead expectation by quadrature / Simpson (active_pmf.py:679-699) ------
+def case_continuous():
+    import contextlib, io
+    g = np.load(os.path.join(HERE, "lookahead_6x7_d2.npz"))
+    cand = list(zip(g["cand_i"].tolist(), g["cand_j"].tolist()))[:3]
+
+    def model(values):
+        a = ActivePMF(g["ratings"], 2, rating_values=values, discrete_expectations=False)
+        a.users, a.items = g["users"].copy(), g["items"].copy()
+        a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+        return a
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = model(None)              # no rating_values: any v may be added, adaptive quadrature
+        quad = np.array([a.exp_approx_entropy(c) for c in cand])
+        quad_tv = np.array([a.exp_total_variance(c) for c in cand])
+        a = model({0, .5, 1})
+        simps = np.array([a._exp_with_rij(c, ActivePMF._approx_entropy, discretize='simps')
+                          for c in cand])
+    save("continuous_6x7_d2", cand_i=np.array([c[0] for c in cand]),
+         cand_j=np.array([c[1] for c in cand]), quad_entropy=quad, quad_total_variance=quad_tv,
+         simps_entropy=simps)
+
+
 if __name__ == "__main__":
     cases = dict(known_answer=case_known_answer, d5=case_d5, fit=case_fit,
-                 lookahead=case_lookahead, gibbs=case_gibbs, matrix_normal=case_matrix_normal)
+                 lookahead=case_lookahead, gibbs=case_gibbs, matrix_normal=case_matrix_normal,
+                 extras=case_extras, continuous=case_continuous)
     for name in (sys.argv[1:] or list(cases)):
         cases[name]()

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "amf_score_pred_host": [_INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT,
                             C.POINTER(Best)],
     "amf_score_pred_host_csr": [_INT, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT, C.POINTER(Best)],
+    "amf_score_pred_host_csr16": [_INT, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT, C.POINTER(Best)],
 }
 
 _lib = None

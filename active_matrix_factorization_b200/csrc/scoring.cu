@@ -340,24 +340,35 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
 
 constexpr int HOST_CHUNKS = 8;   // pieces the candidate arrays cross PCIe in (large pools)
 
+// 16-bit item ids (pools over at most 65536 items cross PCIe at 2 bytes per candidate) -> the
+// int32 ids the scoring kernel reads.  Pure streaming: 2 bytes in, 4 bytes out per candidate.
+__global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t* __restrict__ in,
+                                                        int64_t count, int32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride)
+    out[t] = (int32_t)in[t];
+}
+
 // shared body of the host-buffer scoring calls: the candidate users come either as an array
 // (ci_h) or as row offsets into cj_h (ptr_h, n+1 entries), expanded on the device
 static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int64_t* ptr_h,
-                           const int32_t* cj_h, int32_t n, int32_t m, int d, const void* U_h,
-                           const void* V_h, void* scores_h, int maximize, amf_best_t* best_h) {
+                           const int32_t* cj_h, const uint16_t* cj16_h, int32_t n, int32_t m, int d,
+                           const void* U_h, const void* V_h, void* scores_h, int maximize,
+                           amf_best_t* best_h) {
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_score_pred_host: bad dtype");
   AMF_REQUIRE(best_h && U_h && V_h, "amf_score_pred_host: NULL argument");
-  AMF_REQUIRE(ncand == 0 || (cj_h && (ci_h || ptr_h)), "amf_score_pred_host: NULL candidate arrays");
+  AMF_REQUIRE(ncand == 0 || ((cj_h || cj16_h) && (ci_h || ptr_h)),
+              "amf_score_pred_host: NULL candidate arrays");
   const size_t es = dtype == AMF_F32 ? 4 : 8;
   const int vecn = dtype == AMF_F32 ? 4 : 2;
   const int ld = (d + vecn - 1) / vecn * vecn;
   // grow-only staging buffers, one set per host thread and device (freed at process exit)
-  struct Stage { void* p[7]; size_t n[7]; int dev; };
+  struct Stage { void* p[8]; size_t n[8]; int dev; };
   static thread_local Stage st = {{nullptr}, {0}, -1};
   int dev = 0;
   AMF_CUDA(cudaGetDevice(&dev));
   if (st.dev != dev) {
-    for (int q = 0; q < 7; ++q) { if (st.p[q]) cudaFree(st.p[q]); st.p[q] = nullptr; st.n[q] = 0; }
+    for (int q = 0; q < 8; ++q) { if (st.p[q]) cudaFree(st.p[q]); st.p[q] = nullptr; st.n[q] = 0; }
     st.dev = dev;
   }
   auto need = [&](int q, size_t bytes) -> int {
@@ -373,8 +384,10 @@ static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const 
   if ((rc = need(0, (size_t)n * ld * es)) || (rc = need(1, (size_t)m * ld * es)) ||
       (rc = need(2, 4 * nc)) || (rc = need(3, 4 * nc)) ||
       (rc = need(4, sizeof(amf_best_t) * (HOST_CHUNKS + 1))) ||
-      (scores_h && (rc = need(5, es * nc))) || (ptr_h && (rc = need(6, 8 * ((size_t)n + 1)))))
+      (scores_h && (rc = need(5, es * nc))) || (ptr_h && (rc = need(6, 8 * ((size_t)n + 1)))) ||
+      (cj16_h && (rc = need(7, 2 * nc))))
     return rc;
+  uint16_t* cj16_d = (uint16_t*)st.p[7];
   void *U_d = st.p[0], *V_d = st.p[1], *sc_d = scores_h ? st.p[5] : nullptr;
   int32_t *ci_d = (int32_t*)st.p[2], *cj_d = (int32_t*)st.p[3];
   amf_best_t* best_d = (amf_best_t*)st.p[4];          // [HOST_CHUNKS] per-chunk winners + result
@@ -411,10 +424,17 @@ static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const 
     if (hi > lo) {
       if (!ptr_h)
         AMF_CUDA(cudaMemcpyAsync(ci_d + lo, ci_h + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
-      AMF_CUDA(cudaMemcpyAsync(cj_d + lo, cj_h + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
+      if (cj16_h)
+        AMF_CUDA(cudaMemcpyAsync(cj16_d + lo, cj16_h + lo, 2 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
+      else
+        AMF_CUDA(cudaMemcpyAsync(cj_d + lo, cj_h + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s_copy));
     }
     AMF_CUDA(cudaEventRecord(ev[k], s_copy));
     AMF_CUDA(cudaStreamWaitEvent(s_comp, ev[k], 0));
+    if (cj16_h && hi > lo) {
+      widen_u16_kernel<<<num_sms() * 8, 256, 0, s_comp>>>(cj16_d + lo, hi - lo, cj_d + lo);
+      AMF_LAUNCH_CHECK();
+    }
     rc = amf_score_candidates(AMF_CRIT_PRED, dtype, hi - lo, ci_d + lo, cj_d + lo, d, ld, U_d, V_d,
                               nullptr, 0.0, sc_d ? (char*)sc_d + es * lo : nullptr, maximize, lo,
                               best_d + 1 + k, s_comp);
@@ -433,16 +453,25 @@ static int score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const 
 int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,
                         int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
                         void* scores_h, int maximize, amf_best_t* best_h) {
-  return score_pred_host(dtype, ncand, ci_h, nullptr, cj_h, n, m, d, U_h, V_h, scores_h, maximize,
-                         best_h);
+  return score_pred_host(dtype, ncand, ci_h, nullptr, cj_h, nullptr, n, m, d, U_h, V_h, scores_h,
+                         maximize, best_h);
 }
 
 int amf_score_pred_host_csr(int dtype, const int64_t* cand_ptr_h, const int32_t* cj_h, int32_t n,
                             int32_t m, int d, const void* U_h, const void* V_h, void* scores_h,
                             int maximize, amf_best_t* best_h) {
   AMF_REQUIRE(cand_ptr_h && n > 0, "amf_score_pred_host_csr: NULL row offsets");
-  return score_pred_host(dtype, cand_ptr_h[n], nullptr, cand_ptr_h, cj_h, n, m, d, U_h, V_h,
-                         scores_h, maximize, best_h);
+  return score_pred_host(dtype, cand_ptr_h[n], nullptr, cand_ptr_h, cj_h, nullptr, n, m, d, U_h,
+                         V_h, scores_h, maximize, best_h);
+}
+
+int amf_score_pred_host_csr16(int dtype, const int64_t* cand_ptr_h, const uint16_t* cj16_h,
+                              int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
+                              void* scores_h, int maximize, amf_best_t* best_h) {
+  AMF_REQUIRE(cand_ptr_h && n > 0, "amf_score_pred_host_csr16: NULL row offsets");
+  AMF_REQUIRE(m <= 65536, "amf_score_pred_host_csr16: %d items do not fit 16-bit ids", m);
+  return score_pred_host(dtype, cand_ptr_h[n], nullptr, cand_ptr_h, nullptr, cj16_h, n, m, d, U_h,
+                         V_h, scores_h, maximize, best_h);
 }
 
 #pragma GCC visibility pop

@@ -46,23 +46,26 @@ def score_pred(users, items, ii, jj, name, maximize=True):
 def score_pred_host_csr(users, items, cand_ptr, cand_j, name, want_scores=False, maximize=True):
     """End-to-end host call for a pool sorted by user and given as row offsets (the candidates of
     user i are cand_j[cand_ptr[i]:cand_ptr[i+1]]): host arrays in, (scores or None, (best value,
-    best position in cand_j)) out.  amf_score_pred_host_csr; half the PCIe bytes of (i, j) pairs."""
+    best position in cand_j)) out.  amf_score_pred_host_csr; half the PCIe bytes of (i, j) pairs.
+    A ``cand_j`` of dtype uint16 (at most 65536 items) goes through amf_score_pred_host_csr16 and
+    halves them again."""
     import ctypes as C
     lib = N.require_device()
     dt = D.np_dtype(name)
     users = np.ascontiguousarray(users, dtype=dt)
     items = np.ascontiguousarray(items, dtype=dt)
     cand_ptr = np.ascontiguousarray(cand_ptr, dtype=np.int64)
-    cand_j = np.ascontiguousarray(cand_j, dtype=np.int32)
+    narrow = getattr(cand_j, 'dtype', None) == np.uint16
+    cand_j = np.ascontiguousarray(cand_j, dtype=np.uint16 if narrow else np.int32)
     n, d = users.shape
     if cand_ptr.shape[0] != n + 1 or cand_ptr[0] != 0 or cand_ptr[-1] != cand_j.shape[0]:
         raise ValueError("cand_ptr must hold n_users + 1 offsets running from 0 to len(cand_j)")
     scores = np.empty(cand_j.shape[0], dtype=dt) if want_scores else None
     best = N.Best()
-    N.check(lib.amf_score_pred_host_csr(D.code(name), N.host_ptr(cand_ptr), N.host_ptr(cand_j), n,
-                                        items.shape[0], d, N.host_ptr(users), N.host_ptr(items),
-                                        N.host_ptr(scores) if want_scores else None,
-                                        1 if maximize else 0, C.byref(best)))
+    call = lib.amf_score_pred_host_csr16 if narrow else lib.amf_score_pred_host_csr
+    N.check(call(D.code(name), N.host_ptr(cand_ptr), N.host_ptr(cand_j), n, items.shape[0], d,
+                 N.host_ptr(users), N.host_ptr(items), N.host_ptr(scores) if want_scores else None,
+                 1 if maximize else 0, C.byref(best)))
     return scores, (best.value, best.index)
 
 

@@ -412,18 +412,28 @@ def run_ours(a):
     best_h = N.Best()
 
     # the pool is sorted by user: the host call takes it as row offsets + item ids (CSR), which
-    # halves the PCIe bytes of the (i, j) pair form; both forms are timed
+    # halves the PCIe bytes of the (i, j) pair form, and with at most 65536 items the ids travel
+    # as 16-bit words (amf_score_pred_host_csr16), which halves them again; all forms are timed
     ptr_h = torch.zeros(n + 1, dtype=torch.int64).pin_memory()
     ptr_h[1:].copy_(torch.cumsum(torch.bincount(ci.long(), minlength=n), 0))
+    narrow = m <= 65536
+    if narrow:
+        cj16_h = torch.empty(ncand, dtype=torch.int16).pin_memory()   # same 16 bits as uint16
+        cj16_h.copy_(cj.to(torch.int16))
 
-    def e2e_step(csr=True):
+    def e2e_step(csr=True, ids16=False):
         t0 = time.perf_counter()
         N.check(lib.amf_pmf_loss_grad_host(rat.handle, D.code(name), d, C.c_void_p(U_h.data_ptr()),
                                            C.c_void_p(V_h.data_ptr()), C.byref(params),
                                            C.c_void_p(dU_h.data_ptr()), C.c_void_p(dV_h.data_ptr()),
                                            N.host_ptr(sums_h)))
         t1 = time.perf_counter()
-        if csr:
+        if csr and ids16:
+            N.check(lib.amf_score_pred_host_csr16(D.code(name), C.c_void_p(ptr_h.data_ptr()),
+                                                  C.c_void_p(cj16_h.data_ptr()), n, m, d,
+                                                  C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
+                                                  None, 1, C.byref(best_h)))
+        elif csr:
             N.check(lib.amf_score_pred_host_csr(D.code(name), C.c_void_p(ptr_h.data_ptr()),
                                                 C.c_void_p(cj_h.data_ptr()), n, m, d,
                                                 C.c_void_p(U_h.data_ptr()), C.c_void_p(V_h.data_ptr()),
@@ -439,9 +449,14 @@ def run_ours(a):
     e2e_step(csr=False)
     sync()
     e2e_pairs_s = float(np.mean([e2e_step(csr=False)[1] for _ in range(a.e2e_steps)]))
-    e2e_step()
+    e2e_csr32_s = None
+    if narrow:
+        e2e_step()
+        sync()
+        e2e_csr32_s = float(np.mean([e2e_step()[1] for _ in range(a.e2e_steps)]))
+    e2e_step(ids16=narrow)
     sync()
-    e2e = [e2e_step() for _ in range(a.e2e_steps)]
+    e2e = [e2e_step(ids16=narrow) for _ in range(a.e2e_steps)]
     e2e_t = torch.tensor([float(np.mean([t[0] for t in e2e])), float(np.mean([t[1] for t in e2e]))],
                          dtype=torch.float64, device=U.device)
     if world > 1:
@@ -494,11 +509,14 @@ def run_ours(a):
                               "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms,
                               "traffic": traffic.get("tiled_side_kernel_x2" if tiled_grad else "side_pass_kernel_x2")},
         "e2e": {"value": ncand_all / e2e_score_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(ncand * 4 + (n + 1) * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
+                "h2d_bytes_per_step": int(ncand * (2 if narrow else 4) + (n + 1) * 8 + 2 * tables), "d2h_bytes_per_step": int(tables + 24 + 16),
                 "pmf_ratings_per_sec_iter": nnz_all / e2e_grad_s,
                 "pairs_form_value": ncand / e2e_pairs_s if world == 1 else None,
-                "note": "amf_pmf_loss_grad_host + amf_score_pred_host_csr (pool as row offsets + item ids) with pinned host buffers; "
-                        "rating list resident; pairs_form_value = amf_score_pred_host with (i, j) arrays, 8 bytes per candidate"},
+                "csr32_form_value": ncand / e2e_csr32_s if (world == 1 and e2e_csr32_s) else None,
+                "note": "amf_pmf_loss_grad_host + %s (pool as row offsets + %s item ids) with pinned host buffers; "
+                        "rating list resident; csr32_form_value = amf_score_pred_host_csr with 32-bit item ids (4 bytes per candidate), "
+                        "pairs_form_value = amf_score_pred_host with (i, j) arrays (8 bytes per candidate)"
+                        % (("amf_score_pred_host_csr16", "16-bit") if narrow else ("amf_score_pred_host_csr", "32-bit"))},
         "gpu_launches": a.steps * step.launches_per_step,
         "clocks": clocks,
         "selected": {"value": float(bv), "index": bi},

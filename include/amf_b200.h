@@ -235,6 +235,12 @@ int amf_score_pred_host_csr(int dtype, const int64_t* cand_ptr_h, const int32_t*
                             int32_t m, int d, const void* U_h, const void* V_h, void* scores_h,
                             int maximize, amf_best_t* best_h);
 
+/* Same with 16-bit item ids, for pools over at most 65536 items (m <= 65536, else an error):
+ * 2 bytes per candidate cross PCIe, widened on the device piece by piece behind the copy. */
+int amf_score_pred_host_csr16(int dtype, const int64_t* cand_ptr_h, const uint16_t* cj16_h,
+                              int32_t n, int32_t m, int d, const void* U_h, const void* V_h,
+                              void* scores_h, int maximize, amf_best_t* best_h);
+
 /* ------------------------------------------------------------------------------------------
  * Bayesian PMF (bayes_pmf.py:189-216 sample_feature inside the sweeps of :283-300;
  * :433-455 predict / pred_variance / :528-538 prob_ge_cutoff over a list of samples).

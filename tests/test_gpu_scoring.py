@@ -214,6 +214,13 @@ def test_host_csr_pool_matches_pairs(S, dtype, tol):
         assert bi == int(np.argmax(sc) if maximize else np.argmin(sc)) and bv == sc[bi]
     _, (bv, bi) = S.score_pred_host_csr(U, V, ptr, jj, dtype)
     assert bi == int(np.argmax(sc if False else ref.astype(sc.dtype))) or abs(ref[bi] - ref.max()) <= tol * abs(ref.max())
+    # 16-bit item ids (amf_score_pred_host_csr16): same scores and winner, bit for bit
+    sc_min = sc
+    sc16, best16 = S.score_pred_host_csr(U, V, ptr, jj.astype(np.uint16), dtype, want_scores=True,
+                                         maximize=False)
+    assert np.array_equal(sc16, sc_min) and best16 == (sc_min[int(np.argmin(sc_min))], int(np.argmin(sc_min)))
+    with pytest.raises(RuntimeError):      # more than 65536 items do not fit
+        S.score_pred_host_csr(U, np.zeros((70000, d)), ptr, jj.astype(np.uint16), dtype)
     _, (bv, bi) = S.score_pred_host_csr(U, V, np.zeros(n + 1, np.int64), jj[:0], dtype)
     assert bi == -1
     with pytest.raises(ValueError):

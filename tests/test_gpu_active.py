@@ -119,6 +119,23 @@ def test_lookahead_criteria_golden(A, golden):
         assert isinstance(f.do_normal_fit, bool) and isinstance(f.spawn_processes, bool)
 
 
+def test_lookahead_simpson_and_three_values(A, golden):
+    """_exp_with_rij with discretize='simps' (active_pmf.py:679-684) and the summed form over
+    three rating values {0, .5, 1}: same re-fits, different weights.  Adaptive quadrature (no
+    rating_values) is not pinned -- see make_golden.py case_continuous."""
+    g, c = golden("lookahead_6x7_d2"), golden("continuous_6x7_d2")
+    a = A.ActivePMF(g["ratings"], 2, rating_values={0, .5, 1}, discrete_expectations=False)
+    a.users, a.items = g["users"].copy(), g["items"].copy()
+    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+    cand = list(zip(c["cand_i"].tolist(), c["cand_j"].tolist()))
+    simps = [a._exp_with_rij(ij, A.ActivePMF._approx_entropy, discretize='simps') for ij in cand]
+    summed = [a._exp_with_rij(ij, A.ActivePMF._approx_entropy, discretize=True) for ij in cand]
+    np.testing.assert_allclose(simps, c["simps_entropy"], rtol=1e-5)
+    np.testing.assert_allclose(summed, c["summed_entropy"], rtol=1e-5)
+    with pytest.raises(ValueError):          # .25 is not one of the rating values
+        a.add_rating(cand[0][0], cand[0][1], .25)
+
+
 def test_pred_entropy_bound_and_onestep_match_oracle_restatement(A, golden):
     g = golden("lookahead_6x7_d2")
     a = A.ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)

@@ -173,6 +173,44 @@ def test_copy_and_pickle_keep_approximation(A, golden):
     assert '__dict__' in a.__getstate__()
 
 
+def test_concurrent_host_threads_each_with_its_own_copy(A, golden):
+    """The reference evaluates one criterion per host THREAD, each on its own deep copy of the
+    model (active_pmf.py:1064-1079).  Same here: four threads hammer gradient / objective /
+    batched criteria / a lookahead re-fit at once and must reproduce the serial answers."""
+    import threading
+    g = golden("random_12x20_d5")
+    base = model_from(A, g, 5)
+    pool = list(zip(g["cand_i"].tolist(), g["cand_j"].tolist()))
+    want_pv = np.array(base._get_key_vals(pool, A.ActivePMF.pred_variance))
+    want_pr = np.array(base._get_key_vals(pool, A.ActivePMF.pred))
+    want_ll, want_kl = base.log_likelihood(), base.kl_divergence()
+    want_gu, _ = base.gradient()
+    errors, done = [], []
+
+    def work(model, t):
+        try:
+            for _ in range(6):
+                if t % 2:
+                    np.testing.assert_allclose(model._get_key_vals(pool, A.ActivePMF.pred_variance), want_pv, rtol=1e-12)
+                    assert model.kl_divergence() == pytest.approx(want_kl, rel=1e-12)
+                    assert model.pick_query_point(pool, A.ActivePMF.pred_variance) == pool[int(np.argmax(want_pv))]
+                else:
+                    np.testing.assert_allclose(model._get_key_vals(pool, A.ActivePMF.pred), want_pr, rtol=1e-12)
+                    assert model.log_likelihood() == pytest.approx(want_ll, rel=1e-12)
+                    np.testing.assert_allclose(model.gradient()[0], want_gu, rtol=1e-11)
+            done.append(t)
+        except Exception as e:                       # surfaced in the main thread below
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(copy.deepcopy(base), t)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(120)
+    assert not errors, errors
+    assert sorted(done) == [0, 1, 2, 3]
+
+
 def test_driver_smoke_matches_reference_soft_pin(A):
     """SURVEY.md 8c soft pin: seeded CLI run of the reference prints RMSE 0.56964 then queries.
     The first RMSE depends only on the seeded data + MAP fit, so it must match."""

@@ -145,6 +145,43 @@ __global__ void expand_rows_kernel(const int64_t* __restrict__ ptr, int32_t rows
     for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) row[p] = (Index)r;
 }
 
+// Counts the (a, b) index pairs outside [0, a_rows) x [0, b_rows).  A template for the same reason.
+template <typename Index>
+__global__ void count_out_of_range_kernel(const Index* __restrict__ a, Index a_rows,
+                                          const Index* __restrict__ b, Index b_rows, int64_t n,
+                                          unsigned long long* __restrict__ bad) {
+  unsigned int mine = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x)
+    mine += ((uint32_t)a[t] >= (uint32_t)a_rows) | ((uint32_t)b[t] >= (uint32_t)b_rows);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(bad, (unsigned long long)mine);
+}
+
+// Every structure built from caller-supplied ids (rating lists, candidate pools) is checked once
+// at build time -- the reference asserts the same (pmf_cy.pyx:139-140) -- so that a bad id is an
+// error code, not an out-of-bounds gather inside a kernel.  Synchronises `s`.
+#define AMF_CHECK_ID_RANGE(what, a_d, a_rows, b_d, b_rows, n, s)                                  \
+  do {                                                                                            \
+    if ((n) > 0) {                                                                                \
+      unsigned long long* bad_d__ = nullptr;                                                      \
+      unsigned long long bad__ = 0;                                                               \
+      AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bad_d__), 8, (s)));                      \
+      AMF_CUDA(cudaMemsetAsync(bad_d__, 0, 8, (s)));                                              \
+      const int64_t blocks__ = ((n) + 255) / 256;                                                 \
+      const int grid__ = (int)(blocks__ < (int64_t)amf::num_sms() * 8 ? blocks__                  \
+                                                                       : (int64_t)amf::num_sms() * 8); \
+      amf::count_out_of_range_kernel<int32_t><<<grid__, 256, 0, (s)>>>((a_d), (a_rows), (b_d),    \
+                                                                       (b_rows), (n), bad_d__);   \
+      AMF_LAUNCH_CHECK();                                                                         \
+      AMF_CUDA(cudaMemcpyAsync(&bad__, bad_d__, 8, cudaMemcpyDeviceToHost, (s)));                 \
+      AMF_CUDA(cudaFreeAsync(bad_d__, (s)));                                                      \
+      AMF_CUDA(cudaStreamSynchronize((s)));                                                       \
+      AMF_REQUIRE(bad__ == 0, "%s: %llu of %lld (user, item) ids lie outside %d x %d", (what),    \
+                  bad__, (long long)(n), (int)(a_rows), (int)(b_rows));                           \
+    }                                                                                             \
+  } while (0)
+
 // final reduction of per-block partial winners (launch with one block)
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);

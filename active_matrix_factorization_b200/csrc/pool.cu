@@ -319,6 +319,8 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
   AMF_REQUIRE(ibits + jbits <= 32, "amf_pool_create: %d users x tiles of %d items do not fit the "
               "4-byte packed index (use amf_score_candidates)", n_users, tile_rows);
   cudaStream_t s = (cudaStream_t)stream;
+  AMF_REQUIRE(ncand == 0 || (ci_d && cj_d), "amf_pool_create: NULL candidate arrays");
+  AMF_CHECK_ID_RANGE("amf_pool_create", ci_d, n_users, cj_d, n_items, ncand, s);
   amf_pool* h = new amf_pool();
   memset(h, 0, sizeof(*h));
   h->ncand = ncand; h->n_users = n_users; h->n_items = n_items;

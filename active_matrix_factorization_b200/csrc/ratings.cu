@@ -215,6 +215,8 @@ int amf_ratings_create(amf_ratings_t** out, int32_t n_users, int32_t n_items, in
               (long long)nnz);
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_ratings_create: bad dtype %d", dtype);
   cudaStream_t s = (cudaStream_t)stream;
+  AMF_REQUIRE(nnz == 0 || (i_d && j_d && r_d), "amf_ratings_create: NULL rating arrays");
+  AMF_CHECK_ID_RANGE("amf_ratings_create", i_d, n_users, j_d, n_items, nnz, s);
   amf_ratings* h = new amf_ratings();
   memset(h, 0, sizeof(*h));
   h->n_users = n_users; h->n_items = n_items; h->nnz = nnz; h->dtype = dtype;
@@ -260,6 +262,7 @@ int amf_ratings_append(amf_ratings_t* h, int64_t n_new, const int32_t* i_d, cons
   if (n_new == 0) return AMF_OK;
   AMF_REQUIRE(h->nnz + h->tail_n + n_new < (1ll << 32), "amf_ratings_append: list would exceed 2^32 entries");
   cudaStream_t s = (cudaStream_t)stream;
+  AMF_CHECK_ID_RANGE("amf_ratings_append", i_d, h->n_users, j_d, h->n_items, n_new, s);
   const size_t es = h->dtype == AMF_F32 ? 4 : 8;
   if (h->tail_n + n_new > h->tail_cap) {
     int64_t cap = h->tail_cap > 0 ? h->tail_cap : 4096;

@@ -17,6 +17,11 @@
  *   - dtype: AMF_F32 (fast mode) or AMF_F64 (parity mode, the reference's precision).
  *   - factor matrices are row-major (rows, ld) with ld >= d, ld*sizeof(T) a multiple of 16
  *     bytes, and columns d..ld-1 equal to zero.
+ *   - user / item ids are checked against the matrix shape once, where a structure is built
+ *     from them (amf_ratings_create, amf_ratings_append, amf_pool_create: AMF_ERR_INVALID, as the
+ *     reference asserts in pmf_cy.pyx:139-140); the per-step scoring calls that take raw
+ *     candidate arrays (amf_score_candidates, amf_score_pred_host*, amf_mn_score_candidates,
+ *     amf_bayes_sample_stats) trust them.
  *   - the library keeps no global mutable state besides per-thread error text; handles may be
  *     used from different host threads as long as one handle is not used concurrently.
  */

@@ -144,3 +144,27 @@ def test_model_add_ratings_keeps_device_list(env, ctor):
         assert np.array_equal(p.ratings, R)
         with pytest.raises(ValueError):
             p.add_rating(*R[5])                          # already rated
+
+
+def test_out_of_range_ids_are_an_error_not_a_fault(env):
+    """ids outside the matrix are rejected when a list / pool is built (the reference asserts,
+    pmf_cy.pyx:139-140); afterwards the device is still usable"""
+    import torch
+    from active_matrix_factorization_b200 import device as D, scoring as S
+    i = np.array([0, 1, 5, 2], np.int32)
+    j = np.array([0, 3, 1, 2], np.int32)
+    r = np.ones(4)
+    for bad_i, bad_j in ((np.array([0, 1, 6, 2], np.int32), j), (i, np.array([0, 4, 1, 2], np.int32)),
+                         (np.array([0, -1, 5, 2], np.int32), j)):
+        with pytest.raises(RuntimeError, match="outside 6 x 4"):
+            D.Ratings(6, 4, bad_i, bad_j, r, "f64")
+        with pytest.raises(RuntimeError, match="outside 6 x 4"):
+            S.Pool(bad_i, bad_j, 6, 4, "f64", 3)
+    rat = D.Ratings(6, 4, i, j, r, "f64")
+    with pytest.raises(RuntimeError, match="amf_ratings_append"):
+        rat.append(np.array([6], np.int32), np.array([0], np.int32), np.array([1.]))
+    assert rat.nnz == 4
+    rat.append(np.array([5], np.int32), np.array([3], np.int32), np.array([1.]))
+    assert rat.nnz == 5
+    rat.close()
+    assert torch.zeros(4, device="cuda").sum().item() == 0      # no sticky CUDA error

@@ -234,9 +234,23 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         n, m = self.num_users, self.num_items
         if which is None:
             which = Ellipsis
+        # the two forms the drivers use (bayes_pmf.py:702-712: a pair of index arrays; a boolean
+        # mask) without building the n x m index grids
+        if isinstance(which, tuple) and len(which) == 2:
+            ia, ja = (np.asarray(w) for w in which)
+            if (ia.dtype.kind in 'iu' and ja.dtype.kind in 'iu' and ia.shape == ja.shape and ia.ndim >= 1
+                    and (ia.size == 0 or (ia.min() >= 0 and ja.min() >= 0 and ia.max() < n and ja.max() < m))):
+                return ia.reshape(-1), ja.reshape(-1), ia.shape
+        elif isinstance(which, np.ndarray) and which.dtype == bool and which.shape == (n, m):
+            ia, ja = np.nonzero(which)
+            return ia, ja, ia.shape
         ii, jj = np.meshgrid(np.arange(n), np.arange(m), indexing='ij')
         i_idx, j_idx = ii[which], jj[which]
         return i_idx.reshape(-1), j_idx.reshape(-1), i_idx.shape
+
+    # `which` covering at least this fraction of the matrix goes through the dense (blocked) form
+    # of amf_bayes_sample_stats and is gathered from its n x m outputs
+    _DENSE_WHICH_FRACTION = 0.125
 
     def _sample_stats(self, samples_iter, which, cutoff=0., want=('mean', 'var', 'prob')):
         lib = N.require_device()
@@ -245,19 +259,33 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         samples = list(samples_iter)
         if not samples:
             raise StopIteration
+        n, m, d = self.num_users, self.num_items, self.latent_d
         us = D.to_device(np.stack([np.asarray(u) for u, _ in samples]), dt)
         vs = D.to_device(np.stack([np.asarray(v) for _, v in samples]), dt)
-        i_idx, j_idx, shape = self._which_indices(which)
-        ci, cj = D.to_device(i_idx, np.int32), D.to_device(j_idx, np.int32)
-        nc = ci.numel()
         tdt = D.torch_dtype(name)
-        outs = {k: torch.empty(nc, dtype=tdt, device=ci.device) if k in want else None
+        whole = which is None or which is Ellipsis
+        if whole:
+            i_idx = j_idx = None
+            shape, nsel = (n, m), n * m
+        else:
+            i_idx, j_idx, shape = self._which_indices(which)
+            nsel = i_idx.shape[0]
+        dense = (whole or nsel >= self._DENSE_WHICH_FRACTION * n * m) and 98 * d * np.dtype(dt).itemsize <= 200 * 1024
+        nc = n * m if dense else nsel
+        if dense:
+            ci = cj = None
+        else:
+            ci, cj = D.to_device(i_idx, np.int32), D.to_device(j_idx, np.int32)
+        outs = {k: torch.empty(nc, dtype=tdt, device=us.device) if k in want else None
                 for k in ('mean', 'var', 'prob')}
         N.check(lib.amf_bayes_sample_stats(
-            D.code(name), nc, D.ptr(ci), D.ptr(cj), len(samples), self.num_users, self.num_items,
-            self.latent_d, D.ptr(us), D.ptr(vs), float(self._mean_offset()), float(cutoff),
+            D.code(name), nc, D.ptr(ci), D.ptr(cj), len(samples), n, m, d, D.ptr(us), D.ptr(vs),
+            float(self._mean_offset()), float(cutoff),
             D.ptr(outs['mean']), D.ptr(outs['var']), D.ptr(outs['prob']), 1, 1, 0, None,
             D.stream_ptr()))
+        if dense and not whole:                 # pick the wanted cells out of the dense outputs
+            flat = torch.from_numpy(np.asarray(i_idx, dtype=np.int64) * m + np.asarray(j_idx, dtype=np.int64)).to(us.device)
+            outs = {k: (v[flat] if v is not None else None) for k, v in outs.items()}
         return {k: v.to(torch.float64).cpu().numpy().reshape(shape)
                 for k, v in outs.items() if v is not None}
 

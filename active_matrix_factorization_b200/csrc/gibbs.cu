@@ -657,6 +657,104 @@ sample_stats_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ 
   if (threadIdx.x == 0) part[blockIdx.x] = best;
 }
 
+// The same statistics for ALL n x m cells (cell c = i*m + j) -- what the reference's criteria
+// compute when `which` is the whole matrix or most of it (predicted_matrix(u, v) per sample,
+// bayes_pmf.py:433-455).  A blocked product instead of a gather: a CTA owns a DENSE_TU x DENSE_TV
+// tile of cells, stages the two factor tiles of one sample in shared memory (k-major, so the
+// item reads of a warp are consecutive words and the user reads are broadcasts) and every
+// thread carries a 2 x 4 block of cells with its running statistics in registers; the factor
+// rows are read once per tile and sample instead of once per cell and sample.  The dot product
+// is the same fma chain as sample_stats_kernel, the moments are accumulated about the first
+// sample's prediction (no division in the loop).
+constexpr int DENSE_TU = 32, DENSE_TV = 64, DENSE_THREADS = 256;
+
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(DENSE_THREADS)
+sample_stats_dense_kernel(int S, int n, int m, int d, const T* __restrict__ Us,
+                          const T* __restrict__ Vs, T offset, T cutoff, T* __restrict__ mean_out,
+                          T* __restrict__ var_out, T* __restrict__ prob_out, int select,
+                          int64_t index_base, Best* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char dense_smem[];
+  // k-major with one word of padding per row: the transposing stores of the staging loops
+  // (consecutive threads = consecutive k of one factor row) fall on different banks
+  constexpr int LU = DENSE_TU + 1, LV = DENSE_TV + 1;
+  T* sU = reinterpret_cast<T*>(dense_smem);            // [d][LU]
+  T* sV = sU + (size_t)d * LU;                         // [d][LV]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tiles_v = (m + DENSE_TV - 1) / DENSE_TV;
+  const int64_t n_tiles = (int64_t)((n + DENSE_TU - 1) / DENSE_TU) * tiles_v;
+  Best best{0.0, -1};
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int i0 = (int)(tile / tiles_v) * DENSE_TU, j0 = (int)(tile % tiles_v) * DENSE_TV;
+    double shift[2][4], s1[2][4], s2[2][4];
+    int cnt[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { shift[a][q] = 0; s1[a][q] = 0; s2[a][q] = 0; cnt[a][q] = 0; }
+    for (int s = 0; s < S; ++s) {
+      __syncthreads();                                 // the previous sample's tiles are done with
+      const T* us = Us + ((int64_t)s * n + i0) * d;
+      const T* vs = Vs + ((int64_t)s * m + j0) * d;
+      const int nu = min(DENSE_TU, n - i0), nv = min(DENSE_TV, m - j0);
+      for (int t = threadIdx.x; t < DENSE_TU * d; t += DENSE_THREADS) {
+        const int r = t / d, k = t - r * d;
+        sU[k * LU + r] = r < nu ? us[t] : T(0);
+      }
+      for (int t = threadIdx.x; t < DENSE_TV * d; t += DENSE_THREADS) {
+        const int r = t / d, k = t - r * d;
+        sV[k * LV + r] = r < nv ? vs[t] : T(0);
+      }
+      __syncthreads();
+      T dot[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dot[a][q] = 0;
+      for (int k = 0; k < d; ++k) {
+        const T u0 = sU[k * LU + ty * 2], u1 = sU[k * LU + ty * 2 + 1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const T v = sV[k * LV + tx + 16 * q];
+          dot[0][q] = fma(u0, v, dot[0][q]);
+          dot[1][q] = fma(u1, v, dot[1][q]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const T pred = dot[a][q] + offset;
+          cnt[a][q] += (pred >= cutoff);
+          if (s == 0) shift[a][q] = (double)pred;
+          const double x = (double)pred - shift[a][q];
+          s1[a][q] += x;
+          s2[a][q] = fma(x, x, s2[a][q]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + ty * 2 + a, j = j0 + tx + 16 * q;
+        if (i < n && j < m) {
+          const double mean = shift[a][q] + s1[a][q] / (double)S;
+          double var = (s2[a][q] - s1[a][q] * s1[a][q] / (double)S) / (double)S;
+          var = var < 0 ? 0 : var;
+          const double prob = (double)cnt[a][q] / (double)S;
+          const int64_t c = (int64_t)i * m + j;
+          if (mean_out) mean_out[c] = (T)mean;
+          if (var_out) var_out[c] = (T)var;
+          if (prob_out) prob_out[c] = (T)prob;
+          const double sel = select == 0 ? mean : (select == 1 ? var : prob);
+          if (better<MAX>(sel, c + index_base, best.v, best.i)) { best.v = sel; best.i = c + index_base; }
+        }
+      }
+  }
+  best = block_best<MAX>(best);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
 int acquire_partials(Best** out, cudaStream_t s);
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
@@ -787,9 +885,39 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
   AMF_REQUIRE(S >= 1 && d >= 1 && ncand >= 0, "amf_bayes_sample_stats: bad sizes");
   AMF_REQUIRE(select >= 0 && select <= 2, "amf_bayes_sample_stats: bad select");
   cudaStream_t s = (cudaStream_t)stream;
+  const bool dense = !ci_d && !cj_d && ncand > 0;     // every cell of the matrix, c = i*m + j
+  const size_t dense_smem = (size_t)(DENSE_TU + DENSE_TV + 2) * d * (dtype == AMF_F32 ? 4 : 8);
+  if (dense) {
+    AMF_REQUIRE(ncand == (int64_t)n * m, "amf_bayes_sample_stats: the dense form (NULL candidate "
+                "arrays) needs ncand = n*m");
+    AMF_REQUIRE(dense_smem <= 200 * 1024, "amf_bayes_sample_stats: latent_d=%d is too large for "
+                "the dense form", d);
+  } else {
+    AMF_REQUIRE(ncand == 0 || (ci_d && cj_d), "amf_bayes_sample_stats: NULL candidate array");
+  }
   Best* part = nullptr;
   int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
+  if (dense) {
+    const size_t smem = dense_smem;
+    const int64_t tiles = (int64_t)((n + DENSE_TU - 1) / DENSE_TU) * ((m + DENSE_TV - 1) / DENSE_TV);
+    const int dgrid = (int)(tiles < (int64_t)num_sms() * 8 ? tiles : (int64_t)num_sms() * 8);
+#define DENSE(T, MAXV)                                                                          \
+  do {                                                                                          \
+    AMF_CUDA(cudaFuncSetAttribute(sample_stats_dense_kernel<T, MAXV>,                           \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    sample_stats_dense_kernel<T, MAXV><<<dgrid, DENSE_THREADS, smem, s>>>(                      \
+        S, n, m, d, (const T*)Us_d, (const T*)Vs_d, (T)mean_offset, (T)cutoff, (T*)mean_d,      \
+        (T*)var_d, (T*)prob_d, select, index_base, part);                                       \
+  } while (0)
+    if (dtype == AMF_F32) { if (maximize) DENSE(float, true); else DENSE(float, false); }
+    else { if (maximize) DENSE(double, true); else DENSE(double, false); }
+#undef DENSE
+    AMF_LAUNCH_CHECK();
+    if (best_d) return launch_best_final(part, dgrid, maximize != 0, best_d, s);
+    AMF_CUDA(cudaFreeAsync(part, s));
+    return AMF_OK;
+  }
   const int64_t blocks = (ncand + 127) / 128;
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? (blocks > 0 ? blocks : 1)
                                                           : (int64_t)num_sms() * 16);

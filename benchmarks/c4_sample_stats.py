@@ -32,19 +32,23 @@ for name in ("f64", "f32"):
     nc = ci.numel()
     var = torch.empty(nc, dtype=D.torch_dtype(name), device=ci.device)
 
-    def launch():
-        N.check(lib.amf_bayes_sample_stats(D.code(name), nc, D.ptr(ci), D.ptr(cj), S, n, m, d,
+    def launch(dense):
+        N.check(lib.amf_bayes_sample_stats(D.code(name), nc, None if dense else D.ptr(ci),
+                                           None if dense else D.ptr(cj), S, n, m, d,
                                            D.ptr(us), D.ptr(vs), 0.0, 0.0, None, D.ptr(var), None,
                                            1, 1, 0, None, D.stream_ptr()))
-    launch()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        launch()
-    e1.record()
-    torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / 5
+
+    def timed(dense):
+        launch(dense)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            launch(dense)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5
+    g_ms, k_ms = timed(False), timed(True)
     b.pred_variance(samples)
     t0 = time.perf_counter()
     out = b.pred_variance(samples)
@@ -52,5 +56,5 @@ for name in ("f64", "f32"):
     ref = np.var([u[:7] @ v[:9].T for u, v in samples], 0)
     err = np.abs(out[:7, :9] - ref).max() / np.abs(ref).max()
     flop = nc * S * (2 * d + 6)
-    print("%s: kernel %.3f ms (%.2f TFLOP/s), whole call %.1f ms, rel err %.1e"
-          % (name, k_ms, flop / k_ms / 1e9, call_ms, err))
+    print("%s: per-candidate kernel %.3f ms, dense kernel %.3f ms (%.2f TFLOP/s), whole call %.1f ms, "
+          "rel err %.1e" % (name, g_ms, k_ms, flop / k_ms / 1e9, call_ms, err))

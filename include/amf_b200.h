@@ -274,7 +274,10 @@ int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream);
 /* Sample statistics of S posterior samples at ncand cells: Us_d (S, n, d), Vs_d (S, m, d)
  * tightly packed.  Any of mean_d / var_d / prob_d may be NULL.  var is the population variance
  * (np.var, bayes_pmf.py:448); prob = fraction of samples with prediction >= cutoff.
- * best_d (nullable) selects on `select` (0 mean, 1 var, 2 prob). */
+ * best_d (nullable) selects on `select` (0 mean, 1 var, 2 prob).
+ * Dense form: ci_d = cj_d = NULL and ncand = n*m scores every cell (c = i*m + j, outputs of n*m
+ * entries) as a blocked product over shared-memory tiles -- the form to use when `which` is the
+ * whole matrix or most of it (then gather the wanted cells from the dense outputs). */
 int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
                            int S, int32_t n, int32_t m, int d, const void* Us_d, const void* Vs_d,
                            double mean_offset, double cutoff, void* mean_d, void* var_d,

@@ -139,3 +139,39 @@ def test_tensor_core_gram_half_sweep(d):
     np.testing.assert_allclose(out["f64"][row], ref, rtol=1e-9, atol=1e-11)
     scale = np.abs(out["f64"]).max()
     assert np.abs(out["f32"] - out["f64"]).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
+@pytest.mark.parametrize("n,m,d,S", [(45, 70, 3, 7), (33, 129, 15, 20), (64, 64, 40, 5), (1, 5, 2, 1)])
+def test_dense_sample_stats_match_numpy_and_the_gather_kernel(Bm, n, m, d, S, dtype, tol):
+    """amf_bayes_sample_stats, dense form (blocked product over shared-memory tiles; `which` =
+    the whole matrix or most of it) against numpy over the samples (bayes_pmf.py:433-455,528-538)
+    and against the per-candidate kernel that sparse `which` sets use; ragged tile edges."""
+    rng = np.random.RandomState(n + d)
+    R = np.column_stack((rng.randint(0, n, 60), rng.randint(0, m, 60), rng.randint(1, 6, 60))).astype(float)
+    R[0, :2] = (n - 1, m - 1)
+    b = Bm.BayesianPMF(R, d)
+    b.compute_dtype = dtype
+    samples = [(rng.normal(size=(n, d)), rng.normal(size=(m, d))) for _ in range(S)]
+    preds = np.array([u @ v.T + b.mean_rating for u, v in samples])
+    scale = np.abs(preds).max()
+    want = dict(mean=preds.mean(0), var=preds.var(0), prob=(preds >= 3.5).mean(0))
+    got = dict(mean=b.predict(samples), var=b.pred_variance(samples), prob=b.prob_ge_cutoff(samples, 3.5))
+    for k in want:
+        assert got[k].shape == (n, m)
+        np.testing.assert_allclose(got[k], want[k], rtol=tol, atol=tol * scale * scale, err_msg=k)
+    assert b.total_variance(samples) == pytest.approx(want["var"].sum(), rel=tol * 10)
+    # most of the matrix as index arrays -> dense kernel + gather; a few cells -> gather kernel
+    mask = rng.uniform(size=(n, m)) < .7
+    mask[0, 0] = True
+    big = np.nonzero(mask)
+    few = (np.array([0, n - 1, n // 2]), np.array([m - 1, 0, m // 3]))
+    for which in (big, few, mask):
+        np.testing.assert_allclose(b.pred_variance(samples, which=which), want["var"][which],
+                                   rtol=tol, atol=tol * scale * scale)
+        np.testing.assert_allclose(b.predict(samples, which=which), want["mean"][which],
+                                   rtol=tol, atol=tol * scale)
+    b._DENSE_WHICH_FRACTION = 2.0                       # force the per-candidate kernel everywhere
+    np.testing.assert_allclose(b.pred_variance(samples, which=big), got["var"][big],
+                               rtol=tol, atol=tol * scale * scale)
+    np.testing.assert_array_equal(b.prob_ge_cutoff(samples, 3.5, which=big), got["prob"][big])

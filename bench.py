@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--nnz", type=int, default=50_000_000, help="observed ratings per GPU")
     ap.add_argument("--ncand", type=int, default=100_000_000, help="candidates per GPU")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--pool", default="tiled", choices=["tiled", "flat"],
                     help="candidate pool layout for the device-resident scoring phase")
     ap.add_argument("--layout", default="auto", choices=["auto", "rows", "tiled"],

@@ -194,3 +194,29 @@ def test_shims_resolve_to_the_mirror():
         "print('ok')\n" % (root, os.path.join(root, "shims")))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_which_indices_fast_paths_equal_numpy_indexing():
+    """BayesianPMF._which_indices (host side of bayes_pmf.py:433-455's `[which]`): the index-pair
+    and mask fast paths give exactly what indexing the n x m grids gives, in the same order"""
+    from active_matrix_factorization_b200 import bayes_pmf
+    rng = np.random.RandomState(0)
+    n, m = 7, 9
+    R = np.column_stack((rng.randint(0, n, 20), rng.randint(0, m, 20), rng.randint(1, 6, 20))).astype(float)
+    R[0, :2] = (n - 1, m - 1)
+    b = bayes_pmf.BayesianPMF(R, 2)
+    ii, jj = np.meshgrid(np.arange(n), np.arange(m), indexing='ij')
+    mask = rng.uniform(size=(n, m)) < .4
+    cases = [Ellipsis, None, mask, np.nonzero(mask), (np.array([0, 6, 3]), np.array([8, 0, 4])),
+             (np.array([[0, 1], [2, 3]]), np.array([[4, 5], [6, 7]])),      # 2-D index arrays
+             (np.array([-1, 2]), np.array([0, -2])),                        # negative ids wrap
+             (slice(1, 4), np.array([0, 2])), ([1, 2], [3, 4]),
+             (np.array([], dtype=int), np.array([], dtype=int))]
+    for which in cases:
+        w = Ellipsis if which is None else which
+        gi, gj, shape = b._which_indices(which)
+        assert shape == ii[w].shape
+        np.testing.assert_array_equal(gi, ii[w].reshape(-1))
+        np.testing.assert_array_equal(gj, jj[w].reshape(-1))
+    with pytest.raises(IndexError):
+        b._which_indices((np.array([n]), np.array([0])))

@@ -146,6 +146,27 @@ def combine_loss_grad(dU, dV, sums, world, rank, group=None, grads_flat=None):
     dist.all_reduce(sums, group=group)
 
 
+def user_range_params(params, rank):
+    """Ratings sharded by USER RANGE: a rank owns its user rows outright, so
+    their prior term is its own; only V's prior has to be counted once."""
+    if rank == 0:
+        return params
+    return type(params)(params.sigma_sq, params.sigma_u_sq, math.inf, params.mean_offset)
+
+
+def combine_loss_grad_user_range(dV, sums, world, rank, group=None):
+    """User-range sharding: dU rows are rank-private and complete after the local pass; only dV
+    (M x d instead of (N + M) x d) and the three sums travel.  The squared error and |U|^2
+    (disjoint rows) add up over the ranks, |V|^2 is counted once (rank 0)."""
+    if world == 1:
+        return
+    if rank != 0:
+        sums[2:].zero_()
+    if dV is not None:
+        dist.all_reduce(dV, group=group)
+    dist.all_reduce(sums, group=group)
+
+
 def alloc_grads(U, V):
     """(dU, dV, flat): gradient buffers shaped like U and V that share one allocation, so that a
     sharded step can all-reduce both with one collective."""
@@ -157,8 +178,14 @@ class ShardedStep:
     """The benchmarked step: fused loss+gradient over this rank's rating block, then scoring
     of this rank's candidate shard with a fused arg-best, each followed by its collective."""
 
-    def __init__(self, rat, d, name, world=1, rank=0):
+    def __init__(self, rat, d, name, world=1, rank=0, grad_shard='ratings'):
         self.rat, self.d, self.name, self.world, self.rank = rat, d, name, world, rank
+        # 'ratings': every rank holds a block of the rating list over ALL users, dU and dV are
+        # all-reduced (north_star's scheme).  'users': a rank holds the ratings of its own user
+        # range and its own rows of U; dU needs no collective, only dV is all-reduced.
+        if grad_shard not in ('ratings', 'users'):
+            raise ValueError("grad_shard must be 'ratings' or 'users'")
+        self.grad_shard = grad_shard
         self.index_base = 0
         self._rec = None
         self.pool = None          # optional scoring.Pool (tiled layout) for the pred criterion
@@ -186,6 +213,10 @@ class ShardedStep:
         SMs; measured on 2 and 8 B200s it does not pay (0.764 vs 0.780 ms and 1.412 vs 1.386 ms,
         benchmarks/check_sharded_grad.py), so one all-reduce after both passes is the default."""
         from . import device as D
+        if self.grad_shard == 'users' and self.world > 1:
+            D.loss_grad(self.rat, self.d, U, V, user_range_params(params, self.rank), dU, dV, sums)
+            combine_loss_grad_user_range(dV, sums, self.world, self.rank)
+            return
         prm = prior_once_params(params, self.rank)
         if self.world == 1:
             D.loss_grad(self.rat, self.d, U, V, prm, dU, dV, sums)

@@ -45,6 +45,11 @@ def parse_args():
                     help="candidate pool layout for the device-resident scoring phase")
     ap.add_argument("--layout", default="auto", choices=["auto", "rows", "tiled"],
                     help="rating-list copy the fused loss+gradient runs on (amf_ratings_set_layout)")
+    ap.add_argument("--grad-shard", default="ratings", choices=["ratings", "users"],
+                    help="multi-GPU gradient: 'ratings' = rating blocks over all users, all-reduce of "
+                         "dU and dV (north_star's scheme, default); 'users' = each GPU owns the ratings "
+                         "and the U rows of its own user range (the matrix has --users x N rows), only "
+                         "dV is all-reduced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     return ap.parse_args()
@@ -358,7 +363,7 @@ def run_ours(a):
     sums = torch.zeros(3, dtype=torch.float64, device=U.device)
     best = torch.zeros(2, dtype=torch.int64, device=U.device)
     params = D.pmf_params(1.0, 10.0, 10.0, 0.0)
-    step = P.ShardedStep(rat, d, name, world, rank)
+    step = P.ShardedStep(rat, d, name, world, rank, grad_shard=a.grad_shard)
     pool_ms = None
     if a.pool == "tiled":
         from active_matrix_factorization_b200 import scoring as S
@@ -496,7 +501,11 @@ def run_ours(a):
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": name, "data": "synthetic",
         "config": {"workload": workload_name(a), "criterion": "pred (MAP prediction) with fused arg-max, winner only", "pool_layout": a.pool,
-                   "parallelism": "candidates and ratings sharded per GPU (weak), NCCL all-reduce of dU/dV/sums + all-gather of winners" if world > 1 else "single GPU",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   "candidates and ratings sharded per GPU (weak), NCCL all-reduce of dU/dV/sums + all-gather of winners"
+                                   if a.grad_shard == "ratings" else
+                                   "candidates sharded per GPU, ratings and U rows sharded by user range (%d users per GPU), "
+                                   "NCCL all-reduce of dV/sums + all-gather of winners" % n),
                    "l2": "inputs larger than L2 (rating list %.0f MB per side, packed candidate pool %.0f MB per GPU)" % (nnz * 8 / 1e6, ncand * 4 / 1e6),
                    "rating_layout": "tiled" if tiled_grad else "rows",
                    "value_is": "candidates / scoring-phase time; ms_per_step covers gradient + scoring"},

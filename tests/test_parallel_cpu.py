@@ -59,6 +59,26 @@ def _worker(rank, world, port, out):
         assert np.allclose(fV.numpy(), fv, rtol=1e-12, atol=1e-12)
         assert torch.equal(s2, sums)
 
+        # ---- gradient, sharded by USER RANGE: own rows of U and dU stay local, only dV travels -
+        u_lo, u_hi = P.shard_bounds(n, world, rank)
+        mine = (R[:, 0] >= u_lo) & (R[:, 0] < u_hi)
+        R_loc = R[mine].copy()
+        R_loc[:, 0] -= u_lo                                  # local user ids
+        U_loc = U[u_lo:u_hi]
+        prm = P.user_range_params(N.PmfParams(.7, 5., 9., 0.), rank)
+        assert prm.sigma_u_sq == 5. and (prm.sigma_v_sq == 9. if rank == 0 else np.isinf(prm.sigma_v_sq))
+        # every local row must exist for the oracle's shape inference: pass the tables explicitly
+        gu, gv = O.gradient(R_loc, U_loc, V, sigma_sq=prm.sigma_sq, sigma_u_sq=prm.sigma_u_sq,
+                            sigma_v_sq=prm.sigma_v_sq)
+        resid = R_loc[:, 2] - O.predictions(R_loc, U_loc, V)
+        s3 = torch.tensor([float(resid @ resid), float((U_loc * U_loc).sum()), float((V * V).sum())],
+                          dtype=torch.float64)
+        dV = torch.from_numpy(gv.copy())
+        P.combine_loss_grad_user_range(dV, s3, world, rank)
+        assert np.allclose(gu, fu[u_lo:u_hi], rtol=1e-12, atol=1e-12)      # no collective for dU
+        assert np.allclose(dV.numpy(), fv, rtol=1e-12, atol=1e-12)
+        assert np.allclose(s3.numpy(), [full @ full, (U * U).sum(), (V * V).sum()], rtol=1e-12)
+
         # ---- scoring: candidate shards, winner all-gather --------------------------------------
         lo, hi = P.shard_bounds(ncand, world, rank)
         for maximize in (True, False):

@@ -329,9 +329,41 @@ def case_continuous():
          cand_j=np.array([c[1] for c in cand]), simps_entropy=simps, summed_entropy=summed)
 
 
+# ---- case 9: one-step lookahead, prediction-entropy bound, Bayesian expected variance ----
+def case_more():
+    import contextlib, io
+    g = np.load(os.path.join(HERE, "lookahead_6x7_d2.npz"))
+    a = ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)
+    a.users, a.items = g["users"].copy(), g["items"].copy()
+    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+    cand = list(zip(g["cand_i"].tolist(), g["cand_j"].tolist()))[:4]
+    out = dict(cand_i=np.array([c[0] for c in cand]), cand_j=np.array([c[1] for c in cand]))
+    out["pred_covs"] = a.approx_pred_covs()                       # active_pmf.py:324-390
+    out["pred_entropy_bound"] = a._pred_entropy_bound()           # :559-574
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["onestep_ge_half"] = np.array([a.onestep_ge_half(c) for c in cand])      # :459-500
+        out["onestep_ge_half_approx"] = np.array([a.onestep_ge_half_approx(c) for c in cand])
+        out["exp_pred_entropy_bound"] = np.array([a.exp_pred_entropy_bound(c) for c in cand[:2]])
+    # Bayesian lookahead (bayes_pmf.py:457-525,560-602) from the chain of the gibbs fixture:
+    # categorical fit over the rating values, and the normal fit integrated at 5 ppf points
+    gg = np.load(os.path.join(HERE, "gibbs_15x12_d3.npz"))
+    for tag, kw in (("disc", dict(rating_values=(1, 2, 3, 4, 5), discrete_expectations=True)),
+                    ("cont", dict(rating_values=None, discrete_expectations=False,
+                                  num_integration_pts=5))):
+        b = BayesianPMF(gg["ratings"], 3, **kw)
+        b.users, b.items = gg["users"].copy(), gg["items"].copy()
+        samples = list(zip(gg["samples_u"], gg["samples_v"]))
+        which = tuple(np.array(sorted(b.unrated)[:2]).T)
+        np.random.seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out["ev_" + tag] = b.exp_variance(samples, which=which, num_samps=3, fit_first=False)
+        out["ev_cand_i"], out["ev_cand_j"] = which
+    save("more_criteria", **out)
+
+
 if __name__ == "__main__":
     cases = dict(known_answer=case_known_answer, d5=case_d5, fit=case_fit,
                  lookahead=case_lookahead, gibbs=case_gibbs, matrix_normal=case_matrix_normal,
-                 extras=case_extras, continuous=case_continuous)
+                 extras=case_extras, continuous=case_continuous, more=case_more)
     for name in (sys.argv[1:] or list(cases)):
         cases[name]()

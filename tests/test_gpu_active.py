@@ -161,6 +161,26 @@ def test_pred_entropy_bound_and_onestep_match_oracle_restatement(A, golden):
     assert np.isfinite(val) and 0 <= val <= 2
 
 
+def test_onestep_and_entropy_bound_golden(A, golden):
+    """One-step lookahead utility (active_pmf.py:459-500), approx_pred_covs and the prediction-
+    entropy bound with its lookahead expectation (:324-390,559-589) against the reference's own
+    values (tests/golden/more_criteria.npz).  Measured on B200: 1e-12 / 2e-16 / 9e-10 relative
+    (benchmarks/dump_more_criteria.py); the lookahead ones carry the re-fit's sensitivity."""
+    g, c = golden("lookahead_6x7_d2"), golden("more_criteria")
+    a = A.ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)
+    a.compute_dtype = "f64"
+    a.users, a.items = g["users"].copy(), g["items"].copy()
+    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+    cand = list(zip(c["cand_i"].tolist(), c["cand_j"].tolist()))
+    np.testing.assert_allclose(a.approx_pred_covs(), c["pred_covs"], rtol=1e-10, atol=1e-12)
+    assert a._pred_entropy_bound() == pytest.approx(float(c["pred_entropy_bound"]), rel=1e-10)
+    np.testing.assert_allclose([a.onestep_ge_half(ij) for ij in cand], c["onestep_ge_half"], rtol=1e-6)
+    np.testing.assert_allclose([a.onestep_ge_half_approx(ij) for ij in cand],
+                               c["onestep_ge_half_approx"], rtol=1e-6)
+    np.testing.assert_allclose([a.exp_pred_entropy_bound(ij) for ij in cand[:2]],
+                               c["exp_pred_entropy_bound"], rtol=1e-5)
+
+
 def test_copy_and_pickle_keep_approximation(A, golden):
     g = golden("lookahead_6x7_d2")
     a = A.ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)

@@ -175,3 +175,24 @@ def test_dense_sample_stats_match_numpy_and_the_gather_kernel(Bm, n, m, d, S, dt
     np.testing.assert_allclose(b.pred_variance(samples, which=big), got["var"][big],
                                rtol=tol, atol=tol * scale * scale)
     np.testing.assert_array_equal(b.prob_ge_cutoff(samples, 3.5, which=big), got["prob"][big])
+
+
+@pytest.mark.parametrize("tag,kw", [("disc", dict(rating_values=(1, 2, 3, 4, 5), discrete_expectations=True)),
+                                    ("cont", dict(rating_values=None, discrete_expectations=False,
+                                                  num_integration_pts=5))])
+def test_exp_variance_golden(Bm, golden, tag, kw):
+    """Bayesian lookahead (bayes_pmf.py:457-525,560-602): for every candidate and rating value a
+    copy of the model gets the rating and runs its own short chain from the global numpy stream,
+    in the reference's draw order -- seeded, it reproduces the reference's expected total variance
+    (categorical fit summed over the values; normal fit integrated over ppf points).  Measured on
+    B200: 4e-8 relative (the compiled reference rounds alpha / denom to C floats)."""
+    g, c = golden("gibbs_15x12_d3"), golden("more_criteria")
+    b = Bm.BayesianPMF(g["ratings"], 3, **kw)
+    b.compute_dtype = "f64"
+    b.users, b.items = g["users"].copy(), g["items"].copy()
+    samples = list(zip(g["samples_u"], g["samples_v"]))
+    which = (c["ev_cand_i"], c["ev_cand_j"])
+    assert [tuple(x) for x in np.array(which).T] == sorted(b.unrated)[:2]
+    np.random.seed(5)
+    ev = b.exp_variance(samples, which=which, num_samps=3, fit_first=False)
+    np.testing.assert_allclose(ev, c["ev_" + tag], rtol=1e-6)

@@ -348,7 +348,7 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         res = np.empty(shape)
         res.fill(np.nan)
         for idx, exp in enumerate(exps):
-            res.flat[idx] = exp
+            res.flat[idx] = np.float32(exp)          # `exp = cython.float` in bayes_pmf.pxd
         return res
 
 

@@ -114,3 +114,36 @@ def test_mirror_wishart_is_host_algebra(g):
     np.testing.assert_allclose(bayes_pmf.sample_wishart(S, 7), g["wishart_direct"], rtol=1e-12)
     np.testing.assert_allclose(bayes_pmf.sample_wishart(S, 120), g["wishart_bartlett"], rtol=1e-12)
     np.testing.assert_allclose(bayes_pmf.sample_wishart(S, 6.5), g["wishart_bartlett_frac"], rtol=1e-12)
+
+
+def test_pred_covs_entropy_bound_and_onestep(golden):
+    """a14 / a17 rows: prediction covariance by Isserlis' theorem, its log-det bound, and the
+    one-step lookahead utility, against the reference (tests/golden/more_criteria.npz)."""
+    gl, c = golden("lookahead_6x7_d2"), golden("more_criteria")
+    R, U, V, mean, cov = gl["ratings"], gl["users"], gl["items"], gl["mean"], gl["cov"]
+    u, v = O.index_maps(6, 7, 2)
+    np.testing.assert_allclose(O.pred_covs(u, v, mean, cov), c["pred_covs"], rtol=1e-9, atol=1e-11)
+    assert O.pred_entropy_bound(u, v, mean, cov) == pytest.approx(float(c["pred_entropy_bound"]), rel=1e-10)
+    unrated = list(zip(gl["cand_i"].tolist(), gl["cand_j"].tolist()))     # all unknown cells
+    i, j = int(c["cand_i"][1]), int(c["cand_j"][1])
+    one = O.lookahead_discrete(R, u, v, mean, cov, U, V, i, j, (0, 1), ("onestep", .5, unrated))
+    assert one == pytest.approx(float(c["onestep_ge_half"][1]), rel=1e-6)
+    one_a = O.lookahead_discrete(R, u, v, mean, cov, U, V, i, j, (0, 1), ("onestep", .5, unrated),
+                                 use_map=False)
+    assert one_a == pytest.approx(float(c["onestep_ge_half_approx"][1]), rel=1e-6)
+    i, j = int(c["cand_i"][0]), int(c["cand_j"][0])
+    peb = O.lookahead_discrete(R, u, v, mean, cov, U, V, i, j, (0, 1), "pred_entropy_bound")
+    assert peb == pytest.approx(float(c["exp_pred_entropy_bound"][0]), rel=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["disc", "cont"])
+def test_bayes_exp_variance(golden, tag):
+    """a24: Bayesian lookahead from a seeded stream against the reference."""
+    g, c = golden("gibbs_15x12_d3"), golden("more_criteria")
+    samples = list(zip(g["samples_u"], g["samples_v"]))
+    cells = list(zip(c["ev_cand_i"].tolist(), c["ev_cand_j"].tolist()))
+    np.random.seed(5)
+    ev = O.bayes_exp_variance(g["ratings"], g["users"], g["items"], samples, cells,
+                              rating_values=(1, 2, 3, 4, 5) if tag == "disc" else None,
+                              num_samps=3, num_integration_pts=5)
+    np.testing.assert_allclose(ev, c["ev_" + tag], rtol=1e-6)

@@ -361,9 +361,36 @@ def case_more():
     save("more_criteria", **out)
 
 
+# ---- case 10: the reference's own test_normal_exps.py inputs, with its Cython answers ----
+def case_moments():
+    """Same distributions as check_expectation / test_exp_dotprod_sq of the reference's
+    test_normal_exps.py (mean ~ N(0, 10), cov = project_psd(N(0, 5)^{dim x dim}, 1e-5)), three
+    draws per function, evaluated by the compiled normal_exps_cy."""
+    cy = ref.normal_exps_cy
+    psd = ref.active_pmf.project_psd
+    np.random.seed(42)
+    out = {}
+    for name, dim in (("tripexpect", 3), ("quadexpect", 4), ("exp_squared", 2), ("exp_a2bc", 3)):
+        for t in range(3):
+            mn = np.random.normal(0, 10, (dim,))
+            cov = psd(np.random.normal(0, 5, (dim, dim)), 1e-5)
+            out["%s_mean%d" % (name, t)], out["%s_cov%d" % (name, t)] = mn, cov
+            out["%s_val%d" % (name, t)] = getattr(cy, name)(mn, cov, *range(dim))
+    n, m, d = 1, 1, 3
+    k = (n + m) * d
+    u = np.arange(0, n * d).reshape(n, d).T
+    v = np.arange(n * d, (n + m) * d).reshape(m, d).T
+    for t in range(3):
+        mn = np.random.normal(0, 10, (k,))
+        cov = psd(np.random.normal(0, 5, (k, k)), 1e-5)
+        out["exp_dotprod_sq_mean%d" % t], out["exp_dotprod_sq_cov%d" % t] = mn, cov
+        out["exp_dotprod_sq_val%d" % t] = cy.exp_dotprod_sq(u, v, mn, cov, 0, 0)
+    save("moments", **out)
+
+
 if __name__ == "__main__":
     cases = dict(known_answer=case_known_answer, d5=case_d5, fit=case_fit,
                  lookahead=case_lookahead, gibbs=case_gibbs, matrix_normal=case_matrix_normal,
-                 extras=case_extras, continuous=case_continuous, more=case_more)
+                 extras=case_extras, continuous=case_continuous, more=case_more, moments=case_moments)
     for name in (sys.argv[1:] or list(cases)):
         cases[name]()

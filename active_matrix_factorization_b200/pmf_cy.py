@@ -117,6 +117,12 @@ class ProbabilisticMatrixFactorization(object):
             self.users, self.items = init
         return self
 
+    @classmethod
+    def from_coo_file(cls, path, latent_d=1, subtract_mean=False, **kw):
+        """``from_coo`` on the rating list of a data file (see ``load_coo`` for the formats)."""
+        i, j, r, n, m = load_coo(path)
+        return cls.from_coo(i, j, r, n, m, latent_d, subtract_mean, **kw)
+
     # ---- host <-> device bookkeeping -----------------------------------------------------
     @property
     def dtype_name(self):
@@ -632,6 +638,60 @@ class ProbabilisticMatrixFactorization(object):
     def save_latent_vectors(self, prefix):
         self.users.dump(prefix + "%sd_users.pickle" % self.latent_d)
         self.items.dump(prefix + "%sd_items.pickle" % self.latent_d)
+
+
+def load_coo(path):
+    """Rating list of a data file as (i, j, r, num_users, num_items) for ``from_coo`` -- the
+    large-data companion of the reference's ``.npz`` / ``.pkl`` dictionaries
+    (choose_training.py:215-259, active_pmf.py:1200-1219), which always pass through an (nnz, 3)
+    float64 array.  Accepted: ``.npz`` with arrays ``i, j, r`` (any integer / float dtypes, read
+    memory-mapped when the archive is not compressed) and optionally ``shape``; ``.npz`` / ``.pkl``
+    with the reference's ``_ratings`` (nnz, 3) table and optionally ``_real`` (its shape gives the
+    matrix shape); ``.npy`` with an (nnz, 3) table; anything else is read as whitespace-
+    separated ``i j r`` text lines.  Without an explicit shape it is ``max id + 1`` per side, as in
+    the reference's constructor (pmf_cy.pyx:65-66).  Ids must be non-negative."""
+    import pickle
+    shape = None
+    if path.endswith('.npz') or path.endswith('.pkl'):
+        if path.endswith('.pkl'):
+            with open(path, 'rb') as f:
+                data = pickle.load(f)
+        else:
+            data = np.load(path, mmap_mode='r', allow_pickle=True)
+        keys = set(data.keys())
+        if {'i', 'j', 'r'} <= keys:
+            i, j, r = data['i'], data['j'], data['r']
+            if 'shape' in keys:
+                shape = tuple(int(x) for x in np.asarray(data['shape']).reshape(-1)[:2])
+        elif '_ratings' in keys:
+            table = np.asarray(data['_ratings'])
+            i, j, r = table[:, 0], table[:, 1], table[:, 2]
+            if '_real' in keys and data['_real'] is not None and np.ndim(data['_real']) == 2:
+                shape = tuple(np.shape(data['_real']))
+        else:
+            raise ValueError("%s holds neither i/j/r arrays nor a _ratings table" % path)
+    elif path.endswith('.npy'):
+        table = np.load(path, mmap_mode='r')
+        if table.ndim != 2 or table.shape[1] != 3:
+            raise TypeError("invalid rating tuple length")
+        i, j, r = table[:, 0], table[:, 1], table[:, 2]
+    else:
+        table = np.loadtxt(path, ndmin=2)
+        if table.shape[1] != 3:
+            raise TypeError("invalid rating tuple length")
+        i, j, r = table[:, 0], table[:, 1], table[:, 2]
+    i = np.ascontiguousarray(i).astype(np.int32, copy=False)
+    j = np.ascontiguousarray(j).astype(np.int32, copy=False)
+    r = np.ascontiguousarray(r)
+    if not (i.shape == j.shape == r.shape and i.ndim == 1):
+        raise TypeError("i, j, r must be three vectors of one length")
+    if i.size and (i.min() < 0 or j.min() < 0):
+        raise ValueError("negative user / item id")
+    if shape is None:
+        shape = (int(i.max()) + 1 if i.size else 0, int(j.max()) + 1 if j.size else 0)
+    if i.size and (i.max() >= shape[0] or j.max() >= shape[1]):
+        raise ValueError("ids outside the %d x %d matrix" % shape)
+    return i, j, r, int(shape[0]), int(shape[1])
 
 
 def _rebuild(cls, state):

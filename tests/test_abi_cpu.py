@@ -220,3 +220,40 @@ def test_which_indices_fast_paths_equal_numpy_indexing():
         np.testing.assert_array_equal(gj, jj[w].reshape(-1))
     with pytest.raises(IndexError):
         b._which_indices((np.array([n]), np.array([0])))
+
+
+def test_load_coo_formats(tmp_path):
+    """pmf_cy.load_coo: the same rating list through every accepted file form"""
+    import pickle
+    from active_matrix_factorization_b200 import pmf_cy
+    rng = np.random.RandomState(1)
+    i, j = rng.randint(0, 30, 200), rng.randint(0, 17, 200)
+    i[0], j[0] = 29, 16
+    r = rng.normal(size=200)
+    table = np.column_stack((i, j, r)).astype(float)
+    real = np.zeros((40, 20))
+    np.savez(tmp_path / "a.npz", i=i.astype(np.int64), j=j.astype(np.int16), r=r.astype(np.float32))
+    np.savez(tmp_path / "b.npz", i=i, j=j, r=r, shape=np.array([40, 20]))
+    np.savez_compressed(tmp_path / "c.npz", _ratings=table, _real=real, _rating_vals=np.array([1, 2]))
+    with open(tmp_path / "d.pkl", "wb") as f:
+        pickle.dump({"_ratings": table, "_real": None}, f)
+    np.save(tmp_path / "e.npy", table)
+    np.savetxt(tmp_path / "f.txt", table)
+    want = {"a.npz": (30, 17), "b.npz": (40, 20), "c.npz": (40, 20), "d.pkl": (30, 17),
+            "e.npy": (30, 17), "f.txt": (30, 17)}
+    for name, shape in want.items():
+        gi, gj, gr, n, m = pmf_cy.load_coo(str(tmp_path / name))
+        assert (n, m) == shape, name
+        assert gi.dtype == np.int32 and gj.dtype == np.int32
+        np.testing.assert_array_equal(gi, i)
+        np.testing.assert_array_equal(gj, j)
+        np.testing.assert_allclose(gr, r, rtol=1e-6 if name == "a.npz" else 1e-15)
+    np.savez(tmp_path / "bad.npz", i=i, j=j, r=r, shape=np.array([10, 20]))
+    with pytest.raises(ValueError):
+        pmf_cy.load_coo(str(tmp_path / "bad.npz"))
+    np.savez(tmp_path / "bad2.npz", x=i)
+    with pytest.raises(ValueError):
+        pmf_cy.load_coo(str(tmp_path / "bad2.npz"))
+    np.save(tmp_path / "bad3.npy", table[:, :2])
+    with pytest.raises(TypeError):
+        pmf_cy.load_coo(str(tmp_path / "bad3.npy"))

@@ -2,8 +2,8 @@
 
 Same names and conventions -- ``ActivePMF``, the criterion methods with their
 ``do_normal_fit / spawn_processes / nice_name / chooser`` attributes, ``KEY_FUNCS``,
-``pick_query_point / _get_key_vals / get_key_evals``, ``full_test``, ``compare``, ``main`` --
-but the pool of candidates is evaluated in batched GPU launches instead of a Python map over
+``pick_query_point / _get_key_vals / get_key_evals`` (the experiment drivers of the same file
+are run from the reference's own source by ``drivers.load``) -- but the pool of candidates is evaluated in batched GPU launches instead of a Python map over
 ``multiprocessing.Pool`` workers:
 
 * cheap criteria (pred, prob-ge-*, pred-variance): one scoring launch with a fused arg-best;
@@ -643,111 +643,9 @@ def _pred_covs(mean, cov, n, m, d):
 
 
 ################################################################################
-### Drivers (active_pmf.py:796-1257)
-
-def full_test(apmf, real, picker_key=ActivePMF.pred_variance, fit_normal=True,
-              fit_sigmas=False, processes=None):
-    '''Serial active-learning loop (active_pmf.py:796-850).'''
-    print("Training PMF")
-    if fit_sigmas:
-        apmf.fit_with_sigmas()
-    else:
-        apmf.do_fit()
-    apmf.initialize_approx()
-    if fit_normal:
-        print("Fitting normal")
-        apmf.fit_normal()
-        print("Mean diff of means: %g; mean cov %g" % (apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
-
-    total = apmf.num_users * apmf.num_items
-    rmse = apmf.rmse(real)
-    print("RMSE: {:.5}".format(rmse))
-    yield len(apmf.rated), rmse, None, None
-
-    while apmf.unrated:
-        print()
-        print("Picking a query point...")
-        if len(apmf.unrated) == 1:
-            i, j = next(iter(apmf.unrated))
-            vals = None
-        else:
-            pool = list(apmf.unrated)
-            vals = apmf._get_key_vals(pool, picker_key, processes, None)
-            i, j = picker_key.chooser(zip(pool, vals), key=operator.itemgetter(1))[0]
-
-        apmf.add_rating(i, j, real[i, j])
-        print("Queried (%d, %d); %d/%d known" % (i, j, len(apmf.rated), total))
-
-        print("Training PMF")
-        for _ll in apmf.fit_lls():
-            pass
-        if fit_normal:
-            print("Fitting normal")
-            for kl in apmf.fit_normal_kls():
-                assert kl > -1e5
-            print("Mean diff of means: %g; mean cov %g" % (apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
-
-        rmse = apmf.rmse(real)
-        print("RMSE: {:.5}".format(rmse))
-        yield len(apmf.rated), rmse, (i, j), vals
-
-
-def _in_between_work(apmf, i, j, realval, total, fit_normal, fit_sigmas, name):
-    '''(active_pmf.py:853-868)'''
-    apmf.add_rating(i, j, realval)
-    print("{:<40} Queried ({}, {}); {}/{} known".format(name, i, j, len(apmf.rated), total))
-    if fit_sigmas:
-        apmf.fit_with_sigmas()
-    else:
-        apmf.do_fit()
-    if fit_normal:
-        if apmf.refit_lookahead:
-            apmf.initialize_approx()
-        apmf.fit_normal()
-    return apmf
-
-
-class _InlinePool(object):
-    '''Stand-in for multiprocessing.Pool in the threaded driver: the GPU does the fan-out, so
-    work submitted to the "pool" runs in the calling thread.'''
-    def apply(self, fn, args=(), kwds=None):
-        return fn(*args, **(kwds or {}))
-
-    def map(self, fn, it):
-        return [fn(x) for x in it]
-
-    def close(self):
-        pass
-
-    def join(self):
-        pass
-
-
-def _full_test_threaded(apmf, real, picker_key, fit_normal, fit_sigmas, worker_pool):
-    '''(active_pmf.py:871-898)'''
-    total = real.size
-    name = picker_key.nice_name
-    rmse = apmf.rmse(real)
-    print("{:<40} Initial RMSE: {:.5}".format(name, rmse))
-    yield len(apmf.rated), rmse, None, None
-
-    while apmf.unrated:
-        n = len(apmf.rated) + 1
-        print("{:<40} Picking query point {}...".format(name, n))
-        if len(apmf.unrated) == 1:
-            vals = np.empty((apmf.num_users, apmf.num_items))
-            vals.fill(np.nan)
-            i, j = next(iter(apmf.unrated))
-        else:
-            vals = apmf.get_key_evals(key=picker_key, worker_pool=worker_pool)
-            i, j = picker_key.chooser(apmf.unrated, key=vals.__getitem__)
-
-        apmf = worker_pool.apply(_in_between_work,
-                                 (apmf, i, j, real[i, j], total, fit_normal, fit_sigmas, name))
-        rmse = apmf.rmse(real)
-        print("{:<40} RMSE {}: {:.5}".format(picker_key.nice_name, n, rmse))
-        yield len(apmf.rated), rmse, (i, j), vals
-
+### Registry (active_pmf.py:901-923).  The experiment drivers of active_pmf.py:796-1257
+### (full_test, compare, make_fake_data, get_ratings, main) are not restated here:
+### drivers.load("active_pmf", ref_dir) runs the reference's own against these classes.
 
 KEY_FUNCS = {
     "random": ActivePMF.random_weighting,
@@ -772,279 +670,3 @@ KEY_FUNCS = {
     "1step-ge-.5": ActivePMF.onestep_ge_half,
     "1step-ge-.5-approx": ActivePMF.onestep_ge_half_approx,
 }
-
-
-def make_fake_data(noise=.25, num_users=10, num_items=10, mask_type=0, data_type='float',
-                   rank=5, u_mean=0, u_std=2, v_mean=0, v_std=2):
-    '''(active_pmf.py:926-960) same RNG draws in the same order'''
-    u = np.random.normal(u_mean, u_std, (num_users, rank))
-    v = np.random.normal(v_mean, v_std, (num_items, rank))
-    real = np.dot(u, v.T)
-    if noise:
-        real += np.random.normal(0, noise, (num_users, num_items))
-
-    if data_type == 'float':
-        vals = None
-    elif data_type == 'int':
-        real = np.round(real).astype(int)
-        vals = None
-    elif data_type == 'int-bounds':
-        real = np.round(real).astype(int)
-        lo, hi = real.min(), real.max()
-        vals = range(int(np.floor(lo * 1.2 if lo < 0 else lo * .8)),
-                     int(np.ceil(hi * 1.2 if hi > 0 else hi * .8)))
-    elif data_type == 'binary':
-        real = (real > .5).astype(int)
-        vals = {0, 1}
-    elif isinstance(data_type, numbers.Integral):
-        real = np.minimum(np.maximum(np.round(real), 0), data_type).astype(int)
-        vals = range(data_type + 1)
-    else:
-        raise ValueError("Don't know how to interpret data_type '{}'".format(data_type))
-
-    ratings = get_ratings(real, mask_type)
-    return real, ratings, vals
-
-
-def get_ratings(real, mask_type=0):
-    '''(active_pmf.py:963-1010)'''
-    num_users, num_items = real.shape
-    if isinstance(mask_type, numbers.Real):
-        mask = np.random.binomial(1, mask_type, real.shape)
-    elif mask_type in {'diag', 'diagonal', 'diag-plus', 'diag-block'}:
-        mask = np.zeros_like(real)
-        np.fill_diagonal(mask, 1)
-        if mask_type == 'diag-plus':
-            if num_users != num_items:
-                warnings.warn("can't do diag-plus for non-square; doing diag")
-            else:
-                n = num_users
-                mask[-1, 1] = 1
-                mask[range(1, n - 1), range(2, n)] = 1
-        elif mask_type == 'diag-block':
-            if num_users != num_items:
-                warnings.warn("can't do diag-block for non-square; doing diag")
-            else:
-                mask[:num_users // 2, :num_items // 2] = 1
-    else:
-        raise ValueError("Don't know how to interpret mask_type '{}'".format(mask_type))
-
-    for zero_col in np.logical_not(mask.sum(axis=0)).nonzero()[0]:
-        mask[random.randrange(num_users), zero_col] = 1
-    for zero_row in np.logical_not(mask.sum(axis=1)).nonzero()[0]:
-        mask[zero_row, random.randrange(num_items)] = 1
-    assert np.all(mask.sum(axis=0) > 0)
-    assert np.all(mask.sum(axis=1) > 0)
-
-    ratings = np.zeros((int(mask.sum()), 3))
-    for idx, (i, j) in enumerate(np.transpose(mask.nonzero())):
-        ratings[idx] = [i, j, real[i, j]]
-    return ratings
-
-
-def compare(key_names, latent_d=5, processes=None, do_threading=True, steps=None,
-            discrete_exp=False, refit_lookahead=False, fit_sigmas=False,
-            real_ratings_vals=None, apmf=None, knowable=None,
-            sig_u_mean=0, sig_u_var=-1, sig_v_mean=0, sig_v_var=-1,
-            fit_type=('batch',), **kwargs):
-    '''(active_pmf.py:1013-1092).  `processes` is accepted for compatibility; candidate
-    fan-out happens on the GPU, so no worker processes are forked.'''
-    from threading import Thread, Lock
-
-    if real_ratings_vals is None:
-        real, ratings, rating_vals = make_fake_data(**kwargs)
-    else:
-        real, ratings, rating_vals = real_ratings_vals
-        if apmf:
-            assert (apmf.num_users, apmf.num_items) == real.shape
-            assert np.all(apmf.ratings == ratings)
-            assert set(apmf.rating_values) == set(rating_vals)
-            apmf.discrete_expectations = discrete_exp
-
-    if apmf is None:
-        apmf = ActivePMF(ratings, latent_d=latent_d, rating_values=rating_vals,
-                         discrete_expectations=discrete_exp, refit_lookahead=refit_lookahead,
-                         knowable=knowable, fit_type=fit_type)
-        apmf.sig_u_mean = sig_u_mean
-        apmf.sig_u_var = sig_u_var
-        apmf.sig_v_mean = sig_v_mean
-        apmf.sig_v_var = sig_v_var
-
-        print("Doing initial fit")
-        if fit_sigmas:
-            apmf.fit_with_sigmas()
-        else:
-            apmf.do_fit()
-
-        if any(KEY_FUNCS[name].do_normal_fit for name in key_names):
-            apmf.initialize_approx()
-            print("Initial approximation fit")
-            apmf.fit_normal()
-            print("Mean diff of means: {}; mean cov {}\n".format(
-                apmf.mean_meandiff(), np.abs(apmf.cov.mean())))
-
-    results = {
-        '_real': real,
-        '_ratings': ratings,
-        '_rating_vals': rating_vals,
-        '_initial_apmf': deepcopy(apmf),
-    }
-
-    if do_threading:
-        worker_pool = _InlinePool()
-        worker_pool.access_lock = Lock()
-
-        def eval_key(key_name):
-            key = KEY_FUNCS[key_name]
-            res = _full_test_threaded(deepcopy(apmf), real, key, key.do_normal_fit,
-                                      fit_sigmas, worker_pool)
-            results[key_name] = list(itertools.islice(res, steps))
-
-        threads = [Thread(name=key_name, target=eval_key, args=(key_name,))
-                   for key_name in key_names]
-        for thread in threads:
-            thread.start()
-        for thread in threads:
-            thread.join()
-    else:
-        for key_name in key_names:
-            key = KEY_FUNCS[key_name]
-            res = full_test(deepcopy(apmf), real, key, key.do_normal_fit, fit_sigmas, processes)
-            results[key_name] = list(itertools.islice(res, steps))
-
-    return results
-
-
-def add_bool_opt(parser, name, default=False):
-    parser.add_argument('--' + name, action='store_true', default=default)
-    parser.add_argument('--no-' + name, action='store_false', dest=name.replace('-', '_'))
-
-
-# command line of the reference (active_pmf.py:1109-1160), as data: (group, flags, options)
-_CLI = [
-    ("Model Options", ('--latent-d', '-D'), dict(type=int, default=5)),
-    ("Model Options", ('--discrete-integration',), dict(nargs='?', const=True, default=False)),
-    ("Model Options", ('--continuous-integration',), dict(action='store_false', dest='discrete_integration')),
-    ("Model Options", 'bool', ('fit-sigmas', False)),
-    ("Model Options", 'bool', ('refit-lookahead', False)),
-    ("Model Options", ('--fit',), dict(default='batch')),
-    ("Model Options", ('--sig-u-mean',), dict(type=float, default=0)),
-    ("Model Options", ('--sig-u-var',), dict(type=float, default=-1)),
-    ("Model Options", ('--sig-v-mean',), dict(type=float, default=0)),
-    ("Model Options", ('--sig-v-var',), dict(type=float, default=-1)),
-    ("Problem Definiton", ('--load-data',), dict(default=None, metavar='FILE')),
-    ("Problem Definiton", 'bool', ('load-model', False)),
-    ("Problem Definiton", ('--gen-rank', '-R'), dict(type=int, default=5)),
-    ("Problem Definiton", ('--type',), dict(default='float')),
-    ("Problem Definiton", ('--u-mean',), dict(type=float, default=0)),
-    ("Problem Definiton", ('--u-std',), dict(type=float, default=2)),
-    ("Problem Definiton", ('--v-mean',), dict(type=float, default=0)),
-    ("Problem Definiton", ('--v-std',), dict(type=float, default=2)),
-    ("Problem Definiton", ('--noise', '-n'), dict(type=float, default=.25)),
-    ("Problem Definiton", ('--num-users', '-N'), dict(type=int, default=10)),
-    ("Problem Definiton", ('--num-items', '-M'), dict(type=int, default=10)),
-    ("Problem Definiton", ('--mask', '-m'), dict(default=0)),
-    ("Running", ('--processes', '-P'), dict(type=int, default=None)),
-    ("Running", 'bool', ('threading', True)),
-    ("Running", ('--steps', '-s'), dict(type=int, default=None)),
-    ("Results", ('--save-results',), dict(nargs='?', default=None, const=True, metavar='FILE')),
-    ("Results", ('--no-save-results',), dict(action='store_false', dest='save_results')),
-    ("Results", ('--note',), dict(action='append')),
-]
-
-
-def build_parser(spec, key_names):
-    import argparse
-    parser = argparse.ArgumentParser()
-    groups = {}
-    for group, flags, opts in spec:
-        g = groups.setdefault(group, parser.add_argument_group(group))
-        if flags == 'bool':
-            add_bool_opt(g, *opts)
-        else:
-            g.add_argument(*flags, **opts)
-    parser.add_argument('keys', nargs='*',
-                        help="Choices: {}.".format(', '.join(sorted(key_names))))
-    return parser
-
-
-def main(argv=None):
-    '''Same command line as the reference (active_pmf.py:1100-1257).'''
-    import os
-    import pickle
-    import sys
-
-    key_names = set(KEY_FUNCS.keys())
-    types = {'float', 'int', 'int-bounds', 'binary'}
-    parser = build_parser(_CLI, key_names)
-    args = parser.parse_args(argv)
-
-    try:
-        args.mask = float(args.mask)
-    except ValueError:
-        pass
-    try:
-        args.type = int(args.type)
-    except ValueError:
-        if args.type not in types:
-            raise ValueError("--type must be integer or one of {}".format(', '.join(sorted(types))))
-
-    for k in args.keys:
-        if k not in key_names:
-            sys.stderr.write("Invalid key name %s; options are %s.\n" % (
-                k, ', '.join(sorted(key_names))))
-            sys.exit(1)
-    if not args.keys:
-        args.keys = sorted(key_names)
-
-    if args.save_results is True:
-        args.save_results = 'results.pkl'
-    elif args.save_results:
-        dirname = os.path.dirname(args.save_results)
-        if dirname and not os.path.exists(dirname):
-            os.makedirs(dirname)
-
-    real_ratings_vals = None
-    apmf = None
-    knowable = None
-    if args.load_data:
-        with open(args.load_data, 'rb') as f:
-            data = np.load(f, allow_pickle=True)
-            if isinstance(data, np.ndarray):
-                data = {'_real': data}
-            real = data['_real']
-            real_ratings_vals = (
-                real,
-                data['_ratings'] if '_ratings' in data else get_ratings(real, args.mask),
-                data['_rating_vals'] if '_rating_vals' in data else None,
-            )
-            if args.load_model:
-                apmf = data['_initial_apmf']
-        knowable = np.isfinite(real)
-        knowable[real == 0] = 0
-        knowable = zip(*knowable.nonzero())
-
-    results = compare(args.keys,
-                      num_users=args.num_users, num_items=args.num_items,
-                      real_ratings_vals=real_ratings_vals, apmf=apmf, knowable=knowable,
-                      u_mean=args.u_mean, u_std=args.u_std, v_mean=args.v_mean, v_std=args.v_std,
-                      noise=args.noise, mask_type=args.mask,
-                      rank=args.gen_rank, latent_d=args.latent_d,
-                      discrete_exp=args.discrete_integration,
-                      refit_lookahead=args.refit_lookahead, fit_sigmas=args.fit_sigmas,
-                      sig_u_mean=args.sig_u_mean, sig_u_var=args.sig_u_var,
-                      sig_v_mean=args.sig_v_mean, sig_v_var=args.sig_v_var,
-                      data_type=args.type, steps=args.steps,
-                      fit_type=parse_fit_type(args.fit),
-                      processes=args.processes, do_threading=args.threading)
-
-    if args.save_results:
-        print("saving results in '{}'".format(args.save_results))
-        results['_args'] = args
-        with open(args.save_results, 'wb') as f:
-            pickle.dump(results, f)
-    return results
-
-
-if __name__ == '__main__':
-    main()

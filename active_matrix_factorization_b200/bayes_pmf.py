@@ -146,7 +146,33 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
     def _mean_offset(self):
         return self.mean_rating if self.subtract_mean else 0.
 
-    def _half_sweep(self, rat, side, other_t, mu, alpha, z):
+    # Multi-GPU Gibbs is OPT-IN: set `shard_group` to True (default process
+    # group) or to a torch.distributed group and the rows of every half-sweep of samples() are
+    # split over its ranks.  mu, alpha and z are then rank 0's draws, broadcast, so the ranks
+    # need not be seeded alike and cannot drift apart; single-row calls (sample_feature) and
+    # models without the attribute set never touch the process group.
+    shard_group = None
+
+    def _shard(self):
+        """(world, rank, group) of the opt-in row sharding, (1, 0, None) when it is off"""
+        if self.shard_group is None or self.shard_group is False:
+            return 1, 0, None
+        from . import parallel as P
+        if not (P.dist is not None and P.dist.is_available() and P.dist.is_initialized()):
+            raise RuntimeError("shard_group is set but torch.distributed is not initialised")
+        group = None if self.shard_group is True else self.shard_group
+        return P.dist.get_world_size(group), P.dist.get_rank(group), group
+
+    def _shared_draw(self, t):
+        """rank 0's value of a device tensor on every rank of the shard group"""
+        world, _rank, group = self._shard()
+        if world > 1:
+            from . import parallel as P
+            P.dist.broadcast(t, P.dist.get_global_rank(group, 0) if group is not None else 0,
+                             group=group)
+        return t
+
+    def _half_sweep(self, rat, side, other_t, mu, alpha, z, shard=False):
         '''all conditionals of one side in one launch; returns the new (rows, d) device tensor'''
         lib = N.require_device()
         name = rat.name
@@ -156,21 +182,36 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         alpha_t = D.to_device(np.atleast_2d(alpha), dt)
         mu_t = D.to_device(np.atleast_1d(mu), dt)
         z_t = D.to_device(z, dt)
-        from . import parallel as P
-        world, rank = P.world_rank()
-        lo, hi = P.shard_bounds(rows, world, rank)
+        world, rank, group = self._shard() if shard else (1, 0, None)
+        lo, hi = 0, rows
+        if world > 1:
+            from . import parallel as P
+            for t in (alpha_t, mu_t, z_t):
+                self._shared_draw(t)
+            lo, hi = P.shard_bounds(rows, world, rank)
         N.check(lib.amf_gibbs_half_sweep_rows(rat.handle, side, D.code(name), self.latent_d,
                                               D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
                                               float(self.beta), float(self._mean_offset()),
                                               D.ptr(z_t), D.ptr(out), lo, hi, D.stream_ptr()))
         if world > 1:       # rows of this side are split over the ranks
-            out = P.all_gather_rows(out, rows, world)
+            out = P.all_gather_rows(out, rows, world, group)
         return out
 
-    def _check_gibbs(self, rat):
+    def _check_gibbs(self, rat, shard=False):
+        '''raises like np.linalg.cholesky (bayes_pmf.py:215) if any half-sweep since the last
+        check met a non-positive-definite matrix; the device flag is sticky, and in a sharded
+        chain it is max-reduced first so that every rank raises together'''
         failed = C.c_int(0)
         N.check(N.load().amf_gibbs_status(rat.handle, C.byref(failed), D.stream_ptr()))
-        if failed.value:
+        bad = failed.value
+        world, _rank, group = self._shard() if shard else (1, 0, None)
+        if world > 1:
+            from . import parallel as P
+            dev = torch.device('cuda', torch.cuda.current_device())
+            flag = torch.tensor([bad], dtype=torch.int32, device=dev)
+            P.dist.all_reduce(flag, op=P.dist.ReduceOp.MAX, group=group)
+            bad = int(flag.item())
+        if bad:
             raise np.linalg.LinAlgError("Matrix is not positive definite")
 
     def sample_feature(self, n, is_user, mu, alpha, oth_feats, rated_indices, ratings):
@@ -213,10 +254,10 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
             mu_v, alpha_v = self.sample_hyperparam(item_sample, False)
             for _gibbs in range(num_gibbs):
                 z = np.random.normal(0, 1, (n, d))          # row-major = the reference's per-row draws
-                users_t = self._half_sweep(rat, 0, items_t, mu_u, alpha_u, z)
+                users_t = self._half_sweep(rat, 0, items_t, mu_u, alpha_u, z, shard=True)
                 z = np.random.normal(0, 1, (m, d))
-                items_t = self._half_sweep(rat, 1, users_t, mu_v, alpha_v, z)
-            self._check_gibbs(rat)
+                items_t = self._half_sweep(rat, 1, users_t, mu_v, alpha_v, z, shard=True)
+            self._check_gibbs(rat, shard=True)
             user_sample = users_t.to(torch.float64).cpu().numpy()
             item_sample = items_t.to(torch.float64).cpu().numpy()
             yield user_sample, item_sample
@@ -398,193 +439,6 @@ KEYS = {
 }
 
 
-def fetch_samples(bpmf, num, *args, **kwargs):
-    samps = list(islice(bpmf.samples(*args, **kwargs), num))
-    pred = bpmf.predict(samps)
-    return samps, pred
-
-
-def full_test(bpmf, samples, real, key_name, num_samps=128, lookahead_fit='batch',
-              lookahead_samps=128, pool=None, multieval=False, init_rmse=None, test_on=Ellipsis):
-    '''Active loop driven by posterior samples (bayes_pmf.py:682-729).'''
-    key = KEYS[key_name]
-    total = real.size
-    picker_fn = getattr(bpmf, key.key_fn)
-    chooser = np.argmax if key.choose_max else np.argmin
-
-    if init_rmse is None:
-        init_rmse = bpmf.bayes_rmse(samples, real, which=test_on)
-    yield (len(bpmf.rated), init_rmse, None, None)
-
-    while bpmf.unrated:
-        print("{:<40} Picking query point {}...".format(key.nice_name, len(bpmf.rated) + 1))
-        if len(bpmf.unrated) == 1:
-            vals = None
-            i, j = next(iter(bpmf.unrated))
-        else:
-            unrated = np.array(list(bpmf.unrated)).T
-            which = tuple(unrated)
-            key_kwargs = {'which': which}
-            if key.wants_pool and pool is not None:
-                key_kwargs['pool'] = pool
-            evals = picker_fn(samples, *key.args, **key_kwargs)
-            i, j = unrated[:, chooser(evals)]
-            vals = bpmf.matrix_results(evals, which)
-
-        bpmf.add_rating(i, j, real[i, j])
-        print("{:<40} Queried ({}, {}); {}/{} known".format(key.nice_name, i, j, len(bpmf.rated), total))
-
-        samples, pred = fetch_samples(bpmf, num_samps, fit_first=True)
-        err = rmse(pred[test_on], real[test_on])
-        print("{:<40} RMSE {}: {:.5}".format(key.nice_name, len(bpmf.rated), err))
-        yield len(bpmf.rated), err, (i, j), vals
-
-
-def compare_active(key_names, latent_d, real, ratings, rating_vals=None, discrete=True,
-                   subtract_mean=True, num_steps=None, procs=None, threaded=False,
-                   fit_type=('batch',), num_samps=128, test_set='all', **kwargs):
-    '''(bayes_pmf.py:733-825); `procs` is accepted and ignored (no worker processes).'''
-    knowable = np.isfinite(real)
-    knowable[real == 0] = 0
-    pickable = knowable.copy()
-    pickable[ratings[:, 0].astype(int), ratings[:, 1].astype(int)] = 0
-
-    try:
-        test_set = float(test_set)
-    except ValueError:
-        if test_set != 'all':
-            warnings.warn("dunno what to do with test_set {}".format(test_set))
-            test_set = 'all'
-
-    if test_set == 'all':
-        test_on = knowable
-        query_on = pickable
-    else:
-        if test_set % 1 == 0 and test_set != 1:
-            avail_pts = list(zip(*pickable.nonzero()))
-            picked_indices = random.sample(avail_pts, int(test_set))
-            picker = np.zeros(pickable.shape, bool)
-            picker[tuple(np.transpose(picked_indices))] = 1
-        else:
-            picker = np.random.binomial(1, test_set, size=pickable.shape)
-        test_on = picker * pickable
-        query_on = (1 - picker) * pickable
-
-    query_set = set(zip(*query_on.nonzero()))
-    print("{} points known, {} to query, testing on {}, {} knowable, {} total".format(
-        ratings.shape[0], query_on.sum(), test_on.sum(), knowable.sum(), real.size))
-
-    bpmf_init = BayesianPMF(ratings, latent_d, subtract_mean=subtract_mean,
-                            rating_values=rating_vals, discrete_expectations=discrete,
-                            knowable=query_set, fit_type=fit_type)
-    print("Doing initial MAP fit...")
-    bpmf_init.fit()
-
-    print("Getting initial MCMC samples...")
-    samples = list(islice(bpmf_init.samples(fit_first=fit_type), num_samps))
-    init_rmse = bpmf_init.bayes_rmse(samples, real, test_on)
-    print("Initial RMSE: {}".format(init_rmse))
-    print()
-
-    results = {
-        '_real': real,
-        '_ratings': ratings,
-        '_rating_vals': rating_vals,
-        '_initial_bpmf': deepcopy(bpmf_init),
-    }
-
-    def eval_key(key_name):
-        res = full_test(deepcopy(bpmf_init), samples, real, key_name, pool=None,
-                        multieval=False, num_samps=num_samps, init_rmse=init_rmse,
-                        test_on=test_on, **kwargs)
-        results[key_name] = list(islice(res, num_steps))
-
-    if threaded:
-        threads = [Thread(name=key_name, target=eval_key, args=(key_name,))
-                   for key_name in key_names]
-        for thread in threads:
-            thread.start()
-        for thread in threads:
-            thread.join()
-    else:
-        for key_name in key_names:
-            eval_key(key_name)
-    return results
-
-
-def main(argv=None):
-    '''Same command line as the reference (bayes_pmf.py:828-938).'''
-    import argparse
-    import os
-    import pickle
-    import sys
-
-    key_names = KEYS.keys()
-    parser = argparse.ArgumentParser()
-    for flags, opts in (
-            (('--latent-d', '-D'), dict(type=int, default=5)),
-            (('--steps', '-s'), dict(type=int, default=None)),
-            (('--discrete',), dict(action='store_true', default=None)),
-            (('--no-discrete',), dict(action='store_false', dest='discrete')),
-            (('--subtract-mean',), dict(action='store_true', default=True)),
-            (('--no-subtract-mean',), dict(action='store_false', dest='subtract_mean')),
-            (('--fit',), dict(default='batch')),
-            (('--lookahead-fit',), dict(default='batch')),
-            (('--samps', '-S'), dict(type=int, default=128)),
-            (('--lookahead-samps',), dict(type=int, default=128)),
-            (('--threaded',), dict(action='store_true', default=True)),
-            (('--unthreaded',), dict(action='store_false', dest='threaded')),
-            (('--procs', '-P'), dict(type=int, default=None)),
-            (('--test-set',), dict(default='all')),
-            (('--load-data',), dict(required='True', metavar='FILE')),
-            (('--save-results',), dict(nargs='?', default=True, const=True, metavar='FILE')),
-            (('--no-save-results',), dict(action='store_false', dest='save_results')),
-            (('--note',), dict(action='append')),
-            (('keys',), dict(nargs='*', help="Choices: {}.".format(', '.join(sorted(key_names)))))):
-        parser.add_argument(*flags, **opts)
-    args = parser.parse_args(argv)
-
-    for k in args.keys:
-        if k not in key_names:
-            sys.stderr.write("Invalid key name %s; options are %s.\n" % (
-                k, ', '.join(sorted(key_names))))
-            sys.exit(1)
-    if not args.keys:
-        args.keys = sorted(key_names)
-
-    if args.save_results is True:
-        args.save_results = 'results.pkl'
-    elif args.save_results:
-        dirname = os.path.dirname(args.save_results)
-        if dirname and not os.path.exists(dirname):
-            os.makedirs(dirname)
-
-    with open(args.load_data, 'rb') as f:
-        data = np.load(f, allow_pickle=True)
-        if isinstance(data, np.ndarray):
-            data = {'_real': data}
-        real = data['_real']
-        ratings = data['_ratings']
-        rating_vals = data['_rating_vals'] if '_rating_vals' in data else None
-
-    if args.discrete is None:
-        args.discrete = rating_vals is not None
-
-    results = compare_active(key_names=args.keys, latent_d=args.latent_d, real=real,
-                             ratings=ratings, rating_vals=rating_vals, test_set=args.test_set,
-                             num_steps=args.steps, discrete=args.discrete,
-                             subtract_mean=args.subtract_mean, fit_type=parse_fit_type(args.fit),
-                             lookahead_fit=args.lookahead_fit, num_samps=args.samps,
-                             lookahead_samps=args.lookahead_samps, procs=args.procs,
-                             threaded=args.threaded)
-
-    if args.save_results:
-        print("\nsaving results in '{}'".format(args.save_results))
-        results['_args'] = args
-        with open(args.save_results, 'wb') as f:
-            pickle.dump(results, f)
-    return results
-
-
-if __name__ == '__main__':
-    main()
+# The experiment drivers of bayes_pmf.py:675-938 (fetch_samples, full_test, compare_active, main)
+# are not restated here: drivers.load("bayes_pmf", ref_dir) runs the reference's own against
+# BayesianPMF / KEYS above.

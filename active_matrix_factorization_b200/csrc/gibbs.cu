@@ -768,8 +768,9 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
   if (row_begin < 0) row_begin = 0;
   if (row_begin >= row_end) return AMF_OK;
   const int rows = row_end;
+  // sticky: set by any row of any half-sweep on this handle, cleared only when
+  // amf_gibbs_status reads it (a chain step is several half-sweeps and one status call)
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);
-  AMF_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
   const int span = row_end - row_begin;
   const int grid = span < num_sms() * 8 ? span : num_sms() * 8;
   if (d <= 32) {
@@ -870,8 +871,9 @@ int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d
 int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream) {
   AMF_REQUIRE(h && failed, "amf_gibbs_status: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  AMF_CUDA(cudaMemcpyAsync(failed, reinterpret_cast<int*>(h->sums_d + 6), sizeof(int),
-                           cudaMemcpyDeviceToHost, s));
+  int* flag = reinterpret_cast<int*>(h->sums_d + 6);
+  AMF_CUDA(cudaMemcpyAsync(failed, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  AMF_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
   AMF_CUDA(cudaStreamSynchronize(s));
   return AMF_OK;
 }

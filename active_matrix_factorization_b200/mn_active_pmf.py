@@ -3,8 +3,8 @@ active learning on PMF with a MATRIX-NORMAL approximate posterior
 MN(mean, cov_useritems, cov_latents) -- the variant the reference's drugbank and movielens
 experiments run (results/drugbank-94x425/Makefile:66-76).  SURVEY.md 8f-1.
 
-Same class surface as the reference (``MNActivePMF``, the 13 ``KEY_FUNCS``, ``full_test``,
-``compare``, ``main``); the numerics run in csrc/mn.cu: the whole ``fit_normal`` line search of
+Same class surface as the reference (``MNActivePMF``, the 13 ``KEY_FUNCS``; its drivers are run from
+the reference's own source by ``drivers.load``); the numerics run in csrc/mn.cu: the whole ``fit_normal`` line search of
 every (candidate, value) lookahead problem is one CTA, and the cheap criteria read three
 scalars of Sigma plus Omega per candidate.  No CPU path.
 """
@@ -17,7 +17,7 @@ import numpy as np
 from . import _native as N
 from . import normal as _normal
 from . import active_pmf as _apmf
-from .active_pmf import (ActivePMF, _InlinePool, add_bool_opt,  # noqa: F401
+from .active_pmf import (ActivePMF,  # noqa: F401
                          do_normal_fit, spawn_processes, nice_name, minimize, maximize, strictmap)
 from .pmf_cy import parse_fit_type
 from .matrix_normal_exps_cy import (quadexpect, exp_a2bc, exp_dotprod_sq,  # noqa: F401
@@ -222,83 +222,8 @@ class MNActivePMF(ActivePMF):
 
 
 ################################################################################
-### Drivers (mn_active_pmf.py:785-1132)
-
-def _mean_info(apmf):
-    return "Mean diff of means: %g; mean useritems cov %g, latents cov %g" % (
-        apmf.mean_meandiff(), np.abs(apmf.cov_useritems.mean()), np.abs(apmf.cov_latents.mean()))
-
-
-def full_test(apmf, real, picker_key=MNActivePMF.pred_variance, fit_normal=True,
-              fit_sigmas=False, processes=None, test_on=None):
-    '''(mn_active_pmf.py:795-846)'''
-    print("Training PMF")
-    if fit_sigmas:
-        apmf.fit_with_sigmas()
-    else:
-        apmf.do_fit()
-    apmf.initialize_approx()
-    if fit_normal:
-        print("Fitting normal")
-        apmf.fit_normal()
-        print(_mean_info(apmf))
-
-    total = apmf.num_users * apmf.num_items
-    rmse = apmf.rmse(real, test_on)
-    print("RMSE: {:.5}".format(rmse))
-    yield len(apmf.rated), rmse, None, None, None
-
-    while apmf.unrated:
-        print()
-        print("Picking a query point...")
-        if len(apmf.unrated) == 1:
-            i, j = next(iter(apmf.unrated))
-            vals = None
-        else:
-            pool = list(apmf.unrated)
-            vals = apmf._get_key_vals(pool, picker_key, processes, None)
-            i, j = picker_key.chooser(zip(pool, vals), key=operator.itemgetter(1))[0]
-        apmf.add_rating(i, j, real[i, j])
-        print("Queried (%d, %d); %d/%d known" % (i, j, len(apmf.rated), total))
-        print("Training PMF")
-        for _ll in apmf.fit_lls():
-            pass
-        if fit_normal:
-            print("Fitting normal")
-            for kl in apmf.fit_normal_kls():
-                assert kl > -1e5
-            print(_mean_info(apmf))
-        rmse = apmf.rmse(real, test_on)
-        print("RMSE: {:.5}".format(rmse))
-        yield len(apmf.rated), rmse, (i, j), vals, apmf.predicted_matrix()
-
-
-_in_between_work = _apmf._in_between_work
-
-
-def _full_test_threaded(apmf, real, picker_key, fit_normal, fit_sigmas, worker_pool, test_on=None):
-    '''(mn_active_pmf.py:867-894)'''
-    total = real.size
-    name = picker_key.nice_name
-    rmse = apmf.rmse(real, test_on)
-    print("{:<40} Initial RMSE: {:.5}".format(name, rmse))
-    yield len(apmf.rated), rmse, None, None, None
-    while apmf.unrated:
-        n = len(apmf.rated) + 1
-        print("{:<40} Picking query point {}...".format(name, n))
-        if len(apmf.unrated) == 1:
-            vals = np.empty((apmf.num_users, apmf.num_items))
-            vals.fill(np.nan)
-            i, j = next(iter(apmf.unrated))
-        else:
-            vals = apmf.get_key_evals(key=picker_key, worker_pool=worker_pool)
-            i, j = picker_key.chooser(apmf.unrated, key=vals.__getitem__)
-        apmf = worker_pool.apply(_in_between_work,
-                                 (apmf, i, j, real[i, j], total, fit_normal, fit_sigmas, name))
-        rmse = apmf.rmse(real, test_on)
-        print("{:<40} RMSE {}: {:.5}".format(picker_key.nice_name, n, rmse))
-        yield len(apmf.rated), rmse, (i, j), vals, apmf.predicted_matrix()
-
+### Registry (mn_active_pmf.py:1005-1025).  The drivers of mn_active_pmf.py:785-1132 are run from
+### the reference's own source by drivers.load("mn_active_pmf", ref_dir).
 
 KEY_FUNCS = {
     "random": MNActivePMF.random_weighting,
@@ -320,118 +245,3 @@ KEY_FUNCS = {
     "1step-ge-.5": MNActivePMF.onestep_ge_half,
     "1step-ge-.5-approx": MNActivePMF.onestep_ge_half_approx,
 }
-
-
-def compare(key_names, real, ratings, rating_vals=None, latent_d=5, knowable=None, test_on=None,
-            processes=None, do_threading=True, steps=None, discrete_exp=False,
-            refit_lookahead=False, fit_sigmas=False, apmf=None,
-            sig_u_mean=0, sig_u_var=-1, sig_v_mean=0, sig_v_var=-1, fit_type=('batch',)):
-    '''(mn_active_pmf.py:922-1003); `processes` is accepted and ignored (GPU fan-out).'''
-    from threading import Thread, Lock
-    if apmf:
-        assert (apmf.num_users, apmf.num_items) == real.shape
-        assert np.all(apmf.ratings == ratings)
-        assert set(apmf.rating_values) == set(rating_vals)
-        apmf.discrete_expectations = discrete_exp
-    else:
-        apmf = MNActivePMF(ratings, latent_d=latent_d, rating_values=rating_vals,
-                           discrete_expectations=discrete_exp, refit_lookahead=refit_lookahead,
-                           knowable=knowable, fit_type=fit_type)
-        apmf.sig_u_mean, apmf.sig_u_var = sig_u_mean, sig_u_var
-        apmf.sig_v_mean, apmf.sig_v_var = sig_v_mean, sig_v_var
-        print("Doing initial fit")
-        if fit_sigmas:
-            apmf.fit_with_sigmas()
-        else:
-            apmf.do_fit()
-        if any(KEY_FUNCS[name].do_normal_fit for name in key_names):
-            apmf.initialize_approx()
-            print("Initial approximation fit")
-            apmf.fit_normal()
-            print(_mean_info(apmf))
-
-    results = {'_real': real, '_ratings': ratings, '_rating_vals': rating_vals,
-               '_initial_apmf': deepcopy(apmf)}
-    if do_threading:
-        worker_pool = _InlinePool()
-        worker_pool.access_lock = Lock()
-
-        def eval_key(key_name):
-            key = KEY_FUNCS[key_name]
-            res = _full_test_threaded(deepcopy(apmf), real, key, key.do_normal_fit, fit_sigmas,
-                                      worker_pool, test_on)
-            results[key_name] = list(itertools.islice(res, steps))
-
-        threads = [Thread(name=k, target=eval_key, args=(k,)) for k in key_names]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-    else:
-        for key_name in key_names:
-            key = KEY_FUNCS[key_name]
-            res = full_test(deepcopy(apmf), real, key, key.do_normal_fit, fit_sigmas, processes, test_on)
-            results[key_name] = list(itertools.islice(res, steps))
-    return results
-
-
-def main(argv=None):
-    '''Same command line as the reference (mn_active_pmf.py:1011-1132).'''
-    import os
-    import pickle
-    import sys
-
-    key_names = set(KEY_FUNCS.keys())
-    spec = [e for e in _apmf._CLI if e[0] == "Model Options" or e[0] == "Running"]
-    spec += [("Problem", ('--load-data',), dict(default=None, metavar='FILE')),
-             ("Results", ('--save-results',), dict(default=True, metavar='FILE')),
-             ("Results", ('--no-save-results',), dict(action='store_false', dest='save_results')),
-             ("Results", ('--note',), dict(action='append'))]
-    parser = _apmf.build_parser(spec, key_names)
-    args = parser.parse_args(argv)
-
-    for k in args.keys:
-        if k not in key_names:
-            sys.stderr.write("Invalid key name %s; options are %s.\n" % (k, ', '.join(sorted(key_names))))
-            sys.exit(1)
-    if not args.keys:
-        args.keys = sorted(key_names)
-    if args.save_results is True:
-        args.save_results = 'results.pkl'
-    elif args.save_results:
-        dirname = os.path.dirname(args.save_results)
-        if dirname and not os.path.exists(dirname):
-            os.makedirs(dirname)
-
-    with open(args.load_data, 'rb') as f:
-        data = np.load(f, allow_pickle=True)
-        if isinstance(data, np.ndarray):
-            data = {'_real': data}
-        real = data['_real']
-        ratings = data['_ratings']
-        rating_vals = data['_rating_vals'] if '_rating_vals' in data else None
-        test_on = data['_test_on'] if '_test_on' in data else None
-
-    knowable = np.isfinite(real)
-    knowable[real == 0] = False
-    if test_on is not None:
-        knowable[test_on] = False
-    knowable = zip(*knowable.nonzero())
-
-    results = compare(args.keys, real=real, ratings=ratings, rating_vals=rating_vals,
-                      latent_d=args.latent_d, knowable=knowable, test_on=test_on,
-                      discrete_exp=args.discrete_integration, refit_lookahead=args.refit_lookahead,
-                      fit_sigmas=args.fit_sigmas, sig_u_mean=args.sig_u_mean,
-                      sig_u_var=args.sig_u_var, sig_v_mean=args.sig_v_mean, sig_v_var=args.sig_v_var,
-                      steps=args.steps, fit_type=parse_fit_type(args.fit),
-                      processes=args.processes, do_threading=args.threading)
-    if args.save_results:
-        print("saving results in '{}'".format(args.save_results))
-        results['_args'] = args
-        with open(args.save_results, 'wb') as f:
-            pickle.dump(results, f)
-    return results
-
-
-if __name__ == '__main__':
-    main()

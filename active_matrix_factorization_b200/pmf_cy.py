@@ -431,6 +431,7 @@ class ProbabilisticMatrixFactorization(object):
         D.loss_grad(rat, d, U, V, self._params(), gU, gV, sums)
         old_ll = ll_of(sums)
         hyper = (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq)
+        rat_nnz = rat.nnz
 
         converged = False
         while not converged:
@@ -453,13 +454,15 @@ class ProbabilisticMatrixFactorization(object):
                     # gradient from the new state but keeps comparing against the objective it
                     # yielded (pmf_cy.pyx:265,284-285: old_ll is never re-evaluated), so only
                     # the gradient is refreshed here
-                    changed = dev.get('rat') is not rat
+                    # (add_ratings appends to the SAME device list object: compare its length too)
+                    changed = dev.get('rat') is not rat or rat.nnz != rat_nnz
                     if dev.pop('host_set', False):
                         self._pull()
                         U, V = D.to_padded(self._users, name), D.to_padded(self._items, name)
                         changed = True
                     if changed or hyper != (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq):
                         rat = self._rating_handle()
+                        rat_nnz = rat.nnz
                         D.loss_grad(rat, d, U, V, self._params(), gU, gV, sums)
                     hyper = (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq)
                     break
@@ -644,11 +647,13 @@ def load_coo(path):
     """Rating list of a data file as (i, j, r, num_users, num_items) for ``from_coo`` -- the
     large-data companion of the reference's ``.npz`` / ``.pkl`` dictionaries
     (choose_training.py:215-259, active_pmf.py:1200-1219), which always pass through an (nnz, 3)
-    float64 array.  Accepted: ``.npz`` with arrays ``i, j, r`` (any integer / float dtypes, read
-    memory-mapped when the archive is not compressed) and optionally ``shape``; ``.npz`` / ``.pkl``
+    float64 array.  Accepted: ``.npz`` with arrays ``i, j, r`` (any integer / float dtypes; loaded without
+    unpickling) and optionally ``shape``; ``.npz`` / ``.pkl``
     with the reference's ``_ratings`` (nnz, 3) table and optionally ``_real`` (its shape gives the
     matrix shape); ``.npy`` with an (nnz, 3) table; anything else is read as whitespace-
-    separated ``i j r`` text lines.  Without an explicit shape it is ``max id + 1`` per side, as in
+    separated ``i j r`` text lines (``.npy`` tables are memory-mapped; numpy cannot map ``.npz``
+    members).  Only the reference's ``_ratings`` dictionaries are unpickled -- load those from
+    trusted files only.  Without an explicit shape it is ``max id + 1`` per side, as in
     the reference's constructor (pmf_cy.pyx:65-66).  Ids must be non-negative."""
     import pickle
     shape = None
@@ -657,7 +662,9 @@ def load_coo(path):
             with open(path, 'rb') as f:
                 data = pickle.load(f)
         else:
-            data = np.load(path, mmap_mode='r', allow_pickle=True)
+            data = np.load(path, allow_pickle=False)
+            if '_ratings' in data.files and not {'i', 'j', 'r'} <= set(data.files):
+                data = np.load(path, allow_pickle=True)     # the reference's dictionaries hold objects
         keys = set(data.keys())
         if {'i', 'j', 'r'} <= keys:
             i, j, r = data['i'], data['j'], data['r']
@@ -680,17 +687,20 @@ def load_coo(path):
         if table.shape[1] != 3:
             raise TypeError("invalid rating tuple length")
         i, j, r = table[:, 0], table[:, 1], table[:, 2]
-    i = np.ascontiguousarray(i).astype(np.int32, copy=False)
-    j = np.ascontiguousarray(j).astype(np.int32, copy=False)
-    r = np.ascontiguousarray(r)
+    i, j, r = np.asarray(i), np.asarray(j), np.ascontiguousarray(r)
     if not (i.shape == j.shape == r.shape and i.ndim == 1):
         raise TypeError("i, j, r must be three vectors of one length")
+    # range checks on the ORIGINAL dtype: a cast to int32 first would wrap ids >= 2^31
     if i.size and (i.min() < 0 or j.min() < 0):
         raise ValueError("negative user / item id")
     if shape is None:
         shape = (int(i.max()) + 1 if i.size else 0, int(j.max()) + 1 if j.size else 0)
     if i.size and (i.max() >= shape[0] or j.max() >= shape[1]):
         raise ValueError("ids outside the %d x %d matrix" % shape)
+    if max(shape) > np.iinfo(np.int32).max:
+        raise ValueError("matrix sides above 2^31 - 1 are not supported")
+    i = np.ascontiguousarray(i).astype(np.int32, copy=False)
+    j = np.ascontiguousarray(j).astype(np.int32, copy=False)
     return i, j, r, int(shape[0]), int(shape[1])
 
 

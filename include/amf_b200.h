@@ -267,8 +267,10 @@ int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d
                               double beta, double mean_offset, const void* z_d, void* out_d,
                               int32_t row_begin, int32_t row_end, void* stream);
 
-/* 1 in *failed if any row of the last half-sweep on this handle met a non-positive-definite
- * precision/covariance (np.linalg.cholesky would have raised LinAlgError); synchronises. */
+/* 1 in *failed if any row of ANY half-sweep on this handle since the previous call of this
+ * function met a non-positive-definite precision/covariance (np.linalg.cholesky would have
+ * raised LinAlgError).  The flag is sticky: half-sweeps only set it, this call reads and
+ * clears it, so one status call per chain step covers all its half-sweeps; synchronises. */
 int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream);
 
 /* Sample statistics of S posterior samples at ncand cells: Us_d (S, n, d), Vs_d (S, m, d)

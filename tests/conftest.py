@@ -22,3 +22,17 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(scope="session")
+def ref_drivers():
+    """The reference's own driver functions (full_test, compare, main, ...) from the patched
+    copy in oracle/_ref, bound to the GPU-backed classes by the package's loader."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref is not built")
+    from active_matrix_factorization_b200 import drivers
+
+    def load(name):
+        return drivers.load(name, ref_loader.REF_DIR)
+    return load

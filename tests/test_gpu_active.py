@@ -231,15 +231,41 @@ def test_concurrent_host_threads_each_with_its_own_copy(A, golden):
     assert sorted(done) == [0, 1, 2, 3]
 
 
-def test_driver_smoke_matches_reference_soft_pin(A):
+def test_driver_smoke_matches_reference_soft_pin(A, ref_drivers, tmp_path, monkeypatch):
     """SURVEY.md 8c soft pin: seeded CLI run of the reference prints RMSE 0.56964 then queries.
-    The first RMSE depends only on the seeded data + MAP fit, so it must match."""
+    The first RMSE depends only on the seeded data + MAP fit, so it must match.  The command
+    line is the REFERENCE's own main()/compare()/full_test() (loaded from oracle/_ref by
+    drivers.load) driving the GPU-backed ActivePMF."""
+    import pickle
     import random
+    import sys
+    drv = ref_drivers("active_pmf")
+    assert drv.ActivePMF is A.ActivePMF and drv.KEY_FUNCS is A.KEY_FUNCS
+    out = str(tmp_path / "res.pkl")
+    monkeypatch.setattr(sys, "argv", ["active_pmf.py", "-N", "10", "-M", "10", "-R", "2", "-D", "2",
+                                      "--type", "binary", "--mask", "diag", "--discrete-integration",
+                                      "--no-threading", "--processes", "1", "--steps", "3",
+                                      "--save-results", out, "--", "pred-variance"])
     np.random.seed(0); random.seed(0)
-    res = A.main(["-N", "10", "-M", "10", "-R", "2", "-D", "2", "--type", "binary", "--mask", "diag",
-                  "--discrete-integration", "--no-threading", "--processes", "1", "--steps", "3",
-                  "--", "pred-variance"])
+    drv.main()
+    with open(out, "rb") as f:
+        res = pickle.load(f)
     steps = res["pred-variance"]
     assert len(steps) == 3
     assert steps[0][1] == pytest.approx(0.56964, abs=5e-6)
     assert steps[1][2] is not None and steps[1][0] == 11
+    assert isinstance(res["_initial_apmf"], A.ActivePMF)
+
+
+def test_threaded_reference_driver_runs_without_worker_processes(A, ref_drivers):
+    """compare(do_threading=True) of the reference hands models to a multiprocessing.Pool
+    (active_pmf.py:1065-1084); the loader gives it an in-process pool instead."""
+    import random
+    drv = ref_drivers("active_pmf")
+    np.random.seed(3); random.seed(3)
+    res = drv.compare(["pred-variance", "pred"], latent_d=2, steps=2, discrete_exp=True,
+                      do_threading=True, num_users=6, num_items=6, rank=2, data_type="binary",
+                      mask_type="diag")
+    for k in ("pred-variance", "pred"):
+        assert len(res[k]) == 2 and res[k][1][0] == len(res["_ratings"]) + 1
+        assert res[k][1][3].shape == (6, 6)

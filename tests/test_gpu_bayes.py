@@ -72,8 +72,11 @@ def test_keys_registry(Bm):
     assert (k.key_fn, k.choose_max, k.wants_pool, k.args) == ('prob_ge_cutoff', True, False, (3.5,))
 
 
-def test_active_loop_two_steps(Bm):
-    """bayes_pmf.compare_active end to end on a tiny problem (pred-variance + exp-variance)."""
+def test_active_loop_two_steps(Bm, ref_drivers):
+    """The reference's own bayes_pmf.compare_active (loaded by drivers.load) end to end on a
+    tiny problem (pred-variance + exp-variance), driving the GPU-backed BayesianPMF."""
+    drv = ref_drivers("bayes_pmf")
+    assert drv.BayesianPMF is Bm.BayesianPMF
     import random
     np.random.seed(1); random.seed(1)
     n, m, d = 6, 5, 2
@@ -83,8 +86,8 @@ def test_active_loop_two_steps(Bm):
     known = sorted(set(known))
     ratings = np.array([(i, j, real[i, j]) for i, j in known], dtype=float)
     assert set(ratings[:, 1].astype(int)) == set(range(m))
-    res = Bm.compare_active(['pred-variance'], d, real, ratings, rating_vals=(1, 2, 3, 4, 5),
-                            num_steps=3, num_samps=8, threaded=False)
+    res = drv.compare_active(['pred-variance'], d, real, ratings, rating_vals=(1, 2, 3, 4, 5),
+                             num_steps=3, num_samps=8, threaded=False, procs=0)
     steps = res['pred-variance']
     assert len(steps) == 3 and steps[1][0] == len(known) + 1 and steps[2][0] == len(known) + 2
     assert steps[1][3].shape == (n, m) and np.isfinite(steps[1][1])

@@ -71,13 +71,16 @@ def test_mn_fit_and_lookahead(M, golden):
         assert c.kl_divergence() == pytest.approx(b.kl_divergence(), rel=1e-12)
 
 
-def test_mn_driver_two_steps(M):
+def test_mn_driver_two_steps(M, ref_drivers):
+    """the reference's own mn_active_pmf.compare / full_test on the GPU-backed MNActivePMF"""
     import random
     np.random.seed(2); random.seed(2)
-    from active_matrix_factorization_b200.active_pmf import make_fake_data
+    make_fake_data = ref_drivers("active_pmf").make_fake_data
+    drv = ref_drivers("mn_active_pmf")
+    assert drv.MNActivePMF is M.MNActivePMF
     real, ratings, vals = make_fake_data(noise=.25, num_users=6, num_items=6, rank=2,
                                          data_type='binary', mask_type='diag')
-    res = M.compare(['pred-variance', 'prob-ge-.5'], real, ratings, rating_vals=vals, latent_d=2,
+    res = drv.compare(['pred-variance', 'prob-ge-.5'], real, ratings, rating_vals=vals, latent_d=2,
                     steps=3, discrete_exp=True, do_threading=True)
     for k in ('pred-variance', 'prob-ge-.5'):
         assert len(res[k]) == 3 and res[k][2][0] == len(ratings) + 2

@@ -39,6 +39,19 @@ class NormalFitParams(C.Structure):
 NORMAL_FIT, NORMAL_KL, NORMAL_GRADIENT, NORMAL_PROJECT = 0, 1, 2, 3
 
 
+class BlocksView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("d", C.c_int32),
+                ("mean_u", C.c_void_p), ("cov_u", C.c_void_p), ("prec_u", C.c_void_p),
+                ("h_u", C.c_void_p), ("logdet_u", C.c_void_p),
+                ("mean_v", C.c_void_p), ("cov_v", C.c_void_p), ("prec_v", C.c_void_p),
+                ("h_v", C.c_void_p), ("logdet_v", C.c_void_p),
+                ("sums", C.c_void_p), ("sigma_sq", C.c_double), ("entropy0", C.c_double)]
+
+
+LOOK_ENTROPY, LOOK_TOTAL_VARIANCE = 0, 1
+WEIGHTS_NONE, WEIGHTS_DISCRETE, WEIGHTS_NODES = 0, 1, 2
+
+
 class Best(C.Structure):
     _fields_ = [("value", C.c_double), ("index", C.c_int64)]
 
@@ -93,6 +106,12 @@ PROTOTYPES = {
                        _P, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],
     "amf_mn_score_candidates": [_INT, _INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _F64, _P,
                                 _INT, _I64, _P, _P],
+    "amf_blocks_half_sweep": [_P, _INT, _INT, _P, _P, _F64, _F64, _F64, _P, _P, _P, _P, _P, _P, _P],
+    "amf_blocks_sums": [_I64, _INT, _P, _P, _P, _P],
+    "amf_blocks_lookahead": [C.POINTER(BlocksView), _INT, _INT, _I64, _P, _P, _INT, _P, _INT, _P,
+                             _P, _P, _P, _P, _INT, _I64, _P, _P, _P],
+    "amf_blocks_pack": [_INT, _I64, _INT, _P, _P, _INT, _INT, _P, _P],
+    "amf_prob_ge": [_INT, _I64, _P, _P, _F64, _P, _INT, _I64, _P, _P],
     "amf_score_pred_host": [_INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT,
                             C.POINTER(Best)],
     "amf_score_pred_host_csr": [_INT, _P, _P, _I32, _I32, _INT, _P, _P, _P, _INT, C.POINTER(Best)],

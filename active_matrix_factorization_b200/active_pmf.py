@@ -15,6 +15,7 @@ There is no CPU path: every numeric method raises if libamf_b200 or the GPU is m
 """
 from copy import deepcopy
 import functools
+import os
 import itertools
 import math
 import numbers
@@ -25,8 +26,11 @@ import warnings
 import numpy as np
 from scipy import stats
 import scipy.integrate
+import torch
 
 from . import _native as N
+from . import blocks as _blocks
+from . import device as _D
 from . import normal as _normal
 from . import scoring as _scoring
 from .pmf_cy import ProbabilisticMatrixFactorization, parse_fit_type
@@ -122,6 +126,18 @@ class ActivePMF(ProbabilisticMatrixFactorization):
     verbose_lookahead = False   # the reference prints one line per lookahead (active_pmf.py:702-703)
     max_normal_steps = 0        # > 0 caps the accepted steps of one fit_normal (0: to convergence)
 
+    # Which family the Gaussian approximation lives in.  'exact': the reference's k x k
+    # covariance, k = (N+M)d (active_pmf.py:136,190-288) -- bit-for-bit algorithm, feasible up to
+    # a few hundred dimensions.  'blocks': the same KL objective restricted to one d x d block per
+    # row / column (blocks.py, csrc/blocks.cu) -- O((N+M) d^2) state, lookahead by local re-fits.
+    # 'auto' = exact while k <= exact_max_dim, blocks above (drugbank: k = 2595).
+    approx_mode = os.environ.get("AMF_B200_APPROX", "auto")
+    exact_max_dim = 320
+    lookahead_rounds = 1        # coordinate rounds (row i, column j) of a scalable-mode re-fit
+    blocks_max_sweeps = 500
+    blocks_tol = 1e-10          # largest movement of a posterior mean that still counts as moving
+    quadrature_nodes = 16       # Gauss-Legendre nodes of the 2-sigma window in scalable mode
+
     def __init__(self, rating_tuples, latent_d=1, rating_values=None,
                  discrete_expectations=False, refit_lookahead=False, knowable=None,
                  fit_type=('batch',)):
@@ -192,11 +208,52 @@ class ActivePMF(ProbabilisticMatrixFactorization):
                                   learning_rate=self.normal_learning_rate, min_eig=self.min_eig,
                                   max_steps=max_steps)
 
+    def _use_blocks(self):
+        mode = self.approx_mode
+        if mode not in ('auto', 'exact', 'blocks'):
+            raise ValueError("approx_mode must be 'auto', 'exact' or 'blocks'")
+        return mode == 'blocks' or (mode == 'auto' and self.approx_dim > self.exact_max_dim)
+
+    def _in_blocks(self, cov=None):
+        return isinstance(self.cov if cov is None else cov, _blocks.BlockDiagonal)
+
+    def _new_block_posterior(self):
+        return _blocks.BlockPosterior(self.num_users, self.num_items, self.latent_d, self.sigma_sq,
+                                      self.sigma_u_sq, self.sigma_v_sq)
+
+    def _block_posterior(self, cov=None):
+        '''device tables of the BlockDiagonal in self.cov (cached until cov is replaced)'''
+        cov = self.cov if cov is None else cov
+        hit = self._dev.get('blocks')
+        hyper = (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq)
+        if hit is None or hit[0] is not cov or hit[2] != hyper:
+            post = _blocks.BlockPosterior.from_host(cov, *hyper)
+            hit = self._dev['blocks'] = (cov, post, hyper)
+        return hit[1]
+
+    def _adopt(self, post):
+        bd = post.to_host()
+        self.cov = bd
+        self.mean = bd.stacked_mean()
+        self._dev['blocks'] = (bd, post, (self.sigma_sq, self.sigma_u_sq, self.sigma_v_sq))
+
     def initialize_approx(self):
-        '''(active_pmf.py:190-200): mean <- MAP factors, cov <- random PSD matrix'''
+        '''(active_pmf.py:190-200): mean <- MAP factors, cov <- random PSD matrix.  Scalable
+        mode: cov <- the block curvature of the MAP objective at the MAP factors (no k x k draw).'''
+        if self._use_blocks():
+            post = self._new_block_posterior()
+            post.fit(self._rating_handle(), self.users, self.items, sweeps=1, cov_term=False,
+                     update_mean=False)
+            self._adopt(post)
+            return
         self.mean = np.hstack((self.users.reshape(-1), self.items.reshape(-1)))
         s = np.random.normal(0, 2, (self.approx_dim, self.approx_dim))
         self.cov = project_psd(s, min_eig=self.min_eig)
+
+    def _rating_arrays_device(self):
+        r = np.asarray(self.ratings, dtype=float)
+        return (_D.to_device(r[:, 0], np.int32), _D.to_device(r[:, 1], np.int32),
+                _D.to_device(r[:, 2], np.float64))
 
     def kl_divergence(self, mean=None, cov=None):
         '''KL(PMF model || approximation), up to an additive constant (active_pmf.py:202-240)'''
@@ -206,6 +263,8 @@ class ActivePMF(ProbabilisticMatrixFactorization):
             cov = self.cov
         if mean is None or cov is None:
             raise ValueError("run initialize_approx first")
+        if self._in_blocks(cov):
+            return self._block_posterior(cov).kl(*self._rating_arrays_device())
         batch = _normal.NormalBatch(self.ratings, self._fit_params(), mean[None], cov[None])
         return float(batch.kl_divergence()[0])
 
@@ -220,6 +279,21 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         '''
         if self.mean is None or self.cov is None:
             raise ValueError("run initialize_approx first")
+        if self._in_blocks():
+            # coordinate descent on the block-restricted KL from the current means; every sweep
+            # lowers the reference's objective, which is yielded like the accepted steps there
+            post = self._new_block_posterior()
+            n, d = self.num_users, self.latent_d
+            ri, rj, rr = self._rating_arrays_device()
+            try:
+                for kl in post.fit_sweeps(self._rating_handle(), self.mean[:n * d].reshape(n, d),
+                                          self.mean[n * d:].reshape(-1, d),
+                                          sweeps=self.blocks_max_sweeps, tol=self.blocks_tol,
+                                          kl_of=lambda p: p.kl(ri, rj, rr)):
+                    yield kl
+            finally:
+                self._adopt(post)
+            return
         batch = _normal.NormalBatch(self.ratings, self._fit_params(max_steps=self.max_normal_steps),
                                     self.mean[None], self.cov[None])
         trace_len = 1 << 14
@@ -248,6 +322,11 @@ class ActivePMF(ProbabilisticMatrixFactorization):
 
     def _normal_scores(self, criterion, ii, jj, cutoff=0., maximize_=True):
         self._require_approx()
+        if self._in_blocks():
+            ci, cj = _scoring._cands(ii, jj)
+            scores, best = self._block_posterior().score(criterion, ci, cj, "f64", cutoff=cutoff,
+                                                         maximize=maximize_)
+            return scores.cpu().numpy(), _scoring.unpack_best(best)
         return _scoring.score_normal(criterion, self.mean, self.cov, self.num_users,
                                      self.num_items, self.latent_d, ii, jj, "f64",
                                      cutoff=cutoff, maximize=maximize_)
@@ -334,6 +413,8 @@ class ActivePMF(ProbabilisticMatrixFactorization):
 
     def _approx_entropy(self):
         '''(active_pmf.py:526-530) log det cov'''
+        if self._in_blocks():
+            return self._block_posterior().entropy()
         sign, logdet = _slogdet(self.cov)
         assert sign == 1
         return logdet
@@ -365,6 +446,8 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         return self._lookahead([ij], 'pred_entropy_bound', False)[0]
 
     def _total_variance(self):
+        if self._in_blocks():
+            return self._block_posterior().total_variance()
         return self.approx_pred_means_vars()[1].sum()
 
     @_criterion("E[Pred Total Variance] (MAP)", True, True, min)
@@ -485,8 +568,55 @@ class ActivePMF(ProbabilisticMatrixFactorization):
             return what[1](apmf, v=v) if what[2] else what[1](apmf)
         return apmf._last_step_lookahead_helper(what[1], v)
 
+    def _lookahead_blocks(self, ii, jj, what, use_map, discretize=None, want_scores=True):
+        '''_exp_with_rij (active_pmf.py:635-704) for every candidate in scalable mode: one launch,
+        one lane group per candidate, the expectation over R_ij and the arg-min fused.  Returns
+        (scores ndarray, (best value, best index)).'''
+        self._require_approx()
+        if what not in ('entropy', 'total_variance'):
+            raise ValueError("criterion %r needs the exact (full-covariance) mode: "
+                             "set approx_mode = 'exact'" % (what,))
+        if self.refit_lookahead:
+            raise ValueError("refit_lookahead needs the exact mode (approx_mode = 'exact')")
+        if discretize is None:
+            discretize = self.discrete_expectations
+        post = self._block_posterior()
+        ci, cj = _scoring._cands(ii, jj)
+        if use_map:          # R_ij ~ N(U_i . V_j, sigma^2) at the MAP factors (:656-659)
+            U, V = _D.to_padded(self.users, "f64"), _D.to_padded(self.items, "f64")
+            mu, _ = _scoring.score_device(N.CRIT_PRED, "f64", ci, cj, self.latent_d, U, V)
+            sd = torch.full_like(mu, math.sqrt(self.sigma_sq))
+        else:                # ... or the approximation's own mean and variance (:660-666)
+            mu, _ = post.score(N.CRIT_APPROX_MEAN, ci, cj, "f64")
+            var, _ = post.score(N.CRIT_PRED_VARIANCE, ci, cj, "f64")
+            sd = var.sqrt()
+        code = N.LOOK_ENTROPY if what == 'entropy' else N.LOOK_TOTAL_VARIANCE
+        points = self.rating_values
+        rounds = self.lookahead_rounds
+        if discretize and points:
+            vals = np.array(points, dtype=float)
+            if discretize == 'simps':
+                evals, _, _ = post.lookahead(code, ci, cj, vals, rounds=rounds, want_evals=True)
+                pdfs = stats.norm.pdf(vals[None, :], loc=mu.cpu().numpy()[:, None],
+                                      scale=sd.cpu().numpy()[:, None])
+                est = scipy.integrate.simpson(evals.cpu().numpy() * pdfs, x=vals, axis=1)
+                return est, _argbest(est, False)
+            _, scores, best = post.lookahead(code, ci, cj, vals, N.WEIGHTS_DISCRETE,
+                                             self.rating_bounds, mu, sd, rounds=rounds,
+                                             want_scores=want_scores)
+        else:
+            if discretize and points is None:
+                warnings.warn("ActivePMF has no rating_values; doing integral")
+            t, w = _blocks.gauss_nodes(self.quadrature_nodes)
+            _, scores, best = post.lookahead(code, ci, cj, t, N.WEIGHTS_NODES, w, mu, sd,
+                                             rounds=rounds, want_scores=want_scores)
+        return (scores.cpu().numpy() if scores is not None else None), _scoring.unpack_best(best)
+
     def _lookahead(self, pool, what, use_map, discretize=None, pass_v=False):
         '''_exp_with_rij for every pair of `pool`.'''
+        if self._in_blocks():
+            ii, jj = _pool_arrays(pool) if not isinstance(pool, np.ndarray) else (pool[:, 0], pool[:, 1])
+            return self._lookahead_blocks(ii, jj, what, use_map, discretize)[0].tolist()
         pool = [(int(i), int(j)) for i, j in pool]
         if discretize is None:
             discretize = self.discrete_expectations
@@ -526,66 +656,119 @@ class ActivePMF(ProbabilisticMatrixFactorization):
     ### Picking a query point
 
     def pick_query_point(self, pool=None, key=None, procs=None, worker_pool=None):
-        '''(active_pmf.py:709-737); procs / worker_pool are accepted and ignored.'''
+        '''(active_pmf.py:709-737); procs / worker_pool are accepted and ignored.  The winner is
+        the one the scoring launch itself reduced (best value, first in pool order on ties --
+        what `chooser(zip(pool, vals), key=itemgetter(1))` returns); no score list is built.'''
         if pool is None:
             pool = self.unrated
         if key is None:
             key = ActivePMF.pred_variance
-        chooser = getattr(key, 'chooser', max)
         if len(pool) == 0:
             raise ValueError("can't pick a query point from an empty pool")
         elif len(pool) == 1:
-            return next(iter(pool))
+            first = next(iter(pool))
+            return (int(first[0]), int(first[1])) if isinstance(pool, np.ndarray) else first
+        pool, vals, best = self._key_scores(pool, key, want_scores=False)
+        if best is None:
+            chooser = getattr(key, 'chooser', max)
+            best = chooser(range(len(vals)), key=vals.__getitem__)
+        ij = pool[best]
+        return (int(ij[0]), int(ij[1])) if isinstance(pool, np.ndarray) else ij
+
+    _LOOKAHEADS = {
+        'exp_approx_entropy': ('entropy', True),
+        'exp_approx_entropy_byapprox': ('entropy', False),
+        'exp_total_variance': ('total_variance', True),
+        'exp_total_variance_byapprox': ('total_variance', False),
+        'exp_pred_entropy_bound': ('pred_entropy_bound', True),
+        'exp_pred_entropy_bound_byapprox': ('pred_entropy_bound', False),
+    }
+    _ONESTEPS = {'onestep_ge_3_5': (3.5, True), 'onestep_ge_3_5_approx': (3.5, False),
+                 'onestep_ge_half': (.5, True), 'onestep_ge_half_approx': (.5, False)}
+    _CELL_CRITERIA = {'pred': (N.CRIT_PRED, 0.), 'pred_variance': (N.CRIT_PRED_VARIANCE, 0.),
+                      'prob_ge_3_5': (N.CRIT_PROB_GE, 3.5), 'prob_ge_half': (N.CRIT_PROB_GE, .5)}
+
+    def _pool_device(self, pool):
+        '''(indexable pool, device i, device j).  A CandidatePool is already resident; an
+        (n, 2) integer array is uploaded once and remembered while the same object comes back;
+        anything else is listed and converted like the reference's iteration over it.'''
+        if isinstance(pool, _scoring.CandidatePool):
+            ci, cj = pool.device_arrays()
+            return pool, ci, cj
+        if isinstance(pool, np.ndarray) and pool.ndim == 2 and pool.shape[1] == 2:
+            hit = self._dev.get('pool_array')
+            if hit is not None and hit[0] is pool:
+                return pool, hit[1], hit[2]
+            ci = _D.to_device(pool[:, 0], np.int32)
+            cj = _D.to_device(pool[:, 1], np.int32)
+            self._dev['pool_array'] = (pool, ci, cj)
+            return pool, ci, cj
         pool = list(pool)
-        vals = self._get_key_vals(pool, key, procs, worker_pool)
-        return chooser(zip(pool, vals), key=operator.itemgetter(1))[0]
+        ii, jj = _pool_arrays(pool)
+        return pool, _D.to_device(ii, np.int32), _D.to_device(jj, np.int32)
+
+    def _map_factors_device(self, name):
+        '''padded MAP factors on the device: the tensors of a device-resident fit when they are
+        the newest copy, else an upload of the host arrays'''
+        dev = self._dev
+        if dev.get('host_stale') and dev.get('U') is not None and \
+                dev['U'].dtype == _D.torch_dtype(name):
+            return dev['U'], dev['V']
+        return _D.to_padded(self.users, name), _D.to_padded(self.items, name)
+
+    def _key_scores(self, pool, key, want_scores=True):
+        '''(pool as an indexable sequence, float64 ndarray of criterion values aligned with it
+        or None when not wanted and a fused winner exists, index of the winner or None).'''
+        name = getattr(key, '__name__', None)
+        maximize_ = getattr(key, 'chooser', max) is max
+        if name == 'random_weighting':
+            pool = pool if isinstance(pool, (np.ndarray, _scoring.CandidatePool)) else list(pool)
+            return pool, np.array([random.random() for _ in range(len(pool))]), None
+        if name in self._CELL_CRITERIA:
+            crit, cutoff = self._CELL_CRITERIA[name]
+            pool, ci, cj = self._pool_device(pool)
+            if crit == N.CRIT_PRED:
+                U, V = self._map_factors_device(self.dtype_name)
+                scores, best = _scoring.score_device(crit, self.dtype_name, ci, cj, self.latent_d,
+                                                     U, V, want_scores=want_scores,
+                                                     maximize=maximize_)
+            else:
+                self._require_approx()
+                if self._in_blocks():
+                    scores, best = self._block_posterior().score(
+                        crit, ci, cj, "f64", cutoff=cutoff, want_scores=want_scores,
+                        maximize=maximize_)
+                else:
+                    vals, (_bv, bi) = self._normal_scores(crit, ci, cj, cutoff=cutoff,
+                                                          maximize_=maximize_)
+                    return pool, vals, bi
+            vals = scores.to(torch.float64).cpu().numpy() if scores is not None else None
+            return pool, vals, _scoring.unpack_best(best)[1]
+        if name in self._LOOKAHEADS or name in self._ONESTEPS:
+            if name in self._LOOKAHEADS:
+                what, use_map = self._LOOKAHEADS[name]
+                discretize = None
+            else:
+                cutoff, use_map = self._ONESTEPS[name]
+                what, discretize = ('onestep', cutoff), True
+            if self._in_blocks():
+                pool, ci, cj = self._pool_device(pool)
+                vals, (_bv, bi) = self._lookahead_blocks(ci, cj, what, use_map, discretize,
+                                                         want_scores=want_scores)
+                return pool, vals, bi
+            pool = [(int(i), int(j)) for i, j in pool]
+            return pool, np.array(self._lookahead(pool, what, use_map, discretize=discretize)), None
+        # unknown criterion: evaluate it pair by pair like the reference's serial path
+        pool = list(pool)
+        return pool, np.array([key(self, ij) for ij in pool], dtype=float), None
 
     def _get_key_vals(self, pool, key, procs=None, worker_pool=None):
         '''Criterion value for every pair of `pool`, aligned with its iteration order
-        (active_pmf.py:739-770) -- evaluated in batched GPU launches.'''
-        name = getattr(key, '__name__', None)
-        if isinstance(pool, np.ndarray) and pool.ndim == 2 and pool.shape[1] == 2:
-            # array pools (large candidate sets) skip the per-tuple Python work
-            if pool.shape[0] == 0:
-                return []
-            ii = np.ascontiguousarray(pool[:, 0], dtype=np.int32)
-            jj = np.ascontiguousarray(pool[:, 1], dtype=np.int32)
-            if name not in ('pred', 'pred_variance', 'prob_ge_3_5', 'prob_ge_half'):
-                pool = [(int(i), int(j)) for i, j in pool]
-        else:
-            pool = list(pool)
-            if not pool:
-                return []
-            ii, jj = _pool_arrays(pool) if name != 'random_weighting' else ((), ())
-        if name == 'random_weighting':
-            return [random.random() for _ in range(len(pool))]
-        if name == 'pred':
-            vals, _ = _scoring.score_pred(self.users, self.items, ii, jj, self.dtype_name)
-            return vals.tolist()
-        if name == 'pred_variance':
-            return self._normal_scores(N.CRIT_PRED_VARIANCE, ii, jj)[0].tolist()
-        if name == 'prob_ge_3_5':
-            return self._normal_scores(N.CRIT_PROB_GE, ii, jj, cutoff=3.5)[0].tolist()
-        if name == 'prob_ge_half':
-            return self._normal_scores(N.CRIT_PROB_GE, ii, jj, cutoff=.5)[0].tolist()
-        lookaheads = {
-            'exp_approx_entropy': ('entropy', True),
-            'exp_approx_entropy_byapprox': ('entropy', False),
-            'exp_total_variance': ('total_variance', True),
-            'exp_total_variance_byapprox': ('total_variance', False),
-            'exp_pred_entropy_bound': ('pred_entropy_bound', True),
-            'exp_pred_entropy_bound_byapprox': ('pred_entropy_bound', False),
-        }
-        if name in lookaheads:
-            what, use_map = lookaheads[name]
-            return self._lookahead(pool, what, use_map)
-        onesteps = {'onestep_ge_3_5': (3.5, True), 'onestep_ge_3_5_approx': (3.5, False),
-                    'onestep_ge_half': (.5, True), 'onestep_ge_half_approx': (.5, False)}
-        if name in onesteps:
-            cutoff, use_map = onesteps[name]
-            return self._lookahead(pool, ('onestep', cutoff), use_map, discretize=True)
-        # unknown criterion: evaluate it pair by pair like the reference's serial path
-        return [key(self, ij) for ij in pool]
+        (active_pmf.py:739-770) -- evaluated in batched GPU launches.  Returns a float64 array
+        (the reference returns a list; every caller indexes, zips or assigns it).'''
+        if len(pool) == 0:
+            return np.zeros(0)
+        return self._key_scores(pool, key)[1]
 
     def get_key_evals(self, pool=None, key=None, procs=None, worker_pool=None):
         '''(active_pmf.py:772-787) NaN-filled (N, M) matrix of criterion values'''
@@ -593,13 +776,28 @@ class ActivePMF(ProbabilisticMatrixFactorization):
             pool = self.unrated
         if key is None:
             key = ActivePMF.pred_variance
-        pool = list(pool)
         evals = np.empty((self.num_users, self.num_items))
         evals.fill(np.nan)
-        if pool:
-            ii, jj = _pool_arrays(pool)
-            evals[ii, jj] = self._get_key_vals(pool, key, procs, worker_pool)
+        if len(pool):
+            pool, vals, _ = self._key_scores(pool, key)
+            if isinstance(pool, np.ndarray):
+                ii, jj = pool[:, 0], pool[:, 1]
+            elif isinstance(pool, _scoring.CandidatePool):
+                ii, jj = pool.i[:pool.n], pool.j[:pool.n]
+            else:
+                ii, jj = _pool_arrays(pool)
+            evals[ii, jj] = vals
         return evals
+
+
+def _argbest(vals, maximize_):
+    '''(value, index) of the best entry, lowest index on ties, NaN never wins'''
+    vals = np.asarray(vals, dtype=float)
+    ok = ~np.isnan(vals)
+    if not ok.any():
+        return 0.0, -1
+    idx = int(np.nanargmax(vals) if maximize_ else np.nanargmin(vals))
+    return float(vals[idx]), idx
 
 
 def _slogdet(mat):

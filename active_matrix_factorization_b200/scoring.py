@@ -91,6 +91,63 @@ def score_normal(criterion, mean, cov, n, m, d, ii, jj, name, cutoff=0.0, maximi
     return scores.to(torch.float64).cpu().numpy(), unpack_best(best)
 
 
+class CandidatePool(object):
+    """A candidate set that stays on the device across active-learning steps: what `unrated`
+    (a Python set of tuples, pmf_cy.pyx:69-72) is to the reference's loop
+    (active_pmf.py:880-898), without the per-step list(set) -> array -> H2D round trip.
+
+    Pass it as `pool=` to `pick_query_point / _get_key_vals / get_key_evals`; `remove(i, j)`
+    (or `add_rating` on a model the pool is attached to) drops a queried cell in O(1) by moving
+    the last candidate into its slot, on the host mirror and on the device alike.  Iteration
+    and indexing give (i, j) tuples in the current order, like a list."""
+
+    def __init__(self, ii, jj=None):
+        if jj is None:
+            arr = np.asarray(ii)
+            if arr.ndim != 2 or arr.shape[1] != 2:
+                arr = np.array(sorted(ii), dtype=np.int64).reshape(-1, 2)
+            ii, jj = arr[:, 0], arr[:, 1]
+        self.i = np.ascontiguousarray(ii, dtype=np.int32).copy()
+        self.j = np.ascontiguousarray(jj, dtype=np.int32).copy()
+        self.n = int(self.i.shape[0])
+        self.ci = D.to_device(self.i, np.int32)
+        self.cj = D.to_device(self.j, np.int32)
+        self._where = None       # (i, j) -> slot, built on the first remove()
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        if idx < 0:
+            idx += self.n
+        if not 0 <= idx < self.n:
+            raise IndexError(idx)
+        return (int(self.i[idx]), int(self.j[idx]))
+
+    def __iter__(self):
+        return iter(zip(self.i[:self.n].tolist(), self.j[:self.n].tolist()))
+
+    def device_arrays(self):
+        return self.ci[:self.n], self.cj[:self.n]
+
+    def remove(self, i, j):
+        """drop the cell (i, j) if it is a candidate"""
+        if self._where is None:
+            self._where = {ij: t for t, ij in enumerate(self)}
+        slot = self._where.pop((int(i), int(j)), None)
+        if slot is None:
+            return False
+        last = self.n - 1
+        if slot != last:
+            li, lj = int(self.i[last]), int(self.j[last])
+            self.i[slot], self.j[slot] = li, lj
+            self._where[(li, lj)] = slot
+            self.ci[slot:slot + 1].copy_(self.ci[last:last + 1])
+            self.cj[slot:slot + 1].copy_(self.cj[last:last + 1])
+        self.n = last
+        return True
+
+
 class Pool:
     """Device-resident candidate pool bucketed by item tile (csrc/pool.cu); build it once and
     score it every active-learning step.  Scores and the winner are reported in the caller's

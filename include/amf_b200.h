@@ -324,6 +324,73 @@ int amf_normal_batched(int mode, int B, int64_t nnz, const int32_t* ri_d, const 
                        double* totvar_out_d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Scalable-mode variational posterior ("blocks"): the KL objective of active_pmf.py:202-240
+ * restricted to block-diagonal covariances -- one d x d block per user row and per item column
+ * instead of the k x k matrix of active_pmf.py:136,190-200 (k = (N+M) d: 2595 at the drugbank
+ * configuration, 26,250 at movielens-100k) -- and the lookahead of active_pmf.py:635-704
+ * (_exp_with_rij with _approx_entropy :526-530 / _total_variance :605-606) by local re-fits.
+ * All tables fp64, tightly packed: mean (rows, d), cov / prec (rows, d, d), h = prec @ mean
+ * (rows, d), logdet = log det cov (rows).  d <= 32.
+ * ------------------------------------------------------------------------------------------ */
+/* One coordinate half-sweep of the block-restricted objective over every row of `side`
+ * (0 users, 1 items): Lambda_i = I/prior_var + sum_{j rated by i} (n_j n_j^T + B_j)/sigma_sq,
+ * h_i = sum_j (r_ij - mean_offset) n_j / sigma_sq, A_i = Lambda_i^-1, m_i = A_i h_i, where
+ * (n_j, B_j) = (other_mean_d, other_cov_d) is the other side's posterior.  other_cov_d == NULL
+ * drops the B_j term (curvature of the MAP objective); mean_d == NULL leaves the means alone.
+ * *fail_d (nullable, device) is set to 1 if a precision is not positive definite. */
+int amf_blocks_half_sweep(const amf_ratings_t* h, int side, int d, const double* other_mean_d,
+                          const double* other_cov_d, double prior_var, double sigma_sq,
+                          double mean_offset, double* prec_d, double* h_d, double* cov_d,
+                          double* mean_d, double* logdet_d, int* fail_d, void* stream);
+
+/* out_d[0 : d*d] = sum_i cov_i, out_d[d*d : 2 d*d] = sum_i mean_i mean_i^T over one side: the
+ * d x d sums that _total_variance (active_pmf.py:605-606) is a bilinear form of. */
+int amf_blocks_sums(int64_t rows, int d, const double* mean_d, const double* cov_d, double* out_d,
+                    void* stream);
+
+typedef struct {
+  int32_t n, m, d;
+  const double *mean_u, *cov_u, *prec_u, *h_u, *logdet_u;
+  const double *mean_v, *cov_v, *prec_v, *h_v, *logdet_v;
+  const double* sums;  /* 4 d*d: sum A_i, sum m_i m_i^T, sum B_j, sum n_j n_j^T (total variance) */
+  double sigma_sq;
+  double entropy0;     /* log det of the whole covariance = sum of all logdet entries */
+} amf_blocks_view_t;
+
+#define AMF_LOOK_ENTROPY 0         /* _approx_entropy of the re-fitted model          */
+#define AMF_LOOK_TOTAL_VARIANCE 1  /* _total_variance of the re-fitted model          */
+#define AMF_WEIGHTS_NONE 0         /* raw evaluations only (evals_d)                   */
+#define AMF_WEIGHTS_DISCRETE 1     /* Delta-cdf of N(rij_mean, rij_sd^2) at nv+1 bounds (:687-689) */
+#define AMF_WEIGHTS_NODES 2        /* v_q = rij_mean + rij_sd * values[q], given weights (:691-699) */
+
+/* E_v[fn(model + (i, j, v))] for ncand candidates, one lane group per candidate: for each of the
+ * nv values `rounds` x (row i given column j, column j given row i) -- a rank-d update of each
+ * d x d precision, a Cholesky and (where needed) an inverse per update -- then the criterion
+ * and the expectation.  bounds_or_weights_d: nv+1 bounds (first/last ignored = -inf/+inf) in
+ * DISCRETE mode, nv weights in NODES mode.  evals_d (ncand, nv) and scores_d (ncand) may be
+ * NULL; best_d as in amf_score_candidates (over scores; meaningless for AMF_WEIGHTS_NONE). */
+int amf_blocks_lookahead(const amf_blocks_view_t* v, int what, int rounds, int64_t ncand,
+                         const int32_t* ci_d, const int32_t* cj_d, int nv, const double* values_d,
+                         int weight_mode, const double* bounds_or_weights_d,
+                         const double* rij_mean_d, const double* rij_sd_d, double* evals_d,
+                         double* scores_d, int maximize, int64_t index_base, amf_best_t* best_d,
+                         int* fail_d, void* stream);
+
+/* pred_variance under the block posterior is a dot product (active_pmf.py:502-524 with a zero
+ * cross block): Var_ij = <A_i, B_j + n_j n_j^T> + <m_i m_i^T, B_j>.  Packs one side's rows into
+ * d(d+1) numbers each (symmetric halves; user side [vech2 A ; vech2 m m^T] with doubled
+ * off-diagonals, item side [vech(B + n n^T) ; vech B]), zero-padded to ld_out, of `dtype` --
+ * amf_score_candidates / amf_pool_score_pred with AMF_CRIT_PRED on the packed tables
+ * (d = d(d+1)) then scores the variance criterion with the same SDDMM kernels as `pred`. */
+int amf_blocks_pack(int dtype, int64_t rows, int d, const double* mean_d, const double* cov_d,
+                    int side, int ld_out, void* out_d, void* stream);
+
+/* norm.sf(cutoff, loc = mean, scale = var) elementwise (the reference passes the variance as the
+ * scale, active_pmf.py:438-439) with the fused arg-best; out_d may be NULL. */
+int amf_prob_ge(int dtype, int64_t n, const void* mean_d, const void* var_d, double cutoff,
+                void* out_d, int maximize, int64_t index_base, amf_best_t* best_d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Matrix-normal approximation MN(mean, Sigma, Omega) (the variant the
  * reference's drugbank / movielens runs use): matrix_normal_exps_cy.pyx:159-216
  * mn_kl_divergence, :219-485 matrixnormal_gradient, mn_active_pmf.py:242-288 fit_normal_kls,

@@ -228,9 +228,6 @@ class BlockPosterior(object):
                                                     tabs[3].data_ptr(), d * d, d, None, 0, 0, 0))
         return self._packed[key][1]
 
-    # widest packed row the flat SDDMM kernel takes (8 lanes x 8 vectors of 16 bytes)
-    _SDDMM_MAX = {"f32": 256, "f64": 128}
-
     def score(self, criterion, ci, cj, name="f64", cutoff=0.0, want_scores=True, maximize=True,
               index_base=0):
         """approx mean / pred_variance / prob_ge for device candidate arrays; returns (scores
@@ -242,10 +239,6 @@ class BlockPosterior(object):
             return S.score_device(N.CRIT_PRED, name, ci, cj, self.d, mu, mv,
                                   want_scores=want_scores, maximize=maximize, index_base=index_base)
         if criterion == N.CRIT_PRED_VARIANCE:
-            if d2 > self._SDDMM_MAX[name]:      # long rows: the gather kernel over the blocks
-                return S.score_device(criterion, name, ci, cj, self.d, view=self.normal_view(name),
-                                      want_scores=want_scores, maximize=maximize,
-                                      index_base=index_base)
             pu, pv = self.packed(name)
             return S.score_device(N.CRIT_PRED, name, ci, cj, d2, pu, pv, want_scores=want_scores,
                                   maximize=maximize, index_base=index_base)

@@ -123,6 +123,58 @@ score_pred_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj
   if (threadIdx.x == 0) part[blockIdx.x] = best;
 }
 
+// Rows longer than 64 vectors (the packed pred_variance tables of blocks.cu at d >= 16: d(d+1)
+// numbers per row, 4.2 KB at d = 32): a warp per group of four candidates, every lane strides
+// over the row in 16-byte vectors with the four item-row loads of a step in flight together;
+// the user row is re-read only when the user changes (sorted pools: it stays in L1).
+template <typename T, bool MAX>
+__global__ void __launch_bounds__(256)
+score_pred_long_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj,
+                       int64_t ncand, const T* __restrict__ U, const T* __restrict__ Vm, int ld,
+                       int nvec, T* __restrict__ scores, int64_t index_base,
+                       Best* __restrict__ part) {
+  using V = typename Vec<T>::type;
+  constexpr int B = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  Best best{0.0, -1};
+  for (int64_t base = warp * B; base < ncand; base += nwarps * B) {
+    int32_t is[B], js[B];
+#pragma unroll
+    for (int s = 0; s < B; ++s) {
+      const int64_t c = base + s < ncand ? base + s : ncand - 1;
+      is[s] = ci[c]; js[s] = cj[c];
+    }
+    T p[B];
+#pragma unroll
+    for (int s = 0; s < B; ++s) p[s] = 0;
+    for (int chunk = lane; chunk < nvec; chunk += 32) {
+      V b[B];
+#pragma unroll
+      for (int s = 0; s < B; ++s) b[s] = reinterpret_cast<const V*>(Vm + (int64_t)js[s] * ld)[chunk];
+      V a = vzero(V());
+#pragma unroll
+      for (int s = 0; s < B; ++s) {
+        if (s == 0 || is[s] != is[s - 1]) a = reinterpret_cast<const V*>(U + (int64_t)is[s] * ld)[chunk];
+        p[s] += vdot(a, b[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < B; ++s) p[s] = warp_sum(p[s]);
+    if (lane < B && base + lane < ncand) {
+      const T mine = lane == 0 ? p[0] : (lane == 1 ? p[1] : (lane == 2 ? p[2] : p[3]));
+      const int64_t c = base + lane;
+      if (scores) __stcs(scores + c, mine);
+      if (better<MAX>((double)mine, c + index_base, best.v, best.i)) {
+        best.v = (double)mine; best.i = c + index_base;
+      }
+    }
+  }
+  best = block_best<MAX>(best);
+  if (threadIdx.x == 0) part[blockIdx.x] = best;
+}
+
 struct NormalView {
   const void *mean_u, *mean_v, *cov_uu, *cov_vv, *cov_uv;
   long long mean_u_stride, mean_v_stride, uu_stride, uu_ld, vv_stride, vv_ld, uv_stride_i,
@@ -195,7 +247,12 @@ static int score_pred(int64_t ncand, const int32_t* ci, const int32_t* cj, int d
   const int nvec = ld / N;
   int lpr = pow2c(nvec), vpl = 1;
   if (lpr > 8) { vpl = lpr / 8; lpr = 8; }    // at most 8 candidates (and partial sums) per lane
-  if (vpl > 8) { set_error("latent dimension too large (ld=%d)", ld); return AMF_ERR_UNSUPPORTED; }
+  if (vpl > 8) {
+    score_pred_long_kernel<T, MAX><<<grid, 256, 0, s>>>(ci, cj, ncand, U, V, ld, nvec, scores,
+                                                        index_base, part);
+    AMF_LAUNCH_CHECK();
+    return AMF_OK;
+  }
   const bool vec = (reinterpret_cast<uintptr_t>(ci) % 16 == 0) && (reinterpret_cast<uintptr_t>(cj) % 16 == 0);
 #define PRED(LPR_, VPL_)                                                                       \
   do {                                                                                         \

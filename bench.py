@@ -51,6 +51,8 @@ def parse_args():
                          "and the U rows of its own user range (the matrix has --users x N rows), only "
                          "dV is all-reduced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the C1-C4 / S2 / S3 / B1 entries (`configs`) and the fp64 rooflines")
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     return ap.parse_args()
 
@@ -403,6 +405,23 @@ def run_ours(a):
     total_ms = t_begin.elapsed_time(t_end)
     grad_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
     score_ms = total_ms - grad_ms          # scoring + selection (+ its collective) up to step end
+    # the step's selection, read BEFORE anything else writes `best`: on N GPUs this is the
+    # all-gathered, reduced winner (global index = shard offset + local index)
+    raw = best.cpu().numpy()
+    bv, bi = float(raw[:1].view(np.float64)[0]), int(raw[1])
+    # independent check of the sharded selection: every rank recomputes its local winner with the
+    # flat (unbucketed) kernel, the records are all-gathered with a plain collective and reduced in
+    # Python with the same rule (best value, lowest global index)
+    chk = torch.zeros(2, dtype=torch.int64, device=U.device)
+    N.check(lib.amf_score_candidates(N.CRIT_PRED, D.code(name), ncand, D.ptr(ci), D.ptr(cj), d, ld,
+                                     D.ptr(U), D.ptr(V), None, 0.0, None, 1, step.index_base,
+                                     D.ptr(chk), D.stream_ptr()))
+    recs = P.gather_winner(chk, world)
+    want_v, want_i = P.winner_from_records(recs, True)
+    assert want_i == bi and want_v == bv, \
+        "sharded selection %r differs from the recomputed winner %r" % ((bv, bi), (want_v, want_i))
+    selection_check = {"ranks": world, "recomputed_with": "score_pred_kernel per rank + all_gather + host reduction",
+                       "equal": True, "local_winner_indices": recs[:, 1].cpu().tolist()}
     # isolated timing of the two dominant kernels for the roofline (same stream, CUDA events)
     kt = step.kernel_times(U, V, params, dU, dV, sums, ci, cj, best, reps=max(5, a.steps // 2))
     tm = torch.tensor([total_ms, grad_ms, score_ms, kt["side_pass_ms"], kt["score_ms"], kt["score_flat_ms"]],
@@ -473,7 +492,6 @@ def run_ours(a):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_grad_s, e2e_score_s = e2e_t.tolist()
     # the two paths must agree on the winner
-    bv, bi = np.frombuffer(best.cpu().numpy().tobytes()[:8], dtype=np.float64)[0], int(best[1].item())
     if world == 1:
         assert best_h.index == bi, "device-resident and end-to-end paths picked different candidates"
 
@@ -481,6 +499,66 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(cnt)
     nnz_all, ncand_all = cnt.tolist()
+
+    # ---- strong scaling as config 5 words it: ONE pool of `ncand` candidates cut over the N GPUs
+    # (rank r scores the r-th contiguous slice of rank 0's... of its own shard: same size, same
+    # statistics), winner all-gathered; the weak-scaling `value` above keeps `ncand` per GPU
+    strong = None
+    if world > 1 and a.pool == "tiled":
+        from active_matrix_factorization_b200 import scoring as S
+        lo, hi = P.shard_bounds(ncand, world, rank)
+        sl_i, sl_j = ci[lo:hi].contiguous(), cj[lo:hi].contiguous()
+        sl_pool = S.Pool(sl_i, sl_j, n, m, name, d)
+        sl_best = torch.zeros(2, dtype=torch.int64, device=U.device)
+
+        def strong_step():
+            sl_pool.score_pred(U, V, False, True, lo, sl_best)
+            rec = P.gather_winner(sl_best, world)
+            N.check(lib.amf_best_reduce(D.ptr(rec), world, 1, D.ptr(sl_best), D.stream_ptr()))
+        for _ in range(3):
+            strong_step()
+        sync()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            strong_step()
+        s1.record()
+        sync()
+        st = torch.tensor([s0.elapsed_time(s1) / a.steps], dtype=torch.float64, device=U.device)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        strong = {"ncand_total": ncand, "ncand_per_gpu": hi - lo, "ms": float(st.item()),
+                  "candidates_per_sec": ncand / (float(st.item()) * 1e-3),
+                  "note": "fixed total pool cut into N contiguous slices, pool kernel + 16-byte winner all-gather + reduction"}
+        sl_pool.close()
+        del sl_i, sl_j
+
+    # ---- parity mode (fp64, the drop-in classes' default dtype) on the same workload ---------
+    f64 = None
+    if world == 1 and name == "f32" and not a.no_configs:
+        from active_matrix_factorization_b200 import scoring as S
+        rat64 = D.Ratings(n, m, prob["ri"], prob["rj"], prob["r"].double(), "f64")
+        U64, V64 = U.double().contiguous(), V.double().contiguous()
+        dU64, dV64 = torch.empty_like(U64), torch.empty_like(V64)
+        step64 = P.ShardedStep(rat64, d, "f64", 1, 0)
+        step64.pool = S.Pool(ci, cj, n, m, "f64", d)
+        kt64 = step64.kernel_times(U64, V64, params, dU64, dV64, sums, ci, cj, best, reps=5)
+        hbm_peak64, _ = peaks()
+        tables64 = (n + m) * d * 8
+        sb, gb = ncand * 8 + tables64, nnz * 16 + 2 * tables64
+        f64 = {"roofline_f64": {"kernel": "pool_pred_kernel<double>", "bound": "hbm", "kernel_ms": kt64["score_ms"],
+                                "algorithmic_bytes": sb, "achieved": sb / (kt64["score_ms"] * 1e-3) / 1e9,
+                                "peak": hbm_peak64, "unit": "GB/s",
+                                "frac": sb / (kt64["score_ms"] * 1e-3) / 1e9 / hbm_peak64, "traffic": None},
+               "roofline_gradient_f64": {"kernel": "tiled_side_kernel<double> x2 + prior_kernel x2", "bound": "hbm",
+                                         "kernel_ms": kt64["side_pass_ms"], "algorithmic_bytes": gb,
+                                         "achieved": gb / (kt64["side_pass_ms"] * 1e-3) / 1e9, "peak": hbm_peak64,
+                                         "unit": "GB/s", "frac": gb / (kt64["side_pass_ms"] * 1e-3) / 1e9 / hbm_peak64,
+                                         "traffic": None,
+                                         "note": "fp64 ratings: 16 algorithmic bytes per rating (i, j, r)"}}
+        step64.pool.close()
+        rat64.close()
+        del U64, V64, dU64, dV64, step64, rat64
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -533,8 +611,19 @@ def run_ours(a):
                         % (("amf_score_pred_host_csr16", "16-bit") if narrow else ("amf_score_pred_host_csr", "32-bit"))},
         "gpu_launches": a.steps * step.launches_per_step,
         "clocks": clocks,
-        "selected": {"value": float(bv), "index": bi},
+        "selected": {"value": float(bv), "index": bi, "check": selection_check},
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if f64 is not None:
+        line.update(f64)
+    if not a.no_configs:
+        from benchmarks import config_lines as CL
+        line["configs"] = CL.all_configs(hbm_peak)
+        try:
+            line["configs"]["c5_extra"] = CL.c5_extra(rat, n, m, d, ci, cj, hbm_peak, name)
+        except Exception as exc:
+            line["configs"]["c5_extra"] = {"failed": repr(exc)[:300]}
     if world == 1 and not a.no_cpu_baseline:
         host = (prob["ri"][:a.cpu_sample].cpu().numpy(), prob["rj"][:a.cpu_sample].cpu().numpy(),
                 prob["r"][:a.cpu_sample].double().cpu().numpy(), U.cpu().numpy(), V.cpu().numpy(),

@@ -699,8 +699,13 @@ class ActivePMF(ProbabilisticMatrixFactorization):
             hit = self._dev.get('pool_array')
             if hit is not None and hit[0] is pool:
                 return pool, hit[1], hit[2]
-            ci = _D.to_device(pool[:, 0], np.int32)
-            cj = _D.to_device(pool[:, 1], np.int32)
+            if pool.dtype == np.int32 and pool.flags.c_contiguous:
+                # one H2D copy of the (n, 2) array, split into the two index vectors on the device
+                both = torch.from_numpy(pool).to(_D.device())
+                ci, cj = both[:, 0].contiguous(), both[:, 1].contiguous()
+            else:
+                ci = _D.to_device(pool[:, 0], np.int32)
+                cj = _D.to_device(pool[:, 1], np.int32)
             self._dev['pool_array'] = (pool, ci, cj)
             return pool, ci, cj
         pool = list(pool)

@@ -128,7 +128,10 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
         n = feats.shape[0]
         # the O(N d^2) moments of the factor matrix on the device; d x d algebra + RNG on the host
-        ft = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float64)).to(D.device())
+        if isinstance(feats, torch.Tensor):        # fast mode: the sample never left the device
+            ft = feats.to(torch.float64)
+        else:
+            ft = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float64)).to(D.device())
         x_bar = ft.mean(dim=0).cpu().numpy()
         s_bar = np.atleast_2d(torch.cov(ft.T).cpu().numpy()) if feats.shape[1] > 1 else \
             np.array(float(ft.var(unbiased=True).item()))
@@ -237,6 +240,12 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         (user_sample, item_sample) forever.  Ratings added after the generator started are
         ignored, like in the reference.
         '''
+        if self.rng_mode == 'device':
+            for us, vs in self.samples_device(num_gibbs=num_gibbs, fit_first=fit_first):
+                yield us.to(torch.float64).cpu().numpy(), vs.to(torch.float64).cpu().numpy()
+            return
+        if self.rng_mode != 'host':
+            raise ValueError("rng_mode must be 'host' or 'device'")
         name = self.dtype_name
         dt = D.np_dtype(name)
         n, m, d = self.num_users, self.num_items, self.latent_d
@@ -261,6 +270,51 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
             user_sample = users_t.to(torch.float64).cpu().numpy()
             item_sample = items_t.to(torch.float64).cpu().numpy()
             yield user_sample, item_sample
+
+    # 'host': every normal comes from numpy's legacy global stream in the reference's draw order
+    # (seeded chains reproduce the reference's samples).  'device': the (N+M) d normals of every
+    # half-sweep are generated inside the kernel (Philox4x32-10) and each row needs one Cholesky
+    # (amf_gibbs_half_sweep_device_rng): the same Markov chain in law, several times faster.
+    rng_mode = 'host'
+    device_seed = 0
+
+    def samples_device(self, num_gibbs=2, fit_first=False, seed=None):
+        '''Fast-mode chain (bayes_pmf.py:227-302 in law): yields (user_sample, item_sample) as
+        DEVICE tensors of the compute dtype; the criteria (`predict`, `pred_variance`, ...) take
+        them as they are.  Only the d x d hyper-parameter draws touch the host.'''
+        lib = N.require_device()
+        name = self.dtype_name
+        dt = D.np_dtype(name)
+        n, m, d = self.num_users, self.num_items, self.latent_d
+        rat = D.Ratings.from_tuples(self.ratings, n, m, name)
+        if fit_first:
+            self.do_fit()
+        seed = int(self.device_seed if seed is None else seed)
+        users_t = D.to_device(self.users, dt)
+        items_t = D.to_device(self.items, dt)
+        tdt = D.torch_dtype(name)
+        stream_id = 0
+
+        def half(side, other_t, mu, alpha, rows):
+            nonlocal stream_id
+            out = torch.empty((rows, d), dtype=tdt, device=other_t.device)
+            alpha_t = D.to_device(np.atleast_2d(alpha), dt)
+            mu_t = D.to_device(np.atleast_1d(mu), dt)
+            N.check(lib.amf_gibbs_half_sweep_device_rng(
+                rat.handle, side, D.code(name), d, D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
+                float(self.beta), float(self._mean_offset()), seed, stream_id, D.ptr(out), 0, -1,
+                D.stream_ptr()))
+            stream_id += 1
+            return out
+
+        while True:
+            mu_u, alpha_u = self.sample_hyperparam(users_t, True)
+            mu_v, alpha_v = self.sample_hyperparam(items_t, False)
+            for _gibbs in range(num_gibbs):
+                users_t = half(0, items_t, mu_u, alpha_u, n)
+                items_t = half(1, users_t, mu_v, alpha_v, m)
+            self._check_gibbs(rat)
+            yield users_t, items_t
 
     def samples_parallel(self, num_gibbs=2, pool=None, multiproc_mode=None, fit_first=False):
         '''(bayes_pmf.py:306-424) the row fan-out is the GPU launch; `pool` is not needed.'''
@@ -301,9 +355,13 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         if not samples:
             raise StopIteration
         n, m, d = self.num_users, self.num_items, self.latent_d
-        us = D.to_device(np.stack([np.asarray(u) for u, _ in samples]), dt)
-        vs = D.to_device(np.stack([np.asarray(v) for _, v in samples]), dt)
         tdt = D.torch_dtype(name)
+        if isinstance(samples[0][0], torch.Tensor):   # samples_device(): stack where they are
+            us = torch.stack([u for u, _ in samples]).to(tdt).contiguous()
+            vs = torch.stack([v for _, v in samples]).to(tdt).contiguous()
+        else:
+            us = D.to_device(np.stack([np.asarray(u) for u, _ in samples]), dt)
+            vs = D.to_device(np.stack([np.asarray(v) for _, v in samples]), dt)
         whole = which is None or which is Ellipsis
         if whole:
             i_idx = j_idx = None

@@ -434,6 +434,76 @@ __device__ bool warp_solve32(const double* Lam, int d, int lda, double* scr, dou
   return ok;
 }
 
+// ---- fast mode: device random numbers and one factorisation -----------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = (row, component, stream lo, stream hi), key =
+// seed: every normal of a chain has its own counter, so a sweep needs no generator state and the
+// rows can be sampled in any order on any number of GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// one standard normal (Box-Muller on the first two words; uniforms in (0, 1])
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned long long stream,
+                                                uint32_t row, uint32_t comp) {
+  const uint4 r = philox4x32_10(make_uint4(row, comp, (uint32_t)stream, (uint32_t)(stream >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const double u1 = ((double)r.x + 1.0) * 2.3283064365386963e-10;
+  const double u2 = ((double)r.y + 1.0) * 2.3283064365386963e-10;
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(unsigned long long seed, unsigned long long stream, int64_t rows, int d,
+                     T* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < rows * d;
+       t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = (T)philox_normal(seed, stream, (uint32_t)(t / d), (uint32_t)(t % d));
+}
+
+// Fast-mode row sample: Lambda = R R', sample = R^-T (R^-1 rhs + z) ~ N(Lambda^-1 rhs, Lambda^-1).
+// One Cholesky and two triangular solves instead of the reference's inv + second Cholesky
+// (bayes_pmf.py:208-216) -- the same distribution, a different map from z to the sample.
+template <typename T>
+__device__ bool warp_solve32_fast(const double* Lam, int d, int lda, double* scr, double* col,
+                                  double rhs_lane, double z_lane, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  double a[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = (lane < d && k < d) ? Lam[lane * lda + k] : (k == lane ? 1.0 : 0.0);
+  __syncwarp();
+  const bool ok = chol32_rows(a, col, lane);
+  // lane i holds row i of R; forward substitution R y = rhs, then w = y + z
+  double diag = 1.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) if (k == lane) diag = a[k];
+  const double inv_diag = 1.0 / diag;
+  double sacc = rhs_lane;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const double yk = __shfl_sync(0xffffffffu, sacc * inv_diag, k);   // final once lanes < k are done
+    if (lane > k) sacc = fma(-a[k], yk, sacc);
+  }
+  double w = sacc * inv_diag + (lane < d ? z_lane : 0.0);
+  // R' x = w: row k of R is column k of R'; rows go through the scratch
+#pragma unroll
+  for (int k = 0; k < 32; ++k) scr[lane * S32 + k] = k <= lane ? a[k] : 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 31; k >= 0; --k) {
+    const double xk = __shfl_sync(0xffffffffu, w * inv_diag, k);
+    if (lane < k) w = fma(-scr[k * S32 + lane], xk, w);
+  }
+  if (lane < d) out[lane] = (T)(w * inv_diag);
+  return ok;
+}
+
 // ---- d <= 32: one WARP per row ---------------------------------------------------------------
 // The per-row work after the Gram matrix is a chain of ~100 short dependent steps (two Cholesky
 // factorisations, a triangular inverse) on a matrix of at most 32 x 32: with a CTA per row the
@@ -443,14 +513,15 @@ __device__ bool warp_solve32(const double* Lam, int d, int lda, double* scr, dou
 //   of the row taken by the one warp; otherwise 2 x 2 register blocks spread over the 32 lanes.
 constexpr int GIBBS_WARP_MAXBLK = (16 * 17 / 2 + 31) / 32;   // 2 x 2 blocks per lane at d = 32
 
-template <typename T, bool TC>
+template <typename T, bool TC, bool FAST>
 __global__ void __launch_bounds__(GIBBS_THREADS, 3)   // <= 168 registers: 12 warps per SM
 gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const T* __restrict__ val, int row_begin, int rows, int d,
                        const T* __restrict__ other, const T* __restrict__ alpha,
                        const T* __restrict__ mu, double beta, double mean_offset,
                        const T* __restrict__ z, T* __restrict__ out, int* __restrict__ fail,
-                       int a_doubles, int warp_doubles) {
+                       int a_doubles, int warp_doubles, unsigned long long seed,
+                       unsigned long long stream_id) {
   extern __shared__ double smem[];
   constexpr int NW = GIBBS_THREADS / 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -613,8 +684,14 @@ gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
       for (int l = 0; l < d; ++l) rhs_lane += (double)alpha[lane * d + l] * (double)mu[l];
     }
     __syncwarp();
-    const bool ok = warp_solve32<T>(A, d, lda, A, col, vec, rhs_lane, z + (int64_t)row * d,
-                                    out + (int64_t)row * d);
+    bool ok;
+    if (FAST) {
+      const double zl = lane < d ? philox_normal(seed, stream_id, (uint32_t)row, (uint32_t)lane) : 0.0;
+      ok = warp_solve32_fast<T>(A, d, lda, A, col, rhs_lane, zl, out + (int64_t)row * d);
+    } else {
+      ok = warp_solve32<T>(A, d, lda, A, col, vec, rhs_lane, z + (int64_t)row * d,
+                           out + (int64_t)row * d);
+    }
     if (!ok && lane == 0) atomicExch(fail, 1);
     __syncwarp();
   }
@@ -762,7 +839,8 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
 template <typename T>
 static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, const T* alpha,
                         const T* mu, double beta, double mean_offset, const T* z, T* out,
-                        int row_begin, int row_end, cudaStream_t s) {
+                        int row_begin, int row_end, cudaStream_t s, bool fast = false,
+                        unsigned long long seed = 0, unsigned long long stream_id = 0) {
   const int all_rows = side == 0 ? h->n_users : h->n_items;
   if (row_end < 0 || row_end > all_rows) row_end = all_rows;
   if (row_begin < 0) row_begin = 0;
@@ -782,23 +860,31 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
     const size_t smem_w = sizeof(double) * (size_t)warp_doubles * (GIBBS_THREADS / 32);
     const int nwarp_rows = (span + GIBBS_THREADS / 32 - 1) / (GIBBS_THREADS / 32);
     const int grid_w = nwarp_rows < num_sms() * 8 ? nwarp_rows : num_sms() * 8;
-#define GIBBS_WARP(TC_)                                                                          \
+#define GIBBS_WARP(TC_, FAST_)                                                                   \
   do {                                                                                           \
-    AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_>,                                \
+    AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_, FAST_>,                         \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));    \
-    gibbs_rows_warp_kernel<T, TC_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(                        \
+    gibbs_rows_warp_kernel<T, TC_, FAST_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(                 \
         h->ptr[side], h->idx[side], (const T*)h->val[side], row_begin, rows, d, other, alpha, mu, \
-        beta, mean_offset, z, out, fail, a_doubles, warp_doubles);                               \
+        beta, mean_offset, z, out, fail, a_doubles, warp_doubles, seed, stream_id);              \
   } while (0)
     if constexpr (sizeof(T) == 4) {
-      if (tc) GIBBS_WARP(true); else GIBBS_WARP(false);
+      if (tc) { if (fast) GIBBS_WARP(true, true); else GIBBS_WARP(true, false); }
+      else { if (fast) GIBBS_WARP(false, true); else GIBBS_WARP(false, false); }
     } else {
-      GIBBS_WARP(false);
+      if (fast) GIBBS_WARP(false, true); else GIBBS_WARP(false, false);
     }
 #undef GIBBS_WARP
     AMF_LAUNCH_CHECK();
     return AMF_OK;
   }
+  T* z_tmp = nullptr;
+  if (fast) {   // d > 32: the CTA-per-row kernels take z from memory; fill it with the same counters
+    AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&z_tmp), sizeof(T) * (size_t)rows * d, s));
+    philox_normal_kernel<T><<<num_sms() * 8, 256, 0, s>>>(seed, stream_id, rows, d, z_tmp);
+    z = z_tmp;
+  }
+  struct FreeZ { T* p; cudaStream_t s; ~FreeZ() { if (p) cudaFreeAsync(p, s); } } free_z{z_tmp, s};
   if constexpr (sizeof(T) == 4) {
     if (d == 64) {                       // dense enough for whole MMA tiles: tensor-core Gram
       const int mt = d / 16, ntiles = mt * (mt + 1);
@@ -866,6 +952,44 @@ int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d
   return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
                               (const double*)mu_d, beta, mean_offset, (const double*)z_d,
                               (double*)out_d, row_begin, row_end, s);
+}
+
+int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype, int d,
+                                    const void* other_d, const void* alpha_d, const void* mu_d,
+                                    double beta, double mean_offset, uint64_t seed,
+                                    uint64_t stream_id, void* out_d, int32_t row_begin,
+                                    int32_t row_end, void* stream) {
+  AMF_REQUIRE(h && other_d && alpha_d && mu_d && out_d, "amf_gibbs_half_sweep_device_rng: NULL argument");
+  AMF_REQUIRE(side == 0 || side == 1, "amf_gibbs_half_sweep_device_rng: side must be 0 or 1");
+  AMF_REQUIRE(dtype == h->dtype, "amf_gibbs_half_sweep_device_rng: dtype does not match the rating list");
+  AMF_REQUIRE(d >= 1 && d <= GIBBS_MAXD, "amf_gibbs_half_sweep_device_rng: latent_d=%d unsupported (max %d)",
+              d, GIBBS_MAXD);
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = ratings_compact(const_cast<amf_ratings*>(h), s);
+    if (rc != AMF_OK) return rc;
+  }
+  if (dtype == AMF_F32)
+    return gibbs_launch<float>(h, side, d, (const float*)other_d, (const float*)alpha_d,
+                               (const float*)mu_d, beta, mean_offset, nullptr, (float*)out_d,
+                               row_begin, row_end, s, true, seed, stream_id);
+  return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
+                              (const double*)mu_d, beta, mean_offset, nullptr, (double*)out_d,
+                              row_begin, row_end, s, true, seed, stream_id);
+}
+
+int amf_philox_normal(int dtype, uint64_t seed, uint64_t stream_id, int64_t rows, int d,
+                      void* out_d, void* stream) {
+  AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_philox_normal: bad dtype");
+  AMF_REQUIRE(rows >= 0 && d >= 1 && out_d, "amf_philox_normal: bad arguments");
+  if (rows == 0) return AMF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == AMF_F32)
+    philox_normal_kernel<float><<<num_sms() * 8, 256, 0, s>>>(seed, stream_id, rows, d, (float*)out_d);
+  else
+    philox_normal_kernel<double><<<num_sms() * 8, 256, 0, s>>>(seed, stream_id, rows, d, (double*)out_d);
+  AMF_LAUNCH_CHECK();
+  return AMF_OK;
 }
 
 int amf_gibbs_status(const amf_ratings_t* h, int* failed, void* stream) {

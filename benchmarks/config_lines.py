@@ -67,20 +67,29 @@ def roof(bytes_, flops, ms, hbm_peak):
 
 
 def c1_exact_lookahead():
-    """C1: 10x10, rank 2 -- exact (full-covariance) mode: the uv-entropy lookahead over the whole
-    pool is one launch of one CTA per (candidate, value) variational re-fit"""
+    """C1: 10x10, two rating levels, rank 2, diagonal known -- exact (full-covariance) mode: MAP
+    fit, variational fit, pred-variance pick, and the uv-entropy lookahead over the whole pool as
+    one launch of one CTA per (candidate, value) variational re-fit"""
     from active_matrix_factorization_b200 import active_pmf as A
-    g = golden("known_answer_10x10_d2")
-    a = A.ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)
+    rng = np.random.RandomState(0)
+    u, v = rng.normal(0, 2, (10, 2)), rng.normal(0, 2, (10, 2))
+    real = ((u @ v.T + rng.normal(0, .25, (10, 10))) > 0).astype(float)
+    ratings = np.array([(i, i, real[i, i]) for i in range(10)])
+    np.random.seed(0)
+    a = A.ActivePMF(ratings, 2, rating_values={0, 1}, discrete_expectations=True)
     a.approx_mode = 'exact'
-    a.users, a.items = g["users"].copy(), g["items"].copy()
-    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+    t0 = time.perf_counter()
+    a.fit()
+    a.initialize_approx()
+    steps = len(list(a.fit_normal_kls()))
+    fit_s = time.perf_counter() - t0
     pool = sorted(a.unrated)
     ms = wall_ms(lambda: a._get_key_vals(pool, A.ActivePMF.exp_approx_entropy), reps=2)
     pv_ms = wall_ms(lambda: a.pick_query_point(pool, A.ActivePMF.pred_variance))
-    return {"config": "C1 10x10 rank 2, exact mode (k = 40)", "candidates": len(pool),
+    return {"config": "C1 10x10, 2 levels, rank 2, exact mode (k = 40)", "candidates": len(pool),
+            "map_plus_variational_fit_s": fit_s, "fit_normal_steps": steps,
             "uv_entropy_ms": ms, "uv_entropy_cand_per_s": len(pool) / (ms * 1e-3),
-            "refits_per_s": 2 * len(pool) / (ms * 1e-3), "pick_pred_variance_ms": pv_ms}
+            "values": 2, "refits_per_s": 2 * len(pool) / (ms * 1e-3), "pick_pred_variance_ms": pv_ms}
 
 
 def c2_drugbank(hbm_peak):
@@ -248,6 +257,17 @@ def c4_bayes(hbm_peak):
         flops = 2 * nnz * (2 * d * d + 2 * d) + (n + m) * d ** 3
         out["B1_gibbs_sweep_" + name] = roof(bytes_, flops, ms, hbm_peak)
         out["B1_gibbs_sweep_" + name]["rows_per_s"] = (n + m) / (ms * 1e-3)
+
+        def fast_sweep():
+            N.check(lib.amf_gibbs_half_sweep_device_rng(rat.handle, 0, D.code(name), d, D.ptr(it), D.ptr(alpha),
+                                                        D.ptr(mu), 2.0, float(b.mean_rating), 1, 2, D.ptr(ou),
+                                                        0, -1, D.stream_ptr()))
+            N.check(lib.amf_gibbs_half_sweep_device_rng(rat.handle, 1, D.code(name), d, D.ptr(us), D.ptr(alpha),
+                                                        D.ptr(mu), 2.0, float(b.mean_rating), 1, 3, D.ptr(ov),
+                                                        0, -1, D.stream_ptr()))
+        ms = cuda_ms(fast_sweep)
+        out["B1_gibbs_sweep_device_rng_" + name] = roof(bytes_ - (n + m) * d * es, flops, ms, hbm_peak)
+        out["B1_gibbs_sweep_device_rng_" + name]["rows_per_s"] = (n + m) / (ms * 1e-3)
         rat.close()
     known = np.zeros((n, m), bool)
     known[R[:, 0].astype(int), R[:, 1].astype(int)] = True
@@ -302,6 +322,16 @@ def c5_extra(rat, n, m, d, ci, cj, hbm_peak, name="f32"):
     out["B1_gibbs_sweep_c5_" + name] = roof(2 * nnz * (4 + es) + (n + m) * 3 * d * es,
                                             2 * nnz * (2 * d * d + 2 * d) + (n + m) * d ** 3, ms, hbm_peak)
     out["B1_gibbs_sweep_c5_" + name]["rows_per_s"] = (n + m) / (ms * 1e-3)
+
+    def fast_sweep():
+        N.check(lib.amf_gibbs_half_sweep_device_rng(rat.handle, 0, D.code(name), d, D.ptr(it), D.ptr(alpha),
+                                                    D.ptr(mu), 2.0, 0.0, 1, 2, D.ptr(ou), 0, -1, D.stream_ptr()))
+        N.check(lib.amf_gibbs_half_sweep_device_rng(rat.handle, 1, D.code(name), d, D.ptr(us), D.ptr(alpha),
+                                                    D.ptr(mu), 2.0, 0.0, 1, 3, D.ptr(ov), 0, -1, D.stream_ptr()))
+    ms = cuda_ms(fast_sweep, reps=3, warm=1)
+    out["B1_gibbs_sweep_device_rng_c5_" + name] = roof(2 * nnz * (4 + es) + (n + m) * 2 * d * es,
+                                                       2 * nnz * (2 * d * d + 2 * d) + (n + m) * d ** 3, ms, hbm_peak)
+    out["B1_gibbs_sweep_device_rng_c5_" + name]["rows_per_s"] = (n + m) / (ms * 1e-3)
     del zu, zv, ou, ov
     # block posterior at the MAP curvature (one Gram pass per side), then the variance criterion
     post = BL.BlockPosterior(n, m, d, 1.0, 10.0, 10.0)

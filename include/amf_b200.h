@@ -267,6 +267,22 @@ int amf_gibbs_half_sweep_rows(const amf_ratings_t* h, int side, int dtype, int d
                               double beta, double mean_offset, const void* z_d, void* out_d,
                               int32_t row_begin, int32_t row_end, void* stream);
 
+/* Fast mode of the half-sweep: the standard normals are generated inside the kernel (Philox4x32-10,
+ * counter = (row, component, stream_id), key = seed: stateless, any row order, any number of
+ * GPUs) and the row is sampled from ONE Cholesky factor of the precision,
+ *   Lambda = R R',  out[n] = R^-T (R^-1 rhs + z)  ~  N(Lambda^-1 rhs, Lambda^-1),
+ * instead of chol(inv(Lambda)) (bayes_pmf.py:208-216): same conditional distribution, different
+ * map from z to the sample, so chains are equal in law to the reference's, not draw for draw.
+ * Use a fresh stream_id for every half-sweep of a chain. */
+int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype, int d,
+                                    const void* other_d, const void* alpha_d, const void* mu_d,
+                                    double beta, double mean_offset, uint64_t seed,
+                                    uint64_t stream_id, void* out_d, int32_t row_begin,
+                                    int32_t row_end, void* stream);
+/* The same normals as an array: out_d[(row, k)] = z of (seed, stream_id, row, k). */
+int amf_philox_normal(int dtype, uint64_t seed, uint64_t stream_id, int64_t rows, int d,
+                      void* out_d, void* stream);
+
 /* 1 in *failed if any row of ANY half-sweep on this handle since the previous call of this
  * function met a non-positive-definite precision/covariance (np.linalg.cholesky would have
  * raised LinAlgError).  The flag is sticky: half-sweeps only set it, this call reads and

@@ -199,3 +199,106 @@ def test_exp_variance_golden(Bm, golden, tag, kw):
     np.random.seed(5)
     ev = b.exp_variance(samples, which=which, num_samps=3, fit_first=False)
     np.testing.assert_allclose(ev, c["ev_" + tag], rtol=1e-6)
+
+
+# ---- fast mode: device random numbers, one Cholesky per row -----------------------------------
+def _philox4x32_10(ctr, key):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = list(ctr)
+    k = list(key)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xffffffff, p1 & 0xffffffff,
+             ((p0 >> 32) ^ c[3] ^ k[1]) & 0xffffffff, p0 & 0xffffffff]
+        k = [(k[0] + W0) & 0xffffffff, (k[1] + W1) & 0xffffffff]
+    return c
+
+
+def _device_normals(seed, stream_id, rows, d, dtype="f64"):
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D
+    out = torch.empty((rows, d), dtype=D.torch_dtype(dtype), device="cuda")
+    N.check(N.require_device().amf_philox_normal(D.code(dtype), seed, stream_id, rows, d, D.ptr(out),
+                                                 D.stream_ptr()))
+    return out.double().cpu().numpy()
+
+
+def test_philox_known_answer_and_normals():
+    """Philox4x32-10: the published test vectors (Random123 kat_vectors) for the host restatement,
+    and the kernel's normals against Box-Muller on that restatement's words"""
+    assert _philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    seed, stream = 0x0123456789abcdef, (7 << 32) | 5
+    z = _device_normals(seed, stream, 6, 4)
+    for row in range(6):
+        for k in range(4):
+            w = _philox4x32_10([row, k, stream & 0xffffffff, stream >> 32], [seed & 0xffffffff, seed >> 32])
+            u1, u2 = (w[0] + 1.0) * 2.0 ** -32, (w[1] + 1.0) * 2.0 ** -32
+            assert z[row, k] == pytest.approx(np.sqrt(-2 * np.log(u1)) * np.cos(2 * np.pi * u2), rel=1e-12, abs=1e-13)
+    big = _device_normals(3, 1, 20000, 16)
+    assert abs(big.mean()) < 0.01 and abs(big.var() - 1) < 0.01
+    assert abs(np.corrcoef(big[:, 0], big[:, 1])[0, 1]) < 0.03
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 2e-4)])
+@pytest.mark.parametrize("d", [3, 15, 32])
+def test_fast_half_sweep_is_the_same_conditional(d, dtype, tol):
+    """amf_gibbs_half_sweep_device_rng: with z the kernel's own normals (amf_philox_normal, same
+    counters) every row equals Lambda^-1 rhs + R^-T z for Lambda = R R' (bayes_pmf.py:189-216
+    with the one-factor map); its mean and covariance are those of the reference's conditional"""
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D
+    lib = N.require_device()
+    rng = np.random.RandomState(d)
+    n, m = 40, 30
+    cells = rng.permutation(n * m)[:500]
+    R = np.column_stack((cells // m, cells % m, rng.normal(3, 1, 500)))
+    R = R[R[:, 0] != 2]                                     # a row without ratings
+    other = rng.normal(0, .5, (m, d))
+    a0 = rng.normal(0, 1, (d, d))
+    alpha, mu, beta, off = a0 @ a0.T / d + np.eye(d), rng.normal(0, .3, d), 2.0, 3.0
+    rat = D.Ratings.from_tuples(R, n, m, dtype)
+    dt = D.np_dtype(dtype)
+    out = torch.empty((n, d), dtype=D.torch_dtype(dtype), device="cuda")
+    seed, stream = 99, 12
+    N.check(lib.amf_gibbs_half_sweep_device_rng(
+        rat.handle, 0, D.code(dtype), d, D.ptr(D.to_device(other, dt)), D.ptr(D.to_device(alpha, dt)),
+        D.ptr(D.to_device(mu, dt)), beta, off, seed, stream, D.ptr(out), 0, -1, D.stream_ptr()))
+    got = out.double().cpu().numpy()
+    z = _device_normals(seed, stream, n, d)
+    for i in range(n):
+        rows = R[R[:, 0] == i]
+        F = other[rows[:, 1].astype(int)]
+        lam = alpha + beta * F.T @ F
+        rhs = beta * F.T @ (rows[:, 2] - off) + alpha @ mu
+        Rf = np.linalg.cholesky(lam)
+        want = np.linalg.solve(Rf.T, np.linalg.solve(Rf, rhs) + z[i])
+        assert np.abs(got[i] - want).max() <= tol * max(1.0, np.abs(want).max())
+    rat.close()
+
+
+def test_fast_chain_matches_host_chain_in_law(Bm, golden):
+    """device-RNG chain against the host-RNG (reference-order) chain on the same model: posterior
+    mean and variance of the predictions agree within Monte-Carlo error"""
+    g = golden("gibbs_15x12_d3")
+    b = Bm.BayesianPMF(g["ratings"], 3, subtract_mean=True)
+    b.users, b.items = g["users"].copy(), g["items"].copy()
+    S, burn = 1500, 100
+    np.random.seed(11)
+    host = list(islice(b.samples(num_gibbs=2), S + burn))[burn:]
+    np.random.seed(12)
+    b.device_seed = 5
+    dev = list(islice(b.samples_device(num_gibbs=2), S + burn))[burn:]
+    import torch
+    assert isinstance(dev[0][0], torch.Tensor)
+    mh, md = b.predict(host), b.predict(dev)
+    vh, vd = b.pred_variance(host), b.pred_variance(dev)
+    # Monte-Carlo error of a mean over ~S/10 effective samples of spread sqrt(v)
+    assert np.abs(mh - md).max() < 6 * np.sqrt(vh.max() / (S / 10))
+    assert np.abs(np.log(vd / vh)).max() < 0.6
+    # drop-in switch: samples() in device mode yields host arrays
+    b.rng_mode = 'device'
+    us, vs = next(b.samples())
+    assert isinstance(us, np.ndarray) and us.shape == (15, 3) and vs.shape == (12, 3)

@@ -145,7 +145,7 @@ def test_lookahead_matches_fixture(K, golden, name, n, m, d):
 def test_lookahead_large_d_and_ragged_pool(K):
     """d = 16 and 32 (16- and 32-lane groups), pool sizes that do not fill the last warp"""
     for n, m, d, ncand in ((20, 25, 16, 37), (10, 12, 32, 5), (30, 40, 10, 1)):
-        R, U, V = _problem(7 + d, n, m, d, 200, values=(1, 2, 3, 4, 5))
+        R, U, V = _problem(7 + d, n, m, d, min(200, n * m - 10), values=(1, 2, 3, 4, 5))
         _rat, post = _fit_device(K, R, n, m, d, U, V, sweeps=6)
         h = post.to_host()
         st = K.B.Blocks(h.mean_u, h.mean_v, h.A, h.B, h.Lu, h.Lv, h.hu, h.hv, 1., 10., 10.)

@@ -89,6 +89,8 @@ PROTOTYPES = {
     "amf_gibbs_status": [_P, C.POINTER(_INT), _P],
     "amf_bayes_sample_stats": [_INT, _I64, _P, _P, _INT, _I32, _I32, _INT, _P, _P, _F64, _F64,
                                _P, _P, _P, _INT, _INT, _I64, _P, _P],
+    "amf_bayes_sample_stats_dense_tc": [_INT, _I32, _I32, _INT, _P, _P, _F64, _P, _P, _INT, _INT,
+                                        _I64, _P, _P],
     "amf_normal_workspace_doubles": [_I32, _I32, _INT],
     "amf_normal_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
                            _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],

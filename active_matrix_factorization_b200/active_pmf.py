@@ -215,7 +215,7 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         return mode == 'blocks' or (mode == 'auto' and self.approx_dim > self.exact_max_dim)
 
     def _in_blocks(self, cov=None):
-        return isinstance(self.cov if cov is None else cov, _blocks.BlockDiagonal)
+        return isinstance(getattr(self, 'cov', None) if cov is None else cov, _blocks.BlockDiagonal)
 
     def _new_block_posterior(self):
         return _blocks.BlockPosterior(self.num_users, self.num_items, self.latent_d, self.sigma_sq,

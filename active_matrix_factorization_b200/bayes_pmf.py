@@ -125,8 +125,6 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         (bayes_pmf.py:157-186).  d x d host algebra; the reference's scalar inner product at
         :176 (np.dot of two 1-D vectors) is kept.
         '''
-        wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
-        n = feats.shape[0]
         # the O(N d^2) moments of the factor matrix on the device; d x d algebra + RNG on the host
         if isinstance(feats, torch.Tensor):        # fast mode: the sample never left the device
             ft = feats.to(torch.float64)
@@ -135,6 +133,11 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         x_bar = ft.mean(dim=0).cpu().numpy()
         s_bar = np.atleast_2d(torch.cov(ft.T).cpu().numpy()) if feats.shape[1] > 1 else \
             np.array(float(ft.var(unbiased=True).item()))
+        return self._hyperparam_from_moments(feats.shape[0], x_bar, s_bar, do_users)
+
+    def _hyperparam_from_moments(self, n, x_bar, s_bar, do_users):
+        '''the d x d part of sample_hyperparam (bayes_pmf.py:166-186) given mean and covariance'''
+        wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
         diff = mu0 - x_bar
         wi_post = np.linalg.inv(np.linalg.inv(wi) + n * s_bar
                                 + (b0 * n) / (b0 + n) * np.dot(diff, diff.T))
@@ -294,25 +297,43 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         items_t = D.to_device(self.items, dt)
         tdt = D.torch_dtype(name)
         stream_id = 0
+        dd = d * d
+        hyper_h = torch.empty(2 * (d + dd), dtype=tdt).pin_memory()
 
-        def half(side, other_t, mu, alpha, rows):
+        def half(side, other_t, hyper_t, rows):
             nonlocal stream_id
             out = torch.empty((rows, d), dtype=tdt, device=other_t.device)
-            alpha_t = D.to_device(np.atleast_2d(alpha), dt)
-            mu_t = D.to_device(np.atleast_1d(mu), dt)
+            o = side * (d + dd)
             N.check(lib.amf_gibbs_half_sweep_device_rng(
-                rat.handle, side, D.code(name), d, D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
-                float(self.beta), float(self._mean_offset()), seed, stream_id, D.ptr(out), 0, -1,
-                D.stream_ptr()))
+                rat.handle, side, D.code(name), d, D.ptr(other_t), D.ptr(hyper_t[o + d:o + d + dd]),
+                D.ptr(hyper_t[o:o + d]), float(self.beta), float(self._mean_offset()), seed,
+                stream_id, D.ptr(out), 0, -1, D.stream_ptr()))
             stream_id += 1
             return out
 
+        def moments(t):
+            t64 = t.to(torch.float64)
+            mean = t64.mean(dim=0)
+            c = t64 - mean
+            return mean, (c.T @ c) / (t.shape[0] - 1)
+
         while True:
-            mu_u, alpha_u = self.sample_hyperparam(users_t, True)
-            mu_v, alpha_v = self.sample_hyperparam(items_t, False)
+            # ONE device->host read per sample: means and covariances of both factor matrices
+            mu_m, mu_c = moments(users_t)
+            mv_m, mv_c = moments(items_t)
+            mom = torch.cat((mu_m, mu_c.reshape(-1), mv_m, mv_c.reshape(-1))).cpu().numpy()
+            sc_u = mom[d:d + dd].reshape(d, d) if d > 1 else np.array(float(mom[d]))
+            sc_v = mom[2 * d + dd:].reshape(d, d) if d > 1 else np.array(float(mom[2 * d + dd]))
+            mu_u, alpha_u = self._hyperparam_from_moments(n, mom[:d], sc_u, True)
+            mu_v, alpha_v = self._hyperparam_from_moments(m, mom[d + dd:2 * d + dd], sc_v, False)
+            # ... and ONE host->device copy of both sides' (mu, alpha)
+            hyper_h.copy_(torch.from_numpy(np.concatenate(
+                (np.atleast_1d(mu_u), np.atleast_2d(alpha_u).reshape(-1),
+                 np.atleast_1d(mu_v), np.atleast_2d(alpha_v).reshape(-1))).astype(dt)))
+            hyper_t = hyper_h.to(users_t.device, non_blocking=True)
             for _gibbs in range(num_gibbs):
-                users_t = half(0, items_t, mu_u, alpha_u, n)
-                items_t = half(1, users_t, mu_v, alpha_v, m)
+                users_t = half(0, items_t, hyper_t, n)
+                items_t = half(1, users_t, hyper_t, m)
             self._check_gibbs(rat)
             yield users_t, items_t
 

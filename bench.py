@@ -418,7 +418,9 @@ def run_ours(a):
                                      D.ptr(chk), D.stream_ptr()))
     recs = P.gather_winner(chk, world)
     want_v, want_i = P.winner_from_records(recs, True)
-    assert want_i == bi and want_v == bv, \
+    # same candidate; the value agrees to fp32 rounding (the two kernels sum the 32 products in
+    # different orders)
+    assert want_i == bi and abs(want_v - bv) <= 1e-5 * max(1.0, abs(bv)), \
         "sharded selection %r differs from the recomputed winner %r" % ((bv, bi), (want_v, want_i))
     selection_check = {"ranks": world, "recomputed_with": "score_pred_kernel per rank + all_gather + host reduction",
                        "equal": True, "local_winner_indices": recs[:, 1].cpu().tolist()}

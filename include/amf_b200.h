@@ -302,6 +302,19 @@ int amf_bayes_sample_stats(int dtype, int64_t ncand, const int32_t* ci_d, const 
                            void* prob_d, int select, int maximize, int64_t index_base,
                            amf_best_t* best_d, void* stream);
 
+/* The dense form of amf_bayes_sample_stats (mean / variance of every cell over S samples, fp32)
+ * on the tensor cores: per sample one 128 x 128 tile product U_s V_s^T per CTA issued with
+ * tcgen05.mma (TF32 inputs split hi + lo, three products: fp32-class accuracy; fp32 accumulators
+ * in tensor memory), operands by 2-D TMA, the variance accumulated about the first sample's
+ * prediction, which is subtracted on the tensor cores (negated-A products into the same
+ * accumulator).  amf_bayes_sample_stats routes dense fp32 calls without a prob output here
+ * (AMF_B200_DENSE_TC=0 in the environment keeps them on the CUDA-core kernel).  d <= 32, S >= 2,
+ * select 0 (mean) or 1 (variance). */
+int amf_bayes_sample_stats_dense_tc(int S, int32_t n, int32_t m, int d, const float* Us_d,
+                                    const float* Vs_d, double mean_offset, float* mean_d,
+                                    float* var_d, int select, int maximize, int64_t index_base,
+                                    amf_best_t* best_d, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Variational full-covariance approximation ("exact mode"), batched, fp64:
  * active_pmf.py:202-240 kl_divergence, normal_exps_cy.pyx:140-303 normal_gradient,

@@ -263,9 +263,10 @@ def test_fast_half_sweep_is_the_same_conditional(d, dtype, tol):
     dt = D.np_dtype(dtype)
     out = torch.empty((n, d), dtype=D.torch_dtype(dtype), device="cuda")
     seed, stream = 99, 12
+    other_t, alpha_t, mu_t = D.to_device(other, dt), D.to_device(alpha, dt), D.to_device(mu, dt)
     N.check(lib.amf_gibbs_half_sweep_device_rng(
-        rat.handle, 0, D.code(dtype), d, D.ptr(D.to_device(other, dt)), D.ptr(D.to_device(alpha, dt)),
-        D.ptr(D.to_device(mu, dt)), beta, off, seed, stream, D.ptr(out), 0, -1, D.stream_ptr()))
+        rat.handle, 0, D.code(dtype), d, D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t), beta, off,
+        seed, stream, D.ptr(out), 0, -1, D.stream_ptr()))
     got = out.double().cpu().numpy()
     z = _device_normals(seed, stream, n, d)
     for i in range(n):

@@ -440,7 +440,7 @@ int amf_blocks_lookahead(const amf_blocks_view_t* v, int what, int rounds, int64
   AMF_REQUIRE(rounds >= 1 && nv >= 1 && ncand >= 0 && values_d && best_d,
               "amf_blocks_lookahead: bad arguments");
   AMF_REQUIRE(weight_mode >= 0 && weight_mode <= 2, "amf_blocks_lookahead: bad weight mode");
-  AMF_REQUIRE(weight_mode == 0 || (bounds_or_weights_d && rij_mean_d && rij_sd_d),
+  AMF_REQUIRE(weight_mode == 0 || ncand == 0 || (bounds_or_weights_d && rij_mean_d && rij_sd_d),
               "amf_blocks_lookahead: weights need the R_ij distribution");
   AMF_REQUIRE(v->mean_u && v->cov_u && v->prec_u && v->h_u && v->logdet_u && v->mean_v &&
                   v->cov_v && v->prec_v && v->h_v && v->logdet_v,

@@ -378,10 +378,16 @@ int dense_tc_launch(int S, int32_t n, int32_t m, int d, const float* Us, const f
   const int grid = (n_pad / TC_TILE) * (m_pad / TC_TILE);
   AMF_REQUIRE(grid <= 8192, "dense_tc: %d tiles exceed the winner scratch", grid);
   const size_t smem = (size_t)(1 + (kp >= 32 ? 2 : 3)) * 2 * chunks * TC_CHUNK_BYTES;
+  int dev = 0;
+  AMF_CUDA(cudaGetDevice(&dev));
 #define TC(KP_, MAX_)                                                                             \
   do {                                                                                            \
-    AMF_CUDA(cudaFuncSetAttribute(sample_stats_tc_kernel<KP_, MAX_>,                              \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    static bool attr_set[64] = {false};   /* per instantiation and device; the value is fixed */ \
+    if (dev >= 64 || !attr_set[dev]) {                                                            \
+      AMF_CUDA(cudaFuncSetAttribute(sample_stats_tc_kernel<KP_, MAX_>,                            \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      if (dev < 64) attr_set[dev] = true;                                                         \
+    }                                                                                             \
     sample_stats_tc_kernel<KP_, MAX_><<<grid, TC_THREADS, smem, s>>>(                             \
         mu, mv, S, n, m, offset, mean_d, var_d, select, index_base, part);                        \
   } while (0)

@@ -314,7 +314,7 @@ int acquire_partials(Best** out, cudaStream_t s) {
   if (dev < 64 && !tuned[dev]) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = 64ull << 20;
+      uint64_t keep = 1ull << 30;   // workspaces of the dense kernels are tens of MB per call
       uint64_t cur = 0;
       cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
       if (cur < keep) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);

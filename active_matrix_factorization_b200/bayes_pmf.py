@@ -297,12 +297,17 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         items_t = D.to_device(self.items, dt)
         tdt = D.torch_dtype(name)
         stream_id = 0
+        sample_no = 0
         dd = d * d
         hyper_h = torch.empty(2 * (d + dd), dtype=tdt).pin_memory()
 
-        def half(side, other_t, hyper_t, rows):
+        scratch = [torch.empty((n, d), dtype=tdt, device=users_t.device),
+                   torch.empty((m, d), dtype=tdt, device=users_t.device)]
+
+        def half(side, other_t, hyper_t, rows, keep):
+            # only the last round's rows are handed to the caller; earlier rounds reuse scratch
             nonlocal stream_id
-            out = torch.empty((rows, d), dtype=tdt, device=other_t.device)
+            out = torch.empty((rows, d), dtype=tdt, device=other_t.device) if keep else scratch[side]
             o = side * (d + dd)
             N.check(lib.amf_gibbs_half_sweep_device_rng(
                 rat.handle, side, D.code(name), d, D.ptr(other_t), D.ptr(hyper_t[o + d:o + d + dd]),
@@ -331,10 +336,12 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
                 (np.atleast_1d(mu_u), np.atleast_2d(alpha_u).reshape(-1),
                  np.atleast_1d(mu_v), np.atleast_2d(alpha_v).reshape(-1))).astype(dt)))
             hyper_t = hyper_h.to(users_t.device, non_blocking=True)
-            for _gibbs in range(num_gibbs):
-                users_t = half(0, items_t, hyper_t, n)
-                items_t = half(1, users_t, hyper_t, m)
-            self._check_gibbs(rat)
+            for r in range(num_gibbs):
+                users_t = half(0, items_t, hyper_t, n, r == num_gibbs - 1)
+                items_t = half(1, users_t, hyper_t, m, r == num_gibbs - 1)
+            sample_no += 1
+            if sample_no % 16 == 0:          # the failure flag is sticky: one read covers 16 samples
+                self._check_gibbs(rat)
             yield users_t, items_t
 
     def samples_parallel(self, num_gibbs=2, pool=None, multiproc_mode=None, fit_first=False):

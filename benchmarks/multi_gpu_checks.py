@@ -64,9 +64,7 @@ def main():
         out["gibbs"] = {"samples": 20, "seconds_sharded": t_sh, "seconds_one_gpu": t_1,
                         "max_abs_diff_vs_one_gpu_chain": float(err)}
         assert err < 1e-9, "sharded chain left the single-GPU chain"
-        # and the chain is still the reference's (3 samples of the fixture)
-        for s in range(3):
-            np.testing.assert_allclose(sharded[s][0][:128], g["sample%d_u_head" % s], rtol=1e-6, atol=1e-8)
+        # (that the unsharded chain is the reference's own is tests/test_gpu_configs.py::test_c4)
     if world > 1:
         dist.barrier()
 

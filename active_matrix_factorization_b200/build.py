@@ -11,6 +11,10 @@ LIB = os.path.join(CSRC, "libamf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+# AMF_B200_DEBUG=1: device-side bounds checks on every computed write address (common.cuh);
+# build with --force so that every object is recompiled with the flag
+if os.environ.get("AMF_B200_DEBUG") == "1":
+    FLAGS = FLAGS + ["-DAMF_BOUNDS_CHECK"]
 
 
 def sources():

@@ -107,6 +107,7 @@ blocks_half_sweep_kernel(const int64_t* __restrict__ ptr, const int32_t* __restr
       for (int c = 0; c < d; ++c) M[l * ld + c] = (c == l) ? 1.0 / prior_var : 0.0;
       for (int64_t p = ptr[row]; p < ptr[row + 1]; ++p) {
         const int32_t j = idx[p];
+        AMF_DBG_ASSERT(j >= 0);
         const double r = (double)val[p] - mean_offset;
         const double* nj = other_mean + (int64_t)j * d;
         const double nl = nj[l];
@@ -212,6 +213,7 @@ blocks_lookahead_kernel(BlocksView bv, int rounds, int64_t ncand, const int32_t*
     const bool live = c0 < ncand;
     const int64_t c = live ? c0 : ncand - 1;
     const int32_t i = ci[c], j = cj[c];
+    AMF_DBG_ASSERT((uint32_t)i < (uint32_t)bv.n && (uint32_t)j < (uint32_t)bv.m);
     const double* Lu = bv.prec_u + (int64_t)i * dd;
     const double* Lv = bv.prec_v + (int64_t)j * dd;
     const double* hu = bv.h_u + (int64_t)i * d;

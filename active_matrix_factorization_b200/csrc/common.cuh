@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -33,6 +34,46 @@ void set_error(const char* fmt, ...);
 
 int num_sms();
 
+// ---- debug build (-DAMF_BOUNDS_CHECK, `AMF_B200_DEBUG=1 python -m ...build --force`) --------------
+// compute-sanitizer is closed on the GPU pool this library is developed on, so the kernels that
+// write through computed addresses (vector RED / atomics into the gradient tables, score stores)
+// carry their own checks: the host entry registers the address ranges a launch may write
+// (AMF_DBG_RANGE), every such write asserts that it falls inside one of them (AMF_DBG_WRITE), and
+// index decodes assert their bounds (AMF_DBG_ASSERT).  A violation prints and traps, which the
+// caller sees as a CUDA error.  All of it compiles to nothing in the release build.
+#ifdef AMF_BOUNDS_CHECK
+struct DbgRanges { unsigned long long lo[4], hi[4]; };
+static __device__ DbgRanges amf_dbg_ranges;            // one copy per translation unit
+static inline void dbg_set_range(int slot, const void* p, size_t bytes, cudaStream_t s) {
+  const unsigned long long lo = (unsigned long long)(uintptr_t)p, hi = lo + bytes;
+  cudaMemcpyToSymbolAsync(amf_dbg_ranges, &lo, 8, offsetof(DbgRanges, lo) + 8 * slot,
+                          cudaMemcpyHostToDevice, s);
+  cudaMemcpyToSymbolAsync(amf_dbg_ranges, &hi, 8, offsetof(DbgRanges, hi) + 8 * slot,
+                          cudaMemcpyHostToDevice, s);
+}
+#define AMF_DBG_RANGE(slot, p, bytes, s) amf::dbg_set_range((slot), (p), (bytes), (s))
+#define AMF_DBG_ASSERT(cond)                                                                  \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      printf("amf bounds check failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__,     \
+             __LINE__, (int)blockIdx.x, (int)threadIdx.x);                                    \
+      __trap();                                                                               \
+    }                                                                                         \
+  } while (0)
+#define AMF_DBG_WRITE(p, bytes)                                                               \
+  do {                                                                                        \
+    const unsigned long long a__ = (unsigned long long)(uintptr_t)(p);                        \
+    bool in__ = false;                                                                        \
+    for (int q__ = 0; q__ < 4; ++q__)                                                         \
+      in__ |= a__ >= amf::amf_dbg_ranges.lo[q__] && a__ + (bytes) <= amf::amf_dbg_ranges.hi[q__]; \
+    AMF_DBG_ASSERT(in__ && "write outside the registered output ranges");                      \
+  } while (0)
+#else
+#define AMF_DBG_RANGE(slot, p, bytes, s) ((void)0)
+#define AMF_DBG_ASSERT(cond) ((void)0)
+#define AMF_DBG_WRITE(p, bytes) ((void)0)
+#endif
+
 // ---- 16-byte vectors of the compute type ---------------------------------------------------
 template <typename T> struct Vec;
 template <> struct Vec<float> {
@@ -61,9 +102,11 @@ __device__ __forceinline__ void vfma(double2& acc, double s, const double2& b) {
 }
 // vector reduction into global memory (no return value): RED.E.ADD.F32x4 on sm_100a
 __device__ __forceinline__ void vred_add(float* p, const float4& v) {
+  AMF_DBG_WRITE(p, 16);
   atomicAdd(reinterpret_cast<float4*>(p), v);
 }
 __device__ __forceinline__ void vred_add(double* p, const double2& v) {
+  AMF_DBG_WRITE(p, 16);
   atomicAdd(p, v.x);
   atomicAdd(p + 1, v.y);
 }

@@ -76,6 +76,7 @@ __device__ double loss_grad_grid(int64_t nnz, const int32_t* __restrict__ own,
   for (int64_t p = blockIdx.x * (int64_t)FIT_THREADS + threadIdx.x; p < nnz;
        p += (int64_t)gridDim.x * FIT_THREADS) {
     const int32_t i = own[p], j = idx[p];
+    AMF_DBG_ASSERT((uint32_t)i < (uint32_t)n && (uint32_t)j < (uint32_t)m);
     const T* u = U + (int64_t)i * ld;
     const T* v = V + (int64_t)j * ld;
     T dot = 0;

@@ -318,6 +318,7 @@ static int launch_side(const amf_ratings* h, int side, const T* Self, const T* O
   const int G = 32 / lpr;
   const int64_t warps_needed = (h->n_sub + G - 1) / G;
   const int grid = grid_for((warps_needed + 7) / 8, 8);
+  if (GRAD) AMF_DBG_RANGE(0, dSelf, sizeof(T) * (size_t)(side == 0 ? h->n_users : h->n_items) * ld, s);
 #define SIDE(LPR_, VPL_)                                                                      \
   side_pass_kernel<T, LPR_, VPL_, GRAD><<<grid, 256, 0, s>>>(                                 \
       h->ptr[side], h->idx[side], (const T*)h->val[side], h->sub_row[side], Self, Other, ld,  \
@@ -421,6 +422,14 @@ static int grad_coo(int64_t nnz, const int32_t* i_d, const int32_t* j_d, const T
   const int G = 32 / lpr;
   const int grid = grid_for((((nnz + G - 1) / G) + 7) / 8, 8);
   const T inv_sigma = (T)(1.0 / p->sigma_sq), mo = (T)p->mean_offset;
+#ifdef AMF_BOUNDS_CHECK
+  // the mini-batch entry does not know the table heights: the caller's ids were range-checked
+  // when the list was built, so the widest legal write is bounded by the largest id present
+  {
+    AMF_DBG_RANGE(0, dU, (size_t)1 << 46, s);
+    AMF_DBG_RANGE(1, dV, (size_t)1 << 46, s);
+  }
+#endif
 #define COO(LPR_, VPL_)                                                                        \
   coo_grad_kernel<T, LPR_, VPL_><<<grid, 256, 0, s>>>(i_d, j_d, r_d, nnz, U, V, ld, nvec,      \
                                                       inv_sigma, mo, dU, dV, sums)

@@ -198,6 +198,7 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           // slice t of a row sits at  off0 ^ slice_xor(t)  (rows are ROW_BYTES-aligned)
+          AMF_DBG_ASSERT((int)(w[s] & jmask) < tile_rows);       // inside the shared-memory tile
           const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
           V b[CPL];
 #pragma unroll

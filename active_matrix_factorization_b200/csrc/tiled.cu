@@ -194,11 +194,13 @@ __device__ __forceinline__ void axpy_slices(double2 (&acc)[C], double w, const d
 }
 // fire-and-forget vector reduction into global memory
 __device__ __forceinline__ void red_add(float* p, const float4& v) {
+  AMF_DBG_WRITE(p, 16);
   asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
 __device__ __forceinline__ void red_add(double* p, const double2& v) {
+  AMF_DBG_WRITE(p, 16);
   asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v.x) : "memory");
   asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(v.y) : "memory");
 }
@@ -319,6 +321,7 @@ tiled_side_kernel(const uint32_t* __restrict__ cw, const T* __restrict__ rv,
           for (int s = 0; s < 4; ++s) {
             // sorted offset of this entry inside the chunk: group run, batch, slot
             const bool valid = !CHECK || (g * (4 * TILED_RUN) + r * 4 + s < nvalid);
+            AMF_DBG_ASSERT(!valid || (int)(w[s] & jmask) < min(tile_rows, tile_side_rows - t_cur * tile_rows));
             const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
             V b[CPL];
   #pragma unroll
@@ -382,6 +385,7 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
   if (max_ctas > 0 && grid64 > max_ctas) grid64 = max_ctas;   // leave SMs to a concurrent collective
   if (grid64 > t->n_chunks) grid64 = t->n_chunks > 0 ? t->n_chunks : 1;
   const int grid = (int)grid64;
+  if (GRAD) AMF_DBG_RANGE(0, dOwn, (size_t)(side == 0 ? h->n_users : h->n_items) * nvec * 16, s);
   // 64 registers per thread (fp32) keep 32 warps on the SM: the pass is bound by the latency of
   // the row fetch at every (row, tile) visit, so resident warps are what hides it
   constexpr int THREADS = sizeof(T) == 4 ? 1024 : 512;

@@ -271,7 +271,44 @@ def case_c4():
     save("c4_movielens_bayes", **out)
 
 
+# ---- adaptive quadrature of the continuous lookahead, pinned at the nodes SciPy visits first ------
+def case_quad_nodes():
+    """active_pmf.py:691-699: stats.norm.expect(calculate_fn, lb, ub, epsrel=.02) = QUADPACK's
+    adaptive 21-point Gauss-Kronrod.  The integrand is a line search run to a stopping threshold
+    (piecewise constant in its accepted-step count), so the adaptive loop subdivides for ~1000
+    evaluations; what CAN be pinned is the integrand at the nodes of the first pass: the first
+    21 values of v the reference asks for, and what it computes there."""
+    g = np.load(os.path.join(HERE, "lookahead_6x7_d2.npz"))
+    cand = list(zip(g["cand_i"].tolist(), g["cand_j"].tolist()))[:2]
+    a = ActivePMF(g["ratings"], 2, rating_values=None, discrete_expectations=False)
+    a.users, a.items = g["users"].copy(), g["items"].copy()
+    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+
+    class Enough(Exception):
+        pass
+    out = {"cand_i": np.array([c[0] for c in cand]), "cand_j": np.array([c[1] for c in cand])}
+    for t, c in enumerate(cand):
+        seen = []
+
+        def fn(model, v=None, seen=seen):
+            val = ActivePMF._approx_entropy(model)
+            seen.append((v, val))
+            if len(seen) >= 21:
+                raise Enough()
+            return val
+        fn.__name__ = "_approx_entropy"
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                a._exp_with_rij(c, fn, use_map=True, pass_v=True)
+        except Enough:
+            pass
+        out["nodes%d" % t] = np.array([s[0] for s in seen])
+        out["values%d" % t] = np.array([s[1] for s in seen])
+    save("quad_nodes_6x7_d2", **out)
+
+
 CASES = {
+    "quad_nodes": case_quad_nodes,
     "blocks_6x7": lambda: case_blocks("blocks_6x7_d2", 6, 7, 2, 14, 3, 1000),
     "blocks_12x20": lambda: case_blocks("blocks_12x20_d5", 12, 20, 5, 80, 11, 40),
     "c2": case_c2, "c3": case_c3, "c4": case_c4,

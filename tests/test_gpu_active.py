@@ -136,6 +136,39 @@ def test_lookahead_simpson_and_three_values(A, golden):
         a.add_rating(cand[0][0], cand[0][1], .25)
 
 
+def test_continuous_lookahead_pinned_at_the_first_quadrature_nodes(A, golden):
+    """Adaptive quadrature of the continuous lookahead (active_pmf.py:691-699), pinned where it
+    can be: the first 21 values of v the reference's stats.norm.expect asks for (QUADPACK's first
+    Gauss-Kronrod pass over the left tail) and the re-fitted entropies it computed there
+    (tests/golden/make_golden_configs.py case_quad_nodes).  The same re-fits here, as one batched
+    launch from the same fitted state, and the same node sequence from the host-side quadrature."""
+    g, q = golden("lookahead_6x7_d2"), golden("quad_nodes_6x7_d2")
+    a = A.ActivePMF(g["ratings"], 2, rating_values=None, discrete_expectations=False)
+    a.approx_mode = 'exact'
+    a.users, a.items = g["users"].copy(), g["items"].copy()
+    a.mean, a.cov = g["mean"].copy(), g["cov"].copy()
+    for t, (i, j) in enumerate(zip(q["cand_i"].tolist(), q["cand_j"].tolist())):
+        nodes, want = q["nodes%d" % t], q["values%d" % t]
+        got = a._refits([(i, j, float(v)) for v in nodes], 'entropy')
+        np.testing.assert_allclose(got, want, rtol=5e-5)
+    # the quadrature driven by this package asks for the same nodes first
+    seen = []
+    orig = a._refits
+
+    class Enough(Exception):
+        pass
+
+    def spy(trips, what):
+        seen.extend(v for _i, _j, v in trips)
+        if len(seen) >= 21:
+            raise Enough()
+        return orig(trips, what)
+    a._refits = spy
+    with pytest.raises(Enough):
+        a._lookahead([(int(q["cand_i"][0]), int(q["cand_j"][0]))], 'entropy', True)
+    np.testing.assert_allclose(seen[:21], q["nodes0"], rtol=1e-12)
+
+
 def test_pred_entropy_bound_and_onestep_match_oracle_restatement(A, golden):
     g = golden("lookahead_6x7_d2")
     a = A.ActivePMF(g["ratings"], 2, rating_values={0, 1}, discrete_expectations=True)

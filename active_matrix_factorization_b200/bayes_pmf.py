@@ -344,6 +344,117 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
                 self._check_gibbs(rat)
             yield users_t, items_t
 
+    # ---- batched lookahead chains (fast mode) ---------------------------------------------------
+    def _hyperparams_batched(self, n_rows, x_bar, s_bar, do_users):
+        """_hyperparam_from_moments for P chains at once (numpy batched d x d algebra, global
+        numpy stream): x_bar (P, d), s_bar (P, d, d) -> mu (P, d), alpha (P, d, d)"""
+        wi, b0, df, mu0 = self.u_hyperparams if do_users else self.v_hyperparams
+        P, d = x_bar.shape
+        n = n_rows
+        diff = mu0[None, :] - x_bar
+        quirk = (diff * diff).sum(1)                     # np.dot of two 1-D vectors (bayes_pmf.py:176)
+        wi_post = np.linalg.inv(np.linalg.inv(wi)[None] + n * s_bar
+                                + ((b0 * n) / (b0 + n)) * quirk[:, None, None])
+        wi_post = wi_post / 2
+        wi_post = wi_post + wi_post.transpose(0, 2, 1)
+        dof = int(df + n)
+        chol = np.linalg.cholesky(wi_post)
+        if dof <= 81 + d:
+            X = chol @ np.random.normal(size=(P, d, dof))
+        else:                                            # Bartlett (bayes_pmf.py:52-58)
+            A = np.zeros((P, d, d))
+            A[:, np.arange(d), np.arange(d)] = np.sqrt(np.random.chisquare(dof - np.arange(d), size=(P, d)))
+            lower = np.tri(d, k=-1, dtype=bool)
+            A[:, lower] = np.random.normal(size=(P, d * (d - 1) // 2))
+            X = chol @ A
+        alpha = X @ X.transpose(0, 2, 1)
+        mu_temp = (b0 * mu0[None, :] + n * x_bar) / (b0 + n)
+        lam = np.linalg.cholesky(np.linalg.inv((b0 + n) * alpha))
+        mu = np.einsum('pkl,pl->pk', lam, np.random.normal(size=(P, d))) + mu_temp
+        return mu, alpha
+
+    # device bytes one chunk of lookahead chains may hold (samples of every chain are kept until
+    # its total variance is reduced)
+    lookahead_chunk_bytes = 2 << 30
+
+    def _lookahead_total_variance(self, cells_i, cells_j, values, num_samps, num_gibbs=2, seed=None):
+        """total_variance (bayes_pmf.py:450-451) of `num_samps` samples of the chain of
+        model + (i, j, v) for every (cell, value): values (ncell, nval).  All chains of a chunk run
+        in the same launches (amf_gibbs_half_sweep_batched), each from this model's current
+        factors; the sum over all N x M cells of the sample variance is reduced from d x d Gram
+        matrices of the stacked samples, never from N x M predictions."""
+        lib = N.require_device()
+        name = self.dtype_name
+        dt, tdt = D.np_dtype(name), D.torch_dtype(name)
+        n, m, d = self.num_users, self.num_items, self.latent_d
+        if d > 32:
+            raise ValueError("the batched lookahead supports latent_d <= 32")
+        values = np.asarray(values, dtype=float)
+        ncell, nval = values.shape
+        ei = np.repeat(np.asarray(cells_i, dtype=np.int32), nval)
+        ej = np.repeat(np.asarray(cells_j, dtype=np.int32), nval)
+        ev = values.reshape(-1)
+        P_all = ei.shape[0]
+        rat = D.Ratings.from_tuples(self.ratings, n, m, name)
+        nnz = self.ratings.shape[0]
+        seed = int(self.device_seed if seed is None else seed)
+        S = int(num_samps)
+        per_chain = (S + 2) * (n + m) * d * np.dtype(dt).itemsize + 2 * (S * d) ** 2 * 8
+        chunk = int(max(1, min(P_all, self.lookahead_chunk_bytes // per_chain)))
+        base_u, base_v = D.to_device(self.users, dt), D.to_device(self.items, dt)
+        out = np.empty(P_all)
+        stream_id = 1 << 32            # apart from the counters of samples_device()
+        dd = d * d
+        for lo in range(0, P_all, chunk):
+            hi = min(P_all, lo + chunk)
+            P = hi - lo
+            us = base_u.unsqueeze(0).expand(P, n, d).contiguous()
+            vs = base_v.unsqueeze(0).expand(P, m, d).contiguous()
+            ex_i, ex_j = D.to_device(ei[lo:hi], np.int32), D.to_device(ej[lo:hi], np.int32)
+            ex_v = D.to_device(ev[lo:hi], np.float64)
+            offs = None
+            if self.subtract_mean:       # add_rating moves the mean rating (pmf_cy.pyx:155)
+                offs = D.to_device((self.mean_rating * nnz + ev[lo:hi]) / (nnz + 1), np.float64)
+            keep_u = torch.empty((P, n, S * d), dtype=tdt, device=us.device)
+            keep_v = torch.empty((P, m, S * d), dtype=tdt, device=us.device)
+
+            def half(side, other_t, alpha_t, mu_t, rows):
+                nonlocal stream_id
+                res = torch.empty((P, rows, d), dtype=tdt, device=other_t.device)
+                N.check(lib.amf_gibbs_half_sweep_batched(
+                    rat.handle, side, D.code(name), d, P, D.ptr(other_t), D.ptr(alpha_t), D.ptr(mu_t),
+                    float(self.beta), float(self._mean_offset()), D.ptr(offs),
+                    D.ptr(ex_i if side == 0 else ex_j), D.ptr(ex_j if side == 0 else ex_i), D.ptr(ex_v),
+                    seed, stream_id, D.ptr(res), D.stream_ptr()))
+                stream_id += 1
+                return res
+
+            def moments(t):
+                t64 = t.to(torch.float64)
+                mean = t64.mean(dim=1)
+                c = t64 - mean.unsqueeze(1)
+                return mean, torch.bmm(c.transpose(1, 2), c) / (t.shape[1] - 1)
+
+            for sidx in range(S):
+                mu_m, mu_c = moments(us)
+                mv_m, mv_c = moments(vs)
+                mom = torch.cat((mu_m, mu_c.reshape(P, dd), mv_m, mv_c.reshape(P, dd)), dim=1).cpu().numpy()
+                mu_u, al_u = self._hyperparams_batched(n, mom[:, :d], mom[:, d:d + dd].reshape(P, d, d), True)
+                mu_v, al_v = self._hyperparams_batched(m, mom[:, d + dd:2 * d + dd],
+                                                       mom[:, 2 * d + dd:].reshape(P, d, d), False)
+                au, mu_ut = D.to_device(al_u, dt), D.to_device(mu_u, dt)
+                av, mu_vt = D.to_device(al_v, dt), D.to_device(mu_v, dt)
+                for _g in range(num_gibbs):
+                    us = half(0, vs, au, mu_ut, n)
+                    vs = half(1, us, av, mu_vt, m)
+                keep_u[:, :, sidx * d:(sidx + 1) * d] = us
+                keep_v[:, :, sidx * d:(sidx + 1) * d] = vs
+            self._check_gibbs(rat)
+            out[lo:hi] = _total_variance_of_stacks(keep_u, keep_v, S, d).cpu().numpy()
+            del keep_u, keep_v
+        rat.close()
+        return out.reshape(ncell, nval)
+
     def samples_parallel(self, num_gibbs=2, pool=None, multiproc_mode=None, fit_first=False):
         '''(bayes_pmf.py:306-424) the row fan-out is the GPU launch; `pool` is not needed.'''
         if multiproc_mode == 'force' and pool is None:
@@ -448,6 +559,19 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         '''Expected total variance after learning each R_ij (bayes_pmf.py:457-468).'''
         return self._distribute(_exp_variance_helper, samples_iter, which, pool, fit_first, num_samps)
 
+    def _distribute_batched(self, i_idx, j_idx, shape, discrete, params, num_samps):
+        res = np.empty(shape)
+        res.fill(np.nan)
+        cells = [(int(i), int(j)) for i, j in zip(i_idx.flat, j_idx.flat)]
+        live = [t for t, c in enumerate(cells) if c not in self.rated]
+        if len(live) < len(cells):
+            warnings.warn("Asked to check a known entry; returning NaN")
+        if live:
+            est = _batched_integration(self, [cells[t] for t in live], discrete,
+                                       [params[t] for t in live], num_samps)
+            res.flat[live] = np.float32(est)           # `exp = cython.float` in bayes_pmf.pxd
+        return res
+
     def _distribute(self, fn, samples_iter, which, pool, fit_first, num_samps):
         '''(bayes_pmf.py:470-525); alpha and denom are C floats in the compiled reference.'''
         samples = list(samples_iter)
@@ -470,6 +594,8 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
             discrete = False
             params = list(zip(np.mean(vals, 0).flat, np.var(vals, 0).flat))
 
+        if self.rng_mode == 'device' and fn is _exp_variance_helper:
+            return self._distribute_batched(i_idx, j_idx, shape, discrete, params, num_samps)
         exps = map(fn, zip(repeat(self), i_idx.flat, j_idx.flat, repeat(discrete), params,
                            repeat(fit_first), repeat(num_samps)))
         res = np.empty(shape)
@@ -477,6 +603,37 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         for idx, exp in enumerate(exps):
             res.flat[idx] = np.float32(exp)          # `exp = cython.float` in bayes_pmf.pxd
         return res
+
+
+def _total_variance_of_stacks(keep_u, keep_v, S, d):
+    """sum over ALL cells (i, j) of the population variance over S samples of U_s[i] . V_s[j], for
+    P chains at once, from the samples stacked along columns: keep_u (P, n, S d), keep_v
+    (P, m, S d).  With Gu = X_u' X_u (S d x S d, blocks Gu_st = U_s' U_t):
+        sum_ij Var = (1/S) sum_s <Gu_ss, Gv_ss> - (1/S^2) sum_st <Gu_st, Gv_st>
+    -- O((n + m) (S d)^2) instead of S products of n x m, in fp64."""
+    ku, kv = keep_u.to(torch.float64), keep_v.to(torch.float64)
+    prod = torch.bmm(ku.transpose(1, 2), ku) * torch.bmm(kv.transpose(1, 2), kv)
+    mask = torch.block_diag(*[torch.ones((d, d), dtype=torch.float64, device=ku.device)] * S)
+    return (prod * mask.unsqueeze(0)).sum(dim=(1, 2)) / S - prod.sum(dim=(1, 2)) / (S * S)
+
+
+def _batched_integration(bpmf, cells, discrete, params, num_samps):
+    """_integrate_lookahead (bayes_pmf.py:560-598) for many cells at once in fast mode: every
+    (cell, value) model is a chain of ONE batched launch sequence; chains start from the parent's
+    factors (the reference's `fit_first` MAP re-fit per model is not done)."""
+    ci = np.array([c[0] for c in cells], dtype=np.int32)
+    cj = np.array([c[1] for c in cells], dtype=np.int32)
+    if discrete:
+        vals = np.tile(np.asarray(bpmf.rating_values, dtype=float), (len(cells), 1))
+        evals = bpmf._lookahead_total_variance(ci, cj, vals, num_samps)
+        return (evals * np.asarray(params)).sum(1)
+    means = np.array([p[0] for p in params])
+    sds = np.sqrt(np.array([p[1] for p in params]))
+    q = stats.norm.ppf(np.linspace(.001, .999, bpmf.num_integration_pts))
+    pts = means[:, None] + sds[:, None] * q[None, :]
+    evals = bpmf._lookahead_total_variance(ci, cj, pts, num_samps)
+    pdfs = stats.norm.pdf(pts, loc=means[:, None], scale=sds[:, None])
+    return integrate.trapezoid(evals * pdfs, pts, axis=1)
 
 
 def _integrate_lookahead(fn, bpmf, i, j, discrete, params, fit_first, num_samps):

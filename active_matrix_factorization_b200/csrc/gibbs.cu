@@ -513,6 +513,18 @@ __device__ bool warp_solve32_fast(const double* Lam, int d, int lda, double* scr
 //   of the row taken by the one warp; otherwise 2 x 2 register blocks spread over the 32 lanes.
 constexpr int GIBBS_WARP_MAXBLK = (16 * 17 / 2 + 31) / 32;   // 2 x 2 blocks per lane at d = 32
 
+// A batch of chains over the same rating list, chain p with ONE extra rating (the lookahead of
+// bayes_pmf.py:560-598: model + (i, j, v)): its own factor matrices, hyper-parameters and mean
+// offset.  count <= 1 with NULL arrays is the plain half-sweep.
+struct GibbsBatch {
+  int count;                  // chains (>= 1)
+  int other_rows;             // rows of `other` per chain
+  const int32_t* ex_row;      // row of the side being sampled that holds chain p's extra rating
+  const int32_t* ex_col;      // row of `other` it pairs with
+  const double* ex_val;       // its value
+  const double* offsets;      // mean offset of chain p (NULL: the common one)
+};
+
 template <typename T, bool TC, bool FAST>
 __global__ void __launch_bounds__(GIBBS_THREADS, 3)   // <= 168 registers: 12 warps per SM
 gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -521,7 +533,7 @@ gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
                        const T* __restrict__ mu, double beta, double mean_offset,
                        const T* __restrict__ z, T* __restrict__ out, int* __restrict__ fail,
                        int a_doubles, int warp_doubles, unsigned long long seed,
-                       unsigned long long stream_id) {
+                       unsigned long long stream_id, GibbsBatch gb) {
   extern __shared__ double smem[];
   constexpr int NW = GIBBS_THREADS / 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -551,8 +563,25 @@ gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
     }
   }
 
+  const int span = rows - row_begin;
+  const int64_t tasks = (int64_t)span * (gb.count > 1 ? gb.count : 1);
+  const T* const other0 = other;
+  const T* const alpha0 = alpha;
+  const T* const mu0 = mu;
+  T* const out0 = out;
+  const double mean_offset0 = mean_offset;
 #pragma unroll 1
-  for (int row = row_begin + blockIdx.x * NW + w; row < rows; row += gridDim.x * NW) {
+  for (int64_t task = (int64_t)blockIdx.x * NW + w; task < tasks; task += (int64_t)gridDim.x * NW) {
+    const int chain = (int)(task / span);
+    const int row = row_begin + (int)(task - (int64_t)chain * span);
+    if (gb.count > 1) {
+      other = other0 + (int64_t)chain * gb.other_rows * d;
+      alpha = alpha0 + (int64_t)chain * d * d;
+      mu = mu0 + (int64_t)chain * d;
+      out = out0 + (int64_t)chain * rows * d;
+      if (gb.offsets) mean_offset = gb.offsets[chain];
+    }
+    (void)mean_offset0;
     const int64_t p0 = ptr[row], p1 = ptr[row + 1];
     T acc[GIBBS_WARP_MAXBLK][4];
     float c[6][4];
@@ -684,9 +713,20 @@ gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
       for (int l = 0; l < d; ++l) rhs_lane += (double)alpha[lane * d + l] * (double)mu[l];
     }
     __syncwarp();
+    if (gb.ex_row && gb.ex_row[chain] == row) {
+      // this chain's extra rating: Lambda += beta f f', rhs += beta f (v - offset)
+      const T* f = other + (int64_t)gb.ex_col[chain] * d;
+      if (lane < d) {
+        const double fl = (double)f[lane];
+        for (int l = 0; l < d; ++l) A[lane * lda + l] += beta * fl * (double)f[l];
+        rhs_lane += beta * fl * (gb.ex_val[chain] - mean_offset);
+      }
+      __syncwarp();
+    }
     bool ok;
     if (FAST) {
-      const double zl = lane < d ? philox_normal(seed, stream_id, (uint32_t)row, (uint32_t)lane) : 0.0;
+      const double zl = lane < d ? philox_normal(seed, stream_id, (uint32_t)row,
+                                                 (uint32_t)lane + 32u * (uint32_t)chain) : 0.0;
       ok = warp_solve32_fast<T>(A, d, lda, A, col, rhs_lane, zl, out + (int64_t)row * d);
     } else {
       ok = warp_solve32<T>(A, d, lda, A, col, vec, rhs_lane, z + (int64_t)row * d,
@@ -845,7 +885,8 @@ template <typename T>
 static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, const T* alpha,
                         const T* mu, double beta, double mean_offset, const T* z, T* out,
                         int row_begin, int row_end, cudaStream_t s, bool fast = false,
-                        unsigned long long seed = 0, unsigned long long stream_id = 0) {
+                        unsigned long long seed = 0, unsigned long long stream_id = 0,
+                        GibbsBatch gb = GibbsBatch{1, 0, nullptr, nullptr, nullptr, nullptr}) {
   const int all_rows = side == 0 ? h->n_users : h->n_items;
   if (row_end < 0 || row_end > all_rows) row_end = all_rows;
   if (row_begin < 0) row_begin = 0;
@@ -863,15 +904,16 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
     const int a_doubles = (int)std::max({(size_t)d * (d + 1), (tile_bytes + 7) / 8, (size_t)32 * 34});
     const int warp_doubles = (a_doubles + 64 + 32 + 1) & ~1;                    // 16-byte multiple
     const size_t smem_w = sizeof(double) * (size_t)warp_doubles * (GIBBS_THREADS / 32);
-    const int nwarp_rows = (span + GIBBS_THREADS / 32 - 1) / (GIBBS_THREADS / 32);
-    const int grid_w = nwarp_rows < num_sms() * 8 ? nwarp_rows : num_sms() * 8;
+    const int64_t nwarp_rows = ((int64_t)span * (gb.count > 1 ? gb.count : 1) + GIBBS_THREADS / 32 - 1) /
+                               (GIBBS_THREADS / 32);
+    const int grid_w = (int)(nwarp_rows < (int64_t)num_sms() * 8 ? nwarp_rows : (int64_t)num_sms() * 8);
 #define GIBBS_WARP(TC_, FAST_)                                                                   \
   do {                                                                                           \
     AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_, FAST_>,                         \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));    \
     gibbs_rows_warp_kernel<T, TC_, FAST_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(                 \
         h->ptr[side], h->idx[side], (const T*)h->val[side], row_begin, rows, d, other, alpha, mu, \
-        beta, mean_offset, z, out, fail, a_doubles, warp_doubles, seed, stream_id);              \
+        beta, mean_offset, z, out, fail, a_doubles, warp_doubles, seed, stream_id, gb);          \
   } while (0)
     if constexpr (sizeof(T) == 4) {
       if (tc) { if (fast) GIBBS_WARP(true, true); else GIBBS_WARP(true, false); }
@@ -981,6 +1023,34 @@ int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype,
   return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
                               (const double*)mu_d, beta, mean_offset, nullptr, (double*)out_d,
                               row_begin, row_end, s, true, seed, stream_id);
+}
+
+int amf_gibbs_half_sweep_batched(const amf_ratings_t* h, int side, int dtype, int d, int count,
+                                 const void* other_d, const void* alpha_d, const void* mu_d,
+                                 double beta, double mean_offset, const double* offsets_d,
+                                 const int32_t* ex_row_d, const int32_t* ex_col_d,
+                                 const double* ex_val_d, uint64_t seed, uint64_t stream_id,
+                                 void* out_d, void* stream) {
+  AMF_REQUIRE(h && other_d && alpha_d && mu_d && out_d, "amf_gibbs_half_sweep_batched: NULL argument");
+  AMF_REQUIRE(side == 0 || side == 1, "amf_gibbs_half_sweep_batched: side must be 0 or 1");
+  AMF_REQUIRE(dtype == h->dtype, "amf_gibbs_half_sweep_batched: dtype does not match the rating list");
+  AMF_REQUIRE(d >= 1 && d <= 32, "amf_gibbs_half_sweep_batched: latent_d=%d outside 1..32", d);
+  AMF_REQUIRE(count >= 1, "amf_gibbs_half_sweep_batched: count must be positive");
+  AMF_REQUIRE(!ex_row_d == !ex_col_d && !ex_row_d == !ex_val_d,
+              "amf_gibbs_half_sweep_batched: the extra-rating arrays come together");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = ratings_compact(const_cast<amf_ratings*>(h), s);
+    if (rc != AMF_OK) return rc;
+  }
+  const GibbsBatch gb{count, side == 0 ? h->n_items : h->n_users, ex_row_d, ex_col_d, ex_val_d, offsets_d};
+  if (dtype == AMF_F32)
+    return gibbs_launch<float>(h, side, d, (const float*)other_d, (const float*)alpha_d,
+                               (const float*)mu_d, beta, mean_offset, nullptr, (float*)out_d, 0, -1, s,
+                               true, seed, stream_id, gb);
+  return gibbs_launch<double>(h, side, d, (const double*)other_d, (const double*)alpha_d,
+                              (const double*)mu_d, beta, mean_offset, nullptr, (double*)out_d, 0, -1, s,
+                              true, seed, stream_id, gb);
 }
 
 int amf_philox_normal(int dtype, uint64_t seed, uint64_t stream_id, int64_t rows, int d,

@@ -279,6 +279,20 @@ int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype,
                                     double beta, double mean_offset, uint64_t seed,
                                     uint64_t stream_id, void* out_d, int32_t row_begin,
                                     int32_t row_end, void* stream);
+/* `count` chains over the SAME rating list in one launch, chain p with one extra rating
+ * (ex_row_d[p] = its row on the side being sampled, ex_col_d[p] = the row of `other` it pairs
+ * with, ex_val_d[p] = its value; all NULL: none) -- the per-candidate, per-value models of the
+ * Bayesian lookahead (bayes_pmf.py:560-598: deepcopy + add_rating + a fresh chain each) without
+ * copies of the list.  other_d (count, other_rows, d), alpha_d (count, d, d), mu_d (count, d),
+ * out_d (count, rows, d); offsets_d (count) per-chain mean offsets or NULL for `mean_offset`.
+ * Device random numbers as in amf_gibbs_half_sweep_device_rng, chain p on its own counters;
+ * d <= 32. */
+int amf_gibbs_half_sweep_batched(const amf_ratings_t* h, int side, int dtype, int d, int count,
+                                 const void* other_d, const void* alpha_d, const void* mu_d,
+                                 double beta, double mean_offset, const double* offsets_d,
+                                 const int32_t* ex_row_d, const int32_t* ex_col_d,
+                                 const double* ex_val_d, uint64_t seed, uint64_t stream_id,
+                                 void* out_d, void* stream);
 /* The same normals as an array: out_d[(row, k)] = z of (seed, stream_id, row, k). */
 int amf_philox_normal(int dtype, uint64_t seed, uint64_t stream_id, int64_t rows, int d,
                       void* out_d, void* stream);

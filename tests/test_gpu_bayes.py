@@ -303,3 +303,98 @@ def test_fast_chain_matches_host_chain_in_law(Bm, golden):
     b.rng_mode = 'device'
     us, vs = next(b.samples())
     assert isinstance(us, np.ndarray) and us.shape == (15, 3) and vs.shape == (12, 3)
+
+
+# ---- batched lookahead chains (fast mode) ------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 2e-4)])
+def test_batched_half_sweep_is_each_chains_own_conditional(dtype, tol):
+    """amf_gibbs_half_sweep_batched: chain p = the common rating list + its one extra rating, its
+    own factors, hyper-parameters and mean offset; every row equals the conditional of THAT model
+    with the normals of its own Philox counters (bayes_pmf.py:560-598 without the copies)"""
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D
+    lib = N.require_device()
+    rng = np.random.RandomState(3)
+    n, m, d, P = 12, 9, 4, 5
+    cells = rng.permutation(n * m)[:50]
+    R = np.column_stack((cells // m, cells % m, rng.normal(3, 1, 50)))
+    free = [c for c in range(n * m) if c not in set(cells.tolist())]
+    ex = rng.permutation(free)[:P]
+    ex_i, ex_j, ex_v = (ex // m).astype(np.int32), (ex % m).astype(np.int32), rng.normal(3, 1, P)
+    others = rng.normal(0, .5, (P, m, d))
+    a0 = rng.normal(0, 1, (P, d, d))
+    alphas = a0 @ a0.transpose(0, 2, 1) / d + np.eye(d)
+    mus, offs, beta = rng.normal(0, .3, (P, d)), rng.normal(3, .1, P), 2.0
+    rat = D.Ratings.from_tuples(R, n, m, dtype)
+    dt = D.np_dtype(dtype)
+    t = [D.to_device(x, dt) for x in (others, alphas, mus)]
+    ti, tj, tv, to = (D.to_device(ex_i, np.int32), D.to_device(ex_j, np.int32),
+                      D.to_device(ex_v, np.float64), D.to_device(offs, np.float64))
+    out = torch.empty((P, n, d), dtype=D.torch_dtype(dtype), device="cuda")
+    seed, stream = 1234, 77
+    N.check(lib.amf_gibbs_half_sweep_batched(rat.handle, 0, D.code(dtype), d, P, D.ptr(t[0]), D.ptr(t[1]),
+                                             D.ptr(t[2]), beta, 0.0, D.ptr(to), D.ptr(ti), D.ptr(tj),
+                                             D.ptr(tv), seed, stream, D.ptr(out), D.stream_ptr()))
+    got = out.double().cpu().numpy()
+    for p in range(P):
+        Rp = np.vstack((R, [ex_i[p], ex_j[p], ex_v[p]]))
+        for i in range(n):
+            rows = Rp[Rp[:, 0] == i]
+            F = others[p][rows[:, 1].astype(int)]
+            lam = alphas[p] + beta * F.T @ F
+            rhs = beta * F.T @ (rows[:, 2] - offs[p]) + alphas[p] @ mus[p]
+            z = np.empty(d)
+            for k in range(d):
+                w = _philox4x32_10([i, k + 32 * p, stream & 0xffffffff, stream >> 32],
+                                   [seed & 0xffffffff, seed >> 32])
+                z[k] = np.sqrt(-2 * np.log((w[0] + 1.0) * 2.0 ** -32)) * np.cos(2 * np.pi * (w[1] + 1.0) * 2.0 ** -32)
+            Rf = np.linalg.cholesky(lam)
+            want = np.linalg.solve(Rf.T, np.linalg.solve(Rf, rhs) + z)
+            assert np.abs(got[p, i] - want).max() <= tol * max(1.0, np.abs(want).max()), (p, i)
+    rat.close()
+
+
+def test_total_variance_from_gram_matrices(Bm):
+    """sum over all cells of the sample variance, reduced from d x d Gram blocks of the stacked
+    samples, against bayes_pmf.py:440-451 computed directly"""
+    import torch
+    rng = np.random.RandomState(1)
+    P, n, m, d, S = 3, 17, 11, 4, 6
+    us, vs = rng.normal(size=(P, S, n, d)), rng.normal(1, .5, size=(P, S, m, d))
+    ku = torch.tensor(us.transpose(0, 2, 1, 3).reshape(P, n, S * d), device="cuda")
+    kv = torch.tensor(vs.transpose(0, 2, 1, 3).reshape(P, m, S * d), device="cuda")
+    got = Bm._total_variance_of_stacks(ku, kv, S, d).cpu().numpy()
+    want = [np.einsum("snd,smd->snm", us[p], vs[p]).var(0).sum() for p in range(P)]
+    np.testing.assert_allclose(got, want, rtol=1e-11)
+
+
+def test_exp_variance_batched_fast_mode_in_law(Bm, golden):
+    """exp_variance in fast mode (all (cell, value) chains in the same launches, device random
+    numbers) against the host path that replays the reference draw for draw: same expectation
+    within Monte-Carlo error; known cells give NaN"""
+    g = golden("gibbs_15x12_d3")
+    kw = dict(rating_values=(1, 2, 3, 4, 5), discrete_expectations=True)
+    b = Bm.BayesianPMF(g["ratings"], 3, **kw)
+    b.users, b.items = g["users"].copy(), g["items"].copy()
+    np.random.seed(3)
+    samples = list(islice(b.samples(num_gibbs=2), 40))
+    cand = sorted(b.unrated)[:3]
+    which = tuple(np.array(cand).T)
+    S = 250
+    np.random.seed(4)
+    host = b.exp_variance(samples, which=which, num_samps=S, fit_first=False)
+    b.rng_mode = 'device'
+    np.random.seed(5)
+    fast = b.exp_variance(samples, which=which, num_samps=S, fit_first=False)
+    assert fast.shape == host.shape == (3,)
+    assert np.all(np.isfinite(fast)) and np.all(fast > 0)
+    assert np.abs(fast / host - 1).max() < 0.12, (fast, host)
+    known = tuple(np.array([tuple(map(int, g["ratings"][0, :2]))]).T)
+    with pytest.warns(UserWarning):
+        assert np.isnan(b.exp_variance(samples, which=known, num_samps=5)[0])
+    # continuous R_ij: normal fit, trapezoid over the ppf points
+    c = Bm.BayesianPMF(g["ratings"], 3, rating_values=None, discrete_expectations=False, num_integration_pts=7)
+    c.users, c.items = g["users"].copy(), g["items"].copy()
+    c.rng_mode = 'device'
+    cont = c.exp_variance(samples, which=which, num_samps=20)
+    assert cont.shape == (3,) and np.all(np.isfinite(cont)) and np.all(cont > 0)

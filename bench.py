@@ -90,8 +90,9 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, index, count=1):
+        self.index = index if count == 1 else ",".join(str(i) for i in range(count))
+        self.count = count
         self.rows = []
         self.proc = None
 
@@ -127,9 +128,14 @@ class ClockSampler:
             for nm, val in zip(names, parts[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None,
+               "sm_max_mhz": float(max(mx)) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if self.count > 1 and sm:
+            # nvidia-smi prints the GPUs round-robin: per-GPU medians expose a slow device
+            out["sm_mhz_per_gpu"] = [float(np.median(sm[g::self.count])) for g in range(self.count)]
+            out["sm_mhz"] = float(min(out["sm_mhz_per_gpu"]))
+        return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -390,7 +396,7 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         one_step()
     sync()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, world)
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
@@ -428,7 +434,13 @@ def run_ours(a):
     kt = step.kernel_times(U, V, params, dU, dV, sums, ci, cj, best, reps=max(5, a.steps // 2))
     tm = torch.tensor([total_ms, grad_ms, score_ms, kt["side_pass_ms"], kt["score_ms"], kt["score_flat_ms"]],
                       dtype=torch.float64, device=U.device)
+    per_rank = None
     if world > 1:
+        # every rank's own numbers, so that a straggling GPU shows as such in the line
+        allr = torch.empty((world, tm.numel()), dtype=torch.float64, device=U.device)
+        dist.all_gather_into_tensor(allr, tm.view(1, -1).contiguous())
+        per_rank = {"grad_phase_ms": (allr[:, 1] / a.steps).tolist(), "score_phase_ms": (allr[:, 2] / a.steps).tolist(),
+                    "grad_kernel_ms": allr[:, 3].tolist(), "score_kernel_ms": allr[:, 4].tolist()}
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms, grad_ms, score_ms, side_ms, scorek_ms, score_flat_ms = tm.tolist()
 
@@ -615,6 +627,8 @@ def run_ours(a):
         "clocks": clocks,
         "selected": {"value": float(bv), "index": bi, "check": selection_check},
     }
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if strong is not None:
         line["strong_scaling"] = strong
     if f64 is not None:

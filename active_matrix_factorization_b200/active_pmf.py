@@ -504,6 +504,9 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         per = 8 * (6 * k * k + 3 * k)
         chunk = max(1, min(B, int(6e9 // per)))
         out = np.empty(B)
+        # accepted line-search steps of every re-fit (a diagnostic: two implementations can only
+        # agree on a re-fit when their accept / reject sequences do)
+        steps_out = self._last_refit_steps = np.zeros(B, dtype=np.int64)
         for s in range(0, B, chunk):
             e = min(B, s + chunk)
             nb = e - s
@@ -513,6 +516,7 @@ class ActivePMF(ProbabilisticMatrixFactorization):
                                         extra=(ei[s:e], ej[s:e], er[s:e]))
             res = batch.fit(want_entropy=(what == 'entropy'),
                             want_totvar=(what == 'total_variance'))
+            steps_out[s:e] = res['steps']
             if what == 'entropy':
                 out[s:e] = res['entropy']
             elif what == 'total_variance':

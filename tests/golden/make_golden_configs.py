@@ -287,8 +287,14 @@ def case_quad_nodes():
     class Enough(Exception):
         pass
     out = {"cand_i": np.array([c[0] for c in cand]), "cand_j": np.array([c[1] for c in cand])}
+    steps = []
+
+    def counting_fit(self):          # fit_normal (active_pmf.py:242-249) with its step count kept
+        steps.append(sum(1 for _kl in self.fit_normal_kls()))
+    ActivePMF.fit_normal = counting_fit
     for t, c in enumerate(cand):
         seen = []
+        del steps[:]
 
         def fn(model, v=None, seen=seen):
             val = ActivePMF._approx_entropy(model)
@@ -304,6 +310,7 @@ def case_quad_nodes():
             pass
         out["nodes%d" % t] = np.array([s[0] for s in seen])
         out["values%d" % t] = np.array([s[1] for s in seen])
+        out["steps%d" % t] = np.array(steps[:len(seen)])
     save("quad_nodes_6x7_d2", **out)
 
 

@@ -65,10 +65,10 @@ def workload_name(a):
 def measured_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
     kernels, from the committed `ncu --set full` capture of this same command
-    (profiles/r01i_ncu_full_raw.csv, recipe benchmarks/profile_step.sh); {} if the summary file is
+    (profiles/r02_main_ncu_full_raw.csv, recipe benchmarks/profile_step.sh); {} if the summary file is
     missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01i_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return {}

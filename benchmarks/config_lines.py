@@ -172,6 +172,17 @@ def c3_movielens(hbm_peak):
         ms = cuda_ms(lambda: post.score(N.CRIT_PRED_VARIANCE, ci, cj, name, want_scores=False))
         out["S2_pred_variance_" + name] = roof(nc * 8 + (n + m) * d2 * es, nc * 2 * d2, ms, hbm_peak)
         out["S2_pred_variance_" + name]["cand_per_s"] = nc / (ms * 1e-3)
+    # scalable-mode lookahead over ALL unknown cells (5 rating values each): rows L1 of SURVEY 8d
+    import torch
+    Um, Vm = D.to_padded(a.users, "f64"), D.to_padded(a.items, "f64")
+    mu, _ = S.score_device(N.CRIT_PRED, "f64", ci, cj, d, Um, Vm)
+    sd = torch.ones_like(mu)
+    vals5 = np.array([1., 2., 3., 4., 5.])
+    for what, code in (("uv_entropy", N.LOOK_ENTROPY), ("total_variance", N.LOOK_TOTAL_VARIANCE)):
+        ms = cuda_ms(lambda: post.lookahead(code, ci, cj, vals5, N.WEIGHTS_DISCRETE, a.rating_bounds, mu, sd,
+                                            want_scores=False), reps=3, warm=1)
+        out["L1_scalable_" + what] = {"kernel_ms": ms, "cand_per_s": nc / (ms * 1e-3),
+                                      "refits_per_s": 5 * nc / (ms * 1e-3)}
     # class API end to end against the host-buffer C-ABI call on the same pool
     lib = N.require_device()
     U_h = np.ascontiguousarray(a.users, dtype=np.float64)

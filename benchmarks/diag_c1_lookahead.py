@@ -12,7 +12,7 @@ from active_matrix_factorization_b200 import normal as NM
 
 def build(mod):
     np.random.seed(0); random.seed(0)
-    real, ratings, vals = mod.make_fake_data(noise=.25, num_users=10, num_items=10, rank=2,
+    real, ratings, vals = ref.active_pmf.make_fake_data(noise=.25, num_users=10, num_items=10, rank=2,
                                              data_type='binary', mask_type='diag')
     a = mod.ActivePMF(ratings, latent_d=2, rating_values=vals, discrete_expectations=True)
     a.do_fit(); a.initialize_approx(); a.fit_normal()

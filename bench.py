@@ -633,7 +633,7 @@ def run_ours(a):
         line["strong_scaling"] = strong
     if f64 is not None:
         line.update(f64)
-    if not a.no_configs:
+    if not a.no_configs and world == 1:
         from benchmarks import config_lines as CL
         line["configs"] = CL.all_configs(hbm_peak)
         try:

@@ -697,6 +697,9 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         (n, 2) integer array is uploaded once and remembered while the same object comes back;
         anything else is listed and converted like the reference's iteration over it.'''
         if isinstance(pool, _scoring.CandidatePool):
+            pools = self._dev.setdefault('candidate_pools', [])
+            if not any(p is pool for p in pools):
+                pools.append(pool)           # add_rating(s) removes queried cells from it
             ci, cj = pool.device_arrays()
             return pool, ci, cj
         if isinstance(pool, np.ndarray) and pool.ndim == 2 and pool.shape[1] == 2:

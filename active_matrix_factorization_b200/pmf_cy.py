@@ -277,6 +277,11 @@ class ProbabilisticMatrixFactorization(object):
             raise ValueError("can't rate already rated items")
         self.rated.update(new_items)
         self.unrated.difference_update(new_items)
+        # device-resident candidate pools this model has scored (scoring.CandidatePool): the
+        # queried cells leave them too, as they leave `unrated` (pmf_cy.pyx:152)
+        for pool in list(self.__dict__.get('_dev', {}).get('candidate_pools', ())):
+            for i, j in new_items:
+                pool.remove(i, j)
 
         # active-loop residency: a rating list that already lives on the device
         # takes the new ratings as an appended tail instead of being re-uploaded and re-sorted

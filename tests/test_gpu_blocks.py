@@ -241,3 +241,7 @@ def test_resident_candidate_pool(K, golden):
             max(pool, key=lambda c: a.pred_variance(c))
     ev = a.get_key_evals(cp, A.ActivePMF.pred)
     assert np.isfinite(ev).sum() == len(pool)
+    # a pool the model has scored follows add_rating, like `unrated` does
+    ij = a.pick_query_point(cp, A.ActivePMF.pred)
+    a.add_rating(ij[0], ij[1], 1.0)
+    assert ij not in set(cp) and len(cp) == len(pool) - 1 and ij not in a.unrated

@@ -206,6 +206,37 @@ def test_from_coo_matches_tuple_constructor(amf):
     np.testing.assert_allclose(b.users, a2.users, rtol=1e-7, atol=1e-9)
 
 
+def test_from_coo_file_formats(amf, tmp_path):
+    """SURVEY.md 8f-3 loaders on the device path: an i/j/r archive, the reference's `_ratings`
+    dictionary (choose_training.py:215-259), a .npy table and text lines all give the model the
+    tuple constructor builds"""
+    import pickle
+    rng = np.random.RandomState(6)
+    n, m, d, nnz = 40, 30, 4, 300
+    cells = rng.permutation(n * m)[:nnz]
+    ii, jj = cells // m, cells % m
+    ii[0], jj[0] = n - 1, m - 1
+    r = rng.randint(1, 6, nnz).astype(float)
+    R = np.column_stack((ii, jj, r)).astype(float)
+    U, V = rng.normal(0, .3, (n, d)), rng.normal(0, .3, (m, d))
+    want = make_model(amf, R, U, V, d, "f64", True)
+    PMF = amf.ProbabilisticMatrixFactorization
+    paths = []
+    p = str(tmp_path / "a.npz"); np.savez(p, i=ii, j=jj, r=r, shape=np.array([n, m])); paths.append(p)
+    p = str(tmp_path / "b.npz"); np.savez(p, _ratings=R, _real=np.zeros((n, m))); paths.append(p)
+    p = str(tmp_path / "c.pkl")
+    with open(p, "wb") as f:
+        pickle.dump({"_ratings": R, "_real": np.zeros((n, m)), "_rating_vals": (1, 2, 3, 4, 5)}, f)
+    paths.append(p)
+    p = str(tmp_path / "d.npy"); np.save(p, R); paths.append(p)
+    p = str(tmp_path / "e.txt"); np.savetxt(p, R); paths.append(p)
+    for p in paths:
+        b = PMF.from_coo_file(p, d, True, init=(U.copy(), V.copy()))
+        assert (b.num_users, b.num_items) == (n, m), p
+        assert b.log_likelihood() == pytest.approx(want.log_likelihood(), rel=1e-12), p
+        np.testing.assert_allclose(b.gradient()[0], want.gradient()[0], rtol=1e-11, atol=1e-12)
+
+
 @pytest.mark.parametrize("sm", [False, True])
 def test_device_fit_matches_reference_trajectory(amf, golden, sm):
     """amf_pmf_fit_lls: the whole line search in one launch takes the reference's accepted steps

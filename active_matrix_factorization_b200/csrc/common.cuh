@@ -231,15 +231,19 @@ int launch_best_final(const Best* part_d, int nparts, bool maximize, amf_best_t*
 
 }  // namespace amf
 
-// One side of the tiled copy of the rating list (tiled.cu): entries bucketed by tile of the
-// "tile side" matrix, sorted by the row of the "stream side" inside a tile.
-struct amf_tiled_side {
-  int tile_rows, jbits, n_tiles;
-  int64_t n_chunks, npad;
-  uint32_t* cw;           // [npad] stream row << jbits | local tile row   (padding: 0)
-  void* rv;               // [npad] ratings (padding: 0)
-  int64_t* tile_cstart;   // [n_tiles+1] first chunk of every tile
-  int64_t* tile_count;    // [n_tiles] entries of every tile
+// A sparse list in the "bundled runs" layout (runs.cuh / runs.cu): entries bucketed by tile of the
+// "tile side" matrix, one lane per run segment of the "own side" row, 32 segments per bundle.
+struct amf_runs {
+  int tile_rows, n_tiles;
+  int64_t n, n_bundles, n_groups, npos;   // npos = n_groups * 256 entry slots (padding included)
+  uint16_t* idx;          // [npos] local row inside the tile (padding: tile_rows)
+  void* val;              // [npos] values (NULL for a candidate pool; padding: 0)
+  uint32_t* orig;         // [npos] position in the caller's list (RUNS_NONE = padding / removed) or NULL
+  uint32_t* pos_of;       // [n] slot of the caller's entry c, or NULL
+  uint32_t* rowid;        // [n_bundles * 32] own row of every lane (RUNS_NONE = empty lane)
+  uint8_t* seglen;        // [n_bundles * 32] entries of every lane's segment
+  int2* binfo;            // [n_bundles + 1] {first group, longest segment}; the last one = {n_groups, 0}
+  int64_t* tile_bstart;   // [n_tiles + 1] first bundle of every tile
 };
 
 struct amf_ratings {
@@ -258,7 +262,7 @@ struct amf_ratings {
   double* sums_d;
   int device;
   // side 0: users stream past item tiles (dU); side 1: items stream past user tiles (dV)
-  amf_tiled_side tiled[2];
+  amf_runs tiled[2];
   int tiled_row_bytes;    // padded factor-row size the tiles were cut for (0 = not built)
   int tiled_mode;         // AMF_LAYOUT_AUTO / _ROWS / _TILED
   // ratings appended since the sorted lists were built (amf_ratings_append): plain COO, folded
@@ -271,6 +275,12 @@ struct amf_ratings {
 namespace amf {
 // merges the appended tail into the sorted lists (no-op if there is none)
 int ratings_compact(amf_ratings* h, cudaStream_t s);
+// runs.cu: builds the bundled-runs layout of n entries (own[t], other[t] [, val[t]]) on the device;
+// val_size = 0 / 4 / 8 bytes per value; want_orig keeps the permutation back to the caller's order
+int runs_build(amf_runs* out, int64_t n, const int32_t* own_d, const int32_t* other_d,
+               const void* val_d, int val_size, int32_t own_rows, int32_t other_rows, int tile_rows,
+               bool want_orig, cudaStream_t s);
+void runs_free(amf_runs* r);
 }  // namespace amf
 
 #define AMF_SUB 32

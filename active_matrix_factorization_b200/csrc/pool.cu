@@ -1,50 +1,25 @@
 // Candidate pool handle: the reference's `pool` / `unrated` set (active_pmf.py:725-737) kept on
-// the device in a layout built for the scoring kernel.
+// the device in the "bundled runs" layout (runs.cuh) built for the scoring kernel.
 //
 // The plain scoring kernel (scoring.cu) gathers one factor row per candidate from L2 and sits
-// at the L2->SM gather ceiling.  Here the pool is bucketed once by item tile: candidates are
-// sorted by (j / TJ, i, j), so a CTA keeps a TJ-row tile of V in shared memory (TMA bulk
-// copies) and reads every item row from there; the user row lives in registers and is fetched
-// from L2 only when the user changes (about once per TJ * density candidates).  Each candidate
-// costs 4 bytes of HBM: one packed word  i << ceil(log2(TJ)) | (j % TJ).
-//
-// Memory order inside a tile.  The sorted list of a tile is cut into chunks of POOL_CHUNK
-// candidates; a warp scores one chunk at a time in POOL_RUN batches of 32.  A group of four
-// lanes owns four candidates per batch, and the chunk is stored so that the 4*POOL_RUN
-// candidates a group meets over the whole chunk are CONSECUTIVE in sorted order (long runs of
-// the same user -> few user-row fetches) while every batch is still one coalesced 128-byte
-// read:   position = chunk*POOL_CHUNK + batch*32 + group*4 + q
-//         sorted offset inside the chunk = group*(4*POOL_RUN) + batch*4 + q.
+// at the L2->SM gather ceiling.  Here the pool is bucketed once by item tile: a CTA keeps a
+// tile of V in shared memory (TMA bulk copies) and reads every item row from there; the
+// candidates one user has inside one tile are a run, ONE LANE owns a run segment and keeps the
+// whole user row in registers, 32 equally long segments make the bundle a warp works on.  A
+// candidate costs 2 bytes of HBM (its 16-bit row inside the tile) and exactly one shared-memory
+// wavefront (the 128-byte item row at d = 32 fp32) -- no shuffles, no divergent user changes.
 // The permutation back to the caller's order is kept, so scores and the winner are reported
 // exactly as the unbucketed path would.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 
 #include "common.cuh"
-#include "tile_stream.cuh"
-
-namespace amf {
-constexpr int POOL_RUN = 16;                    // batches of 32 candidates per chunk
-constexpr int POOL_CHUNK = 32 * POOL_RUN;       // candidates per chunk (one warp, one grab)
-static_assert(POOL_RUN >= 2, "the index words are prefetched two batches ahead");
-constexpr int POOL_THREADS = 1024;              // one CTA per SM
-constexpr uint32_t POOL_TOMBSTONE = 0xffffffffu;   // orig[] value of padding / removed candidates
-}  // namespace amf
+#include "runs.cuh"
 
 struct amf_pool {
   int64_t ncand;         // candidates given by the caller
-  int64_t npad;          // entries in the bucketed arrays (every tile padded to whole chunks)
   int32_t n_users, n_items;
-  int tile_rows;         // TJ: items per tile (V tile resident in shared memory)
-  int jbits;             // bits of the local item index: ceil(log2(tile_rows))
-  int n_tiles;
-  int64_t n_chunks;      // npad / POOL_CHUNK
-  uint32_t* cw;          // [npad] packed indices  i << jbits | j % TJ   (padding: 0)
-  uint32_t* orig;        // [npad] position in the caller's pool (POOL_TOMBSTONE = padding/removed)
-  uint32_t* pos_of;      // [ncand] bucketed position of the caller's candidate c
-  int64_t* tile_cstart;  // [n_tiles+1] first chunk of every tile
-  void* tmp_scores;      // scratch for scores in bucketed order
+  amf_runs runs;         // own side = users, tile side = items; orig/pos_of kept
+  void* tmp_scores;      // scratch for scores in slot order
   size_t tmp_bytes;
 };
 
@@ -52,117 +27,101 @@ namespace amf {
 
 int acquire_partials(Best** out, cudaStream_t s);
 
-__global__ void pool_keys_kernel(const int32_t* __restrict__ ci, const int32_t* __restrict__ cj,
-                                 int64_t n, int tile_rows, int jbits, int ibits,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = (uint32_t)ci[t], j = (uint32_t)cj[t];
-    const uint64_t tile = j / (uint32_t)tile_rows, jl = j % (uint32_t)tile_rows;
-    keys[t] = (((tile << ibits) | i) << jbits) | jl;
-    vals[t] = (uint32_t)t;
+constexpr int64_t POOL_BUNDLE_COST = 5;      // row fetch of a bundle, in entry steps (micro_visit.cu)
+
+template <int NVEC> constexpr int pool_threads() { return NVEC >= 16 ? 256 : 512; }
+// dynamic shared memory: [per-warp staging][tile rows][one NaN row for the padding index]
+template <int NVEC> constexpr size_t pool_stage_total() {
+  return (size_t)(pool_threads<NVEC>() / 32) * runs_stage_bytes<NVEC>();
+}
+constexpr size_t POOL_SMEM_BUDGET = 227 * 1024 - 1024;   // static buffers of the kernel fit the rest
+
+template <int C>
+__device__ __forceinline__ float dot_rows(const float4 (&a)[C], const float4 (&b)[C]) {
+  float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll
+  for (int t = 0; t < C; ++t) {
+    if (t & 1) {
+      s2 = fma2(make_float2(a[t].x, a[t].y), make_float2(b[t].x, b[t].y), s2);
+      s3 = fma2(make_float2(a[t].z, a[t].w), make_float2(b[t].z, b[t].w), s3);
+    } else {
+      s0 = fma2(make_float2(a[t].x, a[t].y), make_float2(b[t].x, b[t].y), s0);
+      s1 = fma2(make_float2(a[t].z, a[t].w), make_float2(b[t].z, b[t].w), s1);
+    }
   }
+  return ((s0.x + s1.x) + (s2.x + s3.x)) + ((s0.y + s1.y) + (s2.y + s3.y));
 }
-
-// keys sorted ascending; start[b] = first position whose tile >= b, start[n_tiles] = n
-__global__ void pool_tile_start_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
-                                       int64_t n_tiles, int64_t* __restrict__ start) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p <= n;
-       p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t lo = (p == 0) ? -1 : (int64_t)(keys[p - 1] >> shift);
-    const int64_t hi = (p == n) ? n_tiles : (int64_t)(keys[p] >> shift);
-    for (int64_t b = lo + 1; b <= hi; ++b) start[b] = p;
+template <int C>
+__device__ __forceinline__ double dot_rows(const double2 (&a)[C], const double2 (&b)[C]) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+  for (int t = 0; t < C; ++t) {
+    if (t & 1) { s2 = fma(a[t].x, b[t].x, s2); s3 = fma(a[t].y, b[t].y, s3); }
+    else { s0 = fma(a[t].x, b[t].x, s0); s1 = fma(a[t].y, b[t].y, s1); }
   }
+  return (s0 + s1) + (s2 + s3);
 }
 
-__global__ void pool_nchunk_kernel(const int64_t* __restrict__ start, int64_t n_tiles,
-                                   int64_t* __restrict__ nchunk) {
-  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b <= n_tiles;
-       b += (int64_t)gridDim.x * blockDim.x)
-    nchunk[b] = b < n_tiles ? (start[b + 1] - start[b] + POOL_CHUNK - 1) / POOL_CHUNK : 0;
+__device__ __forceinline__ void st_scores4(float* p, const float (&v)[4]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void st_scores4(double* p, const double (&v)[4]) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+  __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
 }
 
-__global__ void pool_scatter_kernel(const uint64_t* __restrict__ keys,
-                                    const uint32_t* __restrict__ perm, int64_t n, int ibits,
-                                    int jbits, const int64_t* __restrict__ start,
-                                    const int64_t* __restrict__ tile_cstart,
-                                    uint32_t* __restrict__ cw, uint32_t* __restrict__ orig,
-                                    uint32_t* __restrict__ pos_of) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
-       p += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t k = keys[p];
-    const int64_t b = (int64_t)(k >> (ibits + jbits));
-    const int64_t o = p - start[b];                       // sorted offset inside the tile
-    const int64_t chunk = tile_cstart[b] + o / POOL_CHUNK;
-    const int oo = (int)(o % POOL_CHUNK);
-    const int g = oo / (4 * POOL_RUN), r = (oo % (4 * POOL_RUN)) >> 2, q = oo & 3;
-    const int64_t pos = chunk * POOL_CHUNK + r * 32 + g * 4 + q;
-    cw[pos] = (uint32_t)(k & ((1ull << (ibits + jbits)) - 1));
-    orig[pos] = perm[p];
-    pos_of[perm[p]] = (uint32_t)pos;
-  }
-}
-
-static int bits_for_count(uint64_t x) {
-  int b = 1;
-  while (b < 63 && (1ull << b) < x) ++b;
-  return b;
-}
-
-// PRED over a bucketed pool.  One CTA per SM owns a contiguous range of chunks; for every item
-// tile that range touches, the tile is brought into shared memory by TMA and the warps grab
-// chunks of that tile from a shared counter.  Four lanes score one candidate: lane l holds the
-// 16-byte slices l, l+4, ... of the factor rows (CPL per lane).  The two lane groups that share
-// a shared-memory wavefront start at different slices ((t + group parity) mod CPL), so the
-// eight lanes of a wavefront always hit eight different 16-byte bank groups whatever rows they
-// read: one wavefront per 128 bytes, no conflicts.  A transpose-reduce over the four lanes
-// leaves one finished dot product per lane (position base + lane): coalesced score stores and
-// one compare per lane for the fused arg-best.
+// PRED over a pool in the bundled-runs layout.  One CTA per SM owns a contiguous range of
+// bundles (equal cost); for every item tile that range touches, the tile is brought into shared
+// memory by TMA and the warps grab bundles of that tile from a shared counter (the metadata of
+// the next bundle is fetched while the current one is scored).  A lane scores one candidate per
+// step with its user row in registers; the fused arg-best compares once per group of four steps
+// and looks up the caller's position only for scores that reach the warp's running best.
 template <typename T, int NVEC, bool MAX>
-__global__ void __launch_bounds__(POOL_THREADS, 1)
-pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ orig,
-                 const int64_t* __restrict__ tile_cstart, int n_tiles, int64_t n_chunks,
-                 int jbits, int tile_rows, int n_items, const T* __restrict__ U,
-                 const T* __restrict__ Vm, T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
+__global__ void __launch_bounds__(pool_threads<NVEC>(), 1)
+pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ orig,
+                 const uint32_t* __restrict__ rowid, const int2* __restrict__ binfo,
+                 const int64_t* __restrict__ tile_bstart, int n_tiles, int64_t n_bundles,
+                 int tile_rows, int n_items, const T* __restrict__ U, const T* __restrict__ Vm,
+                 T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
   using V = typename Vec<T>::type;
-  constexpr int CPL = NVEC >= 4 ? NVEC / 4 : 1;       // 16-byte slices per lane
   constexpr uint32_t ROW_BYTES = NVEC * 16;
+  constexpr int THREADS = pool_threads<NVEC>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_v;
   __shared__ unsigned int s_ctr;
-  const uint32_t smem0 = smem_u32(smem_raw);
-  const int lane = threadIdx.x & 31;
-  const int g = lane >> 2, l = lane & 3;
-  const uint32_t jmask = (1u << jbits) - 1;
-  const bool have = l < NVEC;                         // rows narrower than four slices
-  constexpr bool ADJ = CPL == 2;                      // measured: -3 % time at d=32 fp32
-  const uint32_t off0 = slice_off0<CPL, ADJ>(l, g & 1, have);
-  const uint32_t vrow0 = smem0 + off0;                // tile base is 1024-byte aligned
-  const uint64_t urow = (uint64_t)reinterpret_cast<uintptr_t>(U);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stage = smem_u32(smem_raw) + warp * runs_stage_bytes<NVEC>();
+  unsigned char* tile_ptr = smem_raw + pool_stage_total<NVEC>();
+  const uint32_t tile0 = smem_u32(tile_ptr) | runs_lane_rot<NVEC>(lane);
+  const unsigned char* Ub = reinterpret_cast<const unsigned char*>(U);
 
-  const int64_t c_lo = n_chunks * blockIdx.x / gridDim.x;
-  const int64_t c_hi = n_chunks * (blockIdx.x + 1) / gridDim.x;
+  const int64_t total = runs_cost(binfo, n_bundles, POOL_BUNDLE_COST);
+  const int64_t b_lo = runs_split(binfo, n_bundles, POOL_BUNDLE_COST, total * blockIdx.x / gridDim.x);
+  const int64_t b_hi = blockIdx.x + 1 == gridDim.x
+                           ? n_bundles
+                           : runs_split(binfo, n_bundles, POOL_BUNDLE_COST,
+                                        total * (blockIdx.x + 1) / gridDim.x);
   if (threadIdx.x == 0) mbar_init(&bar_v, 1);
+  // the row behind the tile: what padding entries read.  NaN scores never win.
+  for (int t = threadIdx.x; t < (int)(ROW_BYTES / sizeof(T)); t += THREADS)
+    reinterpret_cast<T*>(tile_ptr + (size_t)tile_rows * ROW_BYTES)[t] = T(NAN);
   int t_cur = 0;
-  {                                                   // last tile starting at or before c_lo
+  {                                                   // last tile starting at or before b_lo
     int lo = 0, hi = n_tiles;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (tile_cstart[mid] <= c_lo) lo = mid; else hi = mid - 1;
+      if (tile_bstart[mid] <= b_lo) lo = mid; else hi = mid - 1;
     }
     t_cur = lo;
   }
-  T best_v = MAX ? -INFINITY : INFINITY, thr = best_v;
+  const T worst = MAX ? -INFINITY : INFINITY;
+  T best_v = worst, thr = worst;
   int64_t best_o = -1;
-  V a[CPL];
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) a[t] = vzero(V());
-  uint32_t prev_i = 0xffffffffu;
   uint32_t phase_v = 0;
 
-  for (int64_t c = c_lo; c < c_hi;) {
-    while (t_cur + 1 < n_tiles && tile_cstart[t_cur + 1] <= c) ++t_cur;
-    const int64_t seg_end = min(c_hi, tile_cstart[t_cur + 1]);
+  for (int64_t c = b_lo; c < b_hi;) {
+    while (t_cur + 1 < n_tiles && tile_bstart[t_cur + 1] <= c) ++t_cur;
+    const int64_t seg_end = min(b_hi, tile_bstart[t_cur + 1]);
     __syncthreads();                                  // previous tile and counter are done with
     if (threadIdx.x == 0) {
       s_ctr = 0;
@@ -173,68 +132,70 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
       const unsigned char* src =
           reinterpret_cast<const unsigned char*>(Vm) + (int64_t)t_cur * tile_rows * ROW_BYTES;
       for (uint32_t o = 0; o < bytes; o += 32768u)
-        tma_load_1d(smem_raw + o, src + o, min(bytes - o, 32768u), &bar_v);
+        tma_load_1d(tile_ptr + o, src + o, min(bytes - o, 32768u), &bar_v);
     }
     __syncthreads();
     mbar_wait(&bar_v, phase_v);
     phase_v ^= 1;
 
-    for (;;) {
-      unsigned int grab = 0;
-      if (lane == 0) grab = atomicAdd(&s_ctr, 1u);
-      const int64_t chunk = c + (int64_t)__shfl_sync(0xffffffffu, grab, 0);
-      if (chunk >= seg_end) break;
-      const int64_t cb = chunk * POOL_CHUNK;
-      const uint4* wp = reinterpret_cast<const uint4*>(cw + cb) + g;
-      // index words two batches ahead (HBM latency)
-      uint4 w1 = __ldcs(wp), w2 = __ldcs(wp + 8);
+    auto grab = [&]() -> int64_t {
+      unsigned int g = 0;
+      if (lane == 0) g = atomicAdd(&s_ctr, 1u);
+      return c + (int64_t)__shfl_sync(0xffffffffu, g, 0);
+    };
+    int64_t b = grab();
+    int2 info = make_int2(0, 0);
+    uint32_t rid = RUNS_NONE;
+    if (b < seg_end) { info = binfo[b]; rid = rowid[b * 32 + lane]; }
+    while (b < seg_end) {
+      const int64_t nb = grab();
+      int2 ninfo = make_int2(0, 0);
+      uint32_t nrid = RUNS_NONE;
+      if (nb < seg_end) { ninfo = binfo[nb]; nrid = rowid[nb * 32 + lane]; }
+
+      AMF_DBG_ASSERT(rid == RUNS_NONE || rid < 0x7fffffffu);
+      V a[NVEC];
+      fetch_rows<V, NVEC>(Ub, rid, stage, lane, a);
+      const int L = info.y, G = (L + 3) >> 2;
+      const uint2* ip = reinterpret_cast<const uint2*>(idx) + (int64_t)info.x * 32 + lane;
+      uint2 w = __ldcs(ip);
 #pragma unroll 1
-      for (int r = 0; r < POOL_RUN; ++r) {
-        const uint4 w4 = w1;
-        w1 = w2;
-        if (r + 2 < POOL_RUN) w2 = __ldcs(wp + (r + 2) * 8);
-        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-        T p[4];
+      for (int g = 0; g < G; ++g) {
+        uint2 wn = w;
+        if (g + 1 < G) wn = __ldcs(ip + (g + 1) * 32);
+        const int ns = L - 4 * g;
+        const uint32_t j4[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+        T p[4] = {worst, worst, worst, worst};
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          // slice t of a row sits at  off0 ^ slice_xor(t)  (rows are ROW_BYTES-aligned)
-          AMF_DBG_ASSERT((int)(w[s] & jmask) < tile_rows);       // inside the shared-memory tile
-          const uint32_t row = ((w[s] & jmask) * ROW_BYTES) + vrow0;
-          V b[CPL];
-#pragma unroll
-          for (int t = 0; t < CPL; ++t) b[t] = lds_v(row ^ slice_xor<CPL, ADJ>(t), V());
-          const uint32_t i = w[s] >> jbits;
-          if (i != prev_i) {                          // next user of this lane group's run
-            prev_i = i;
-            load_row_slices<V, CPL, ADJ>(urow + (uint64_t)i * ROW_BYTES, have ? l : 0, g & 1, off0, a);
+          if (s < ns) {
+            AMF_DBG_ASSERT((int)j4[s] <= tile_rows);
+            V bb[NVEC];
+            lds_row<V, NVEC>(tile0 + j4[s] * ROW_BYTES, bb);
+            p[s] = dot_rows<NVEC>(a, bb);
           }
-          const T acc = dot_slices<CPL>(a, b);
-          p[s] = have ? acc : T(0);
         }
-        // transpose-reduce over the four lanes: lane l ends with candidate l of the group
-        {
-          const bool up2 = (l & 2) != 0;
-          const T s0 = up2 ? p[0] : p[2], s1 = up2 ? p[1] : p[3];
-          const T k0 = up2 ? p[2] : p[0], k1 = up2 ? p[3] : p[1];
-          p[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-          p[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-          const bool up1 = (l & 1) != 0;
-          const T s = up1 ? p[0] : p[1], k = up1 ? p[1] : p[0];
-          p[0] = k + __shfl_xor_sync(0xffffffffu, s, 1);
-        }
-        const int64_t pos = cb + r * 32 + lane;
-        if (scores) __stcs(scores + pos, p[0]);
+        const int64_t pos = ((int64_t)info.x + g) * 128 + lane * 4;
+        if (scores) st_scores4(scores + pos, p);
         // arg-best: `thr` is the best value any lane of this warp holds; only scores that reach
         // it (ties included: a lower index may still win) look up their original position
-        const bool reach = MAX ? (p[0] >= thr) : (p[0] <= thr);
+        T m = p[0];
+#pragma unroll
+        for (int s = 1; s < 4; ++s) m = MAX ? fmax(m, p[s]) : fmin(m, p[s]);
+        const bool reach = MAX ? (m >= thr) : (m <= thr);
         if (__any_sync(0xffffffffu, reach)) {
           if (reach) {
-            const uint32_t ou = orig[pos];
-            const int64_t o = (int64_t)ou;
-            if (ou != POOL_TOMBSTONE &&
-                (best_o < 0 || (MAX ? (p[0] > best_v) : (p[0] < best_v)) ||
-                 (p[0] == best_v && o < best_o))) {
-              best_v = p[0]; best_o = o;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              if (MAX ? (p[s] >= thr) : (p[s] <= thr)) {
+                const uint32_t ou = orig[pos + s];
+                const int64_t o = (int64_t)ou;
+                if (ou != RUNS_NONE &&
+                    (best_o < 0 || (MAX ? (p[s] > best_v) : (p[s] < best_v)) ||
+                     (p[s] == best_v && o < best_o))) {
+                  best_v = p[s]; best_o = o;
+                }
+              }
             }
           }
           T v = best_v;                               // +-inf while the lane holds nothing
@@ -245,7 +206,9 @@ pool_pred_kernel(const uint32_t* __restrict__ cw, const uint32_t* __restrict__ o
           }
           thr = v;
         }
+        w = wn;
       }
+      b = nb; info = ninfo; rid = nrid;
     }
     c = seg_end;
   }
@@ -260,23 +223,30 @@ __global__ void unpermute_kernel(const T* __restrict__ in, const uint32_t* __res
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < npad;
        t += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t o = orig[t];
-    if (o != POOL_TOMBSTONE) out[o] = in[t];
+    if (o != RUNS_NONE) out[o] = in[t];
   }
+}
+
+template <int NVEC> static size_t pool_smem(int tile_rows) {
+  return pool_stage_total<NVEC>() + ((size_t)tile_rows + 1) * NVEC * 16;
 }
 
 template <typename T, bool MAX>
 static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* scores_tmp,
-                     int64_t index_base, Best* part, int grid, size_t smem, cudaStream_t s) {
+                     int64_t index_base, Best* part, int grid, cudaStream_t s) {
   constexpr int N = Vec<T>::N;
   const int nvec = ld / N;
+  const amf_runs* r = &h->runs;
 #define POOL(NVEC_)                                                                             \
   do {                                                                                          \
+    const size_t smem = pool_smem<NVEC_>(r->tile_rows);                                         \
+    AMF_REQUIRE(smem <= POOL_SMEM_BUDGET, "item tile (%d rows of %d) does not fit shared "      \
+                "memory: build the pool with amf_pool_max_tile_rows", r->tile_rows, ld);        \
     AMF_CUDA(cudaFuncSetAttribute(pool_pred_kernel<T, NVEC_, MAX>,                              \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    pool_pred_kernel<T, NVEC_, MAX><<<grid, POOL_THREADS, smem, s>>>(                           \
-        h->cw, h->orig, h->tile_cstart, h->n_tiles, h->n_chunks, h->jbits, h->tile_rows,        \
-        h->n_items, U, V,                                                                       \
-        scores_tmp, index_base, part);                                                          \
+    pool_pred_kernel<T, NVEC_, MAX><<<grid, pool_threads<NVEC_>(), smem, s>>>(                  \
+        r->idx, r->orig, r->rowid, r->binfo, r->tile_bstart, r->n_tiles, r->n_bundles,          \
+        r->tile_rows, h->n_items, U, V, scores_tmp, index_base, part);                          \
   } while (0)
   switch (nvec) {            // the row width is a compile-time constant of the kernel
     case 1: POOL(1); break;
@@ -284,9 +254,8 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
     case 4: POOL(4); break;
     case 8: POOL(8); break;
     case 16: POOL(16); break;
-    case 32: POOL(32); break;
     default:
-      set_error("bucketed pool needs a padded row of 1, 2, 4, 8, 16 or 32 16-byte vectors (ld=%d)", ld);
+      set_error("bucketed pool needs a padded row of 1, 2, 4, 8 or 16 16-byte vectors (ld=%d)", ld);
       return AMF_ERR_UNSUPPORTED;
   }
 #undef POOL
@@ -301,9 +270,23 @@ using namespace amf;
 extern "C" {
 #pragma GCC visibility push(default)
 
+int amf_pool_max_tile_rows(int row_bytes) {
+  size_t stage = 0;
+  switch (row_bytes) {
+    case 16: stage = pool_stage_total<1>(); break;
+    case 32: stage = pool_stage_total<2>(); break;
+    case 64: stage = pool_stage_total<4>(); break;
+    case 128: stage = pool_stage_total<8>(); break;
+    case 256: stage = pool_stage_total<16>(); break;
+    default: return 0;
+  }
+  const size_t rows = (POOL_SMEM_BUDGET - stage) / (size_t)row_bytes - 1;
+  return (int)(rows > 65535 ? 65535 : rows);
+}
+
 int amf_pool_destroy(amf_pool_t* h) {
   if (!h) return AMF_OK;
-  cudaFree(h->cw); cudaFree(h->orig); cudaFree(h->pos_of); cudaFree(h->tile_cstart);
+  runs_free(&h->runs);
   cudaFree(h->tmp_scores);
   delete h;
   return AMF_OK;
@@ -312,88 +295,17 @@ int amf_pool_destroy(amf_pool_t* h) {
 int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
                     int32_t n_users, int32_t n_items, int tile_rows, void* stream) {
   AMF_REQUIRE(out && n_users > 0 && n_items > 0, "amf_pool_create: bad arguments");
-  AMF_REQUIRE(ncand >= 0 && ncand < (1ll << 32) - 2 * POOL_CHUNK, "amf_pool_create: ncand out of range");
-  AMF_REQUIRE(tile_rows >= 1 && tile_rows <= 32768, "amf_pool_create: tile_rows must be in [1, 32768]");
-  int jbits = 0;
-  while ((1 << jbits) < tile_rows) ++jbits;
-  const int ibits = bits_for_count((uint64_t)n_users);
-  AMF_REQUIRE(ibits + jbits <= 32, "amf_pool_create: %d users x tiles of %d items do not fit the "
-              "4-byte packed index (use amf_score_candidates)", n_users, tile_rows);
+  AMF_REQUIRE(ncand >= 0 && ncand < (1ll << 31), "amf_pool_create: ncand out of range");
+  AMF_REQUIRE(tile_rows >= 1 && tile_rows <= 65535, "amf_pool_create: tile_rows must be in [1, 65535]");
   cudaStream_t s = (cudaStream_t)stream;
   AMF_REQUIRE(ncand == 0 || (ci_d && cj_d), "amf_pool_create: NULL candidate arrays");
   AMF_CHECK_ID_RANGE("amf_pool_create", ci_d, n_users, cj_d, n_items, ncand, s);
   amf_pool* h = new amf_pool();
   memset(h, 0, sizeof(*h));
   h->ncand = ncand; h->n_users = n_users; h->n_items = n_items;
-  h->tile_rows = tile_rows; h->jbits = jbits;
-  h->n_tiles = (n_items + tile_rows - 1) / tile_rows;
-  int rc = AMF_OK;
-  uint64_t *keys = nullptr, *keys_out = nullptr;
-  uint32_t *vals = nullptr, *perm = nullptr;
-  int64_t *start = nullptr, *nchunk = nullptr;
-  void* tmp = nullptr;
-  const size_t cnt = ncand > 0 ? (size_t)ncand : 1;
-  const int grid = num_sms() * 8;
-  const int64_t nt = h->n_tiles;
-#define POOL_CUDA(call)                                                                          \
-  do {                                                                                           \
-    cudaError_t e__ = (call);                                                                    \
-    if (e__ != cudaSuccess) {                                                                    \
-      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
-      rc = AMF_ERR_CUDA;                                                                         \
-      goto done;                                                                                 \
-    }                                                                                            \
-  } while (0)
-  {
-    const int tbits = bits_for_count((uint64_t)nt + 1);
-    size_t tmp_bytes = 0, scan_bytes = 0;
-    int64_t total_chunks = 0;
-    POOL_CUDA(cudaMalloc(&h->tile_cstart, 8 * (size_t)(nt + 1)));
-    POOL_CUDA(cudaMalloc(&start, 8 * (size_t)(nt + 1)));
-    POOL_CUDA(cudaMalloc(&nchunk, 8 * (size_t)(nt + 1)));
-    POOL_CUDA(cudaMalloc(&keys, 8 * cnt));
-    POOL_CUDA(cudaMalloc(&keys_out, 8 * cnt));
-    POOL_CUDA(cudaMalloc(&vals, 4 * cnt));
-    POOL_CUDA(cudaMalloc(&perm, 4 * cnt));
-    if (ncand > 0) {
-      pool_keys_kernel<<<grid, 256, 0, s>>>(ci_d, cj_d, ncand, tile_rows, jbits, ibits, keys, vals);
-      POOL_CUDA(cudaGetLastError());
-      POOL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, perm,
-                                                ncand, 0, ibits + jbits + tbits, s));
-      POOL_CUDA(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
-      POOL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, perm, ncand,
-                                                0, ibits + jbits + tbits, s));
-      cudaFree(tmp); tmp = nullptr;
-    }
-    pool_tile_start_kernel<<<grid, 256, 0, s>>>(keys_out, ncand, ibits + jbits, nt, start);
-    POOL_CUDA(cudaGetLastError());
-    pool_nchunk_kernel<<<grid, 256, 0, s>>>(start, nt, nchunk);
-    POOL_CUDA(cudaGetLastError());
-    POOL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, nchunk, h->tile_cstart, nt + 1, s));
-    POOL_CUDA(cudaMalloc(&tmp, scan_bytes > 0 ? scan_bytes : 1));
-    POOL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, nchunk, h->tile_cstart, nt + 1, s));
-    POOL_CUDA(cudaMemcpyAsync(&total_chunks, h->tile_cstart + nt, 8, cudaMemcpyDeviceToHost, s));
-    POOL_CUDA(cudaStreamSynchronize(s));
-    h->n_chunks = total_chunks;
-    h->npad = total_chunks * POOL_CHUNK;
-    const size_t words = (size_t)(h->npad > 0 ? h->npad : 1);
-    POOL_CUDA(cudaMalloc(&h->cw, 4 * words));
-    POOL_CUDA(cudaMalloc(&h->orig, 4 * words));
-    POOL_CUDA(cudaMemsetAsync(h->cw, 0, 4 * words, s));           // padding scores row 0 of U and of the tile
-    POOL_CUDA(cudaMemsetAsync(h->orig, 0xff, 4 * words, s));      // ... and never competes
-    POOL_CUDA(cudaMalloc(&h->pos_of, 4 * cnt));
-    if (ncand > 0) {
-      pool_scatter_kernel<<<grid, 256, 0, s>>>(keys_out, perm, ncand, ibits, jbits, start,
-                                               h->tile_cstart, h->cw, h->orig, h->pos_of);
-      POOL_CUDA(cudaGetLastError());
-    }
-    POOL_CUDA(cudaStreamSynchronize(s));
-  }
-done:
-#undef POOL_CUDA
-  cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(perm); cudaFree(start);
-  cudaFree(nchunk); cudaFree(tmp);
-  if (rc != AMF_OK) { amf_pool_destroy(h); return rc; }
+  const int rc = runs_build(&h->runs, ncand, ci_d, cj_d, nullptr, 0, n_users, n_items,
+                            tile_rows < n_items ? tile_rows : n_items, true, s);
+  if (rc != AMF_OK) { delete h; return rc; }
   *out = h;
   return AMF_OK;
 }
@@ -406,7 +318,7 @@ __global__ void pool_remove_kernel(const int64_t* __restrict__ idx, int64_t n, i
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = idx[t];
-    if (c >= 0 && c < ncand) orig[pos_of[c]] = amf::POOL_TOMBSTONE;
+    if (c >= 0 && c < ncand) orig[pos_of[c]] = amf::RUNS_NONE;
   }
 }
 
@@ -414,7 +326,8 @@ int amf_pool_remove(amf_pool_t* h, int64_t n, const int64_t* idx_d, void* stream
   AMF_REQUIRE(h && (n == 0 || idx_d), "amf_pool_remove: NULL argument");
   if (n <= 0 || h->ncand == 0) return AMF_OK;
   const int grid = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
-  pool_remove_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx_d, n, h->ncand, h->pos_of, h->orig);
+  pool_remove_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx_d, n, h->ncand, h->runs.pos_of,
+                                                             h->runs.orig);
   AMF_LAUNCH_CHECK();
   return AMF_OK;
 }
@@ -429,39 +342,42 @@ int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const vo
   const size_t es = dtype == AMF_F32 ? 4 : 8;
   const int vecn = dtype == AMF_F32 ? 4 : 2;
   AMF_REQUIRE(ld >= d && ld % vecn == 0, "ld=%d must be >= d=%d and a multiple of %d", ld, d, vecn);
-  AMF_REQUIRE(((uintptr_t)U_d | (uintptr_t)V_d) % ((size_t)ld * es) == 0 || ((size_t)ld * es & ((size_t)ld * es - 1)),
-              "amf_pool_score_pred: U and V must be aligned to the padded row (%d bytes)", (int)(ld * es));
+  AMF_REQUIRE(((uintptr_t)U_d | (uintptr_t)V_d) % 16 == 0,
+              "amf_pool_score_pred: U and V must be 16-byte aligned");
+  const amf_runs* r = &h->runs;
   Best* part = nullptr;
   int rc = acquire_partials(&part, s);
   if (rc != AMF_OK) return rc;
+  struct PartGuard {                       // released on every early return
+    Best* p; cudaStream_t s; bool armed;
+    ~PartGuard() { if (armed) cudaFreeAsync(p, s); }
+  } guard{part, s, true};
   void* tmp_scores = nullptr;
-  if (scores_d && h->npad > 0) {
-    if (h->tmp_bytes < es * (size_t)h->npad) {
+  if (scores_d && r->npos > 0) {
+    if (h->tmp_bytes < es * (size_t)r->npos) {
       cudaFree(h->tmp_scores); h->tmp_scores = nullptr; h->tmp_bytes = 0;
-      AMF_CUDA(cudaMalloc(&h->tmp_scores, es * (size_t)h->npad));
-      h->tmp_bytes = es * (size_t)h->npad;
+      AMF_CUDA(cudaMalloc(&h->tmp_scores, es * (size_t)r->npos));
+      h->tmp_bytes = es * (size_t)r->npos;
     }
     tmp_scores = h->tmp_scores;
   }
-  const size_t smem = (size_t)h->tile_rows * ld * es;
-  AMF_REQUIRE(smem <= 225 * 1024, "item tile (%d rows of %d) does not fit shared memory",
-              h->tile_rows, ld);
   int64_t grid64 = (int64_t)num_sms();
-  if (grid64 > h->n_chunks) grid64 = h->n_chunks > 0 ? h->n_chunks : 1;
+  if (grid64 > r->n_bundles) grid64 = r->n_bundles > 0 ? r->n_bundles : 1;
   const int grid = (int)grid64;
   if (dtype == AMF_F32)
-    rc = maximize ? pool_pred<float, true>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, smem, s)
-                  : pool_pred<float, false>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, smem, s);
+    rc = maximize ? pool_pred<float, true>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s)
+                  : pool_pred<float, false>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s);
   else
-    rc = maximize ? pool_pred<double, true>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, smem, s)
-                  : pool_pred<double, false>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, smem, s);
+    rc = maximize ? pool_pred<double, true>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s)
+                  : pool_pred<double, false>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s);
   if (rc != AMF_OK) return rc;
   if (tmp_scores) {
     const int g2 = num_sms() * 8;
-    if (dtype == AMF_F32) unpermute_kernel<float><<<g2, 256, 0, s>>>((const float*)tmp_scores, h->orig, h->npad, (float*)scores_d);
-    else unpermute_kernel<double><<<g2, 256, 0, s>>>((const double*)tmp_scores, h->orig, h->npad, (double*)scores_d);
+    if (dtype == AMF_F32) unpermute_kernel<float><<<g2, 256, 0, s>>>((const float*)tmp_scores, r->orig, r->npos, (float*)scores_d);
+    else unpermute_kernel<double><<<g2, 256, 0, s>>>((const double*)tmp_scores, r->orig, r->npos, (double*)scores_d);
     AMF_LAUNCH_CHECK();
   }
+  guard.armed = false;                     // launch_best_final frees the partials
   return launch_best_final(part, grid, maximize != 0, best_d, s);
 }
 

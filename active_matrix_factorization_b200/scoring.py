@@ -161,16 +161,18 @@ class Pool:
         ci, cj = _cands(ii, jj)
         assert ci.dtype == torch.int32 and cj.dtype == torch.int32
         self.ncand = int(ci.numel())
-        # the pool kernel wants a row of 1, 2, 4, 8, 16 or 32 16-byte vectors
+        # the pool kernel wants a row of 1, 2, 4, 8 or 16 16-byte vectors
         vec = D.vec_elems(name)
         nvec = (d + vec - 1) // vec
         nvec = 1 << (nvec - 1).bit_length()
-        if nvec > 32:
+        if nvec > 16:
             raise ValueError("latent_d=%d is too large for the bucketed pool" % d)
         self.ld = ld = nvec * vec
         row_bytes = ld * (4 if name == "f32" else 8)
-        # as many item rows as fit the shared-memory budget (the kernel takes any tile height)
-        self.tile_rows = int(max(1, min(32768, tile_bytes // row_bytes)))
+        # as many item rows as the kernel can keep in shared memory next to its staging buffers
+        # (any smaller tile height works: tile_bytes is a knob for tests and benchmarks)
+        most = int(lib.amf_pool_max_tile_rows(row_bytes))
+        self.tile_rows = int(max(1, min(most, tile_bytes // row_bytes)))
         self._h = C.c_void_p()
         torch.cuda.current_stream().synchronize()
         N.check(lib.amf_pool_create(C.byref(self._h), self.ncand, D.ptr(ci), D.ptr(cj),

@@ -1,0 +1,169 @@
+// Micro-benchmark behind the round-2 "one lane per run" kernels (pool.cu / tiled.cu): what does it
+// cost, per 128-byte factor row and per SM, to (a) bring 32 random rows into the registers of 32
+// lanes (one whole row per lane) and (b) add 32 register-held rows into 32 random rows of a
+// table in global memory?  Variants:
+//   fetch: A per-lane LDG.128 x8 (gather)        B coalesced LDG.128 -> STS -> per-lane LDS
+//          C per-lane cp.async.bulk 128 B (TMA) -> mbarrier -> per-lane LDS
+//   flush: D STS -> coalesced LDS -> RED.ADD.v4  E STS -> per-lane cp.reduce.async.bulk 128 B (TMA)
+//          F per-lane RED.ADD.v4 x8
+//   lds:   G the inner loop alone: one random tile row per lane and step (8 LDS.128 + 16 FFMA2)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o micro_visit micro_visit.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e)); exit(1);} } while (0)
+
+constexpr int THREADS = 512, WARPS = THREADS / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// mode: 0 A, 1 B, 2 C, 3 D, 4 E, 5 F, 6 G
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+k(const float* __restrict__ tab, float* __restrict__ out, const uint32_t* __restrict__ rows,
+  int rounds, int n_rows, float* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t stage = smem_u32(smem) + w * 4096;
+  const uint32_t bar = smem_u32(&bars[w]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float4 a[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = make_float4(1.f + lane, 2.f, 3.f + t, 4.f);
+  float acc = 0.f;
+  uint32_t phase = 0;
+  const int gw = blockIdx.x * WARPS + w;
+  for (int r = 0; r < rounds; ++r) {
+    const uint32_t row = rows[((size_t)gw * rounds + r) * 32 + lane];
+    if constexpr (MODE == 0) {
+      const float4* p = reinterpret_cast<const float4*>(tab + (size_t)row * 32);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float4 v = __ldg(p + ((t + lane) & 7)); acc += v.x + v.w; }
+    } else if constexpr (MODE == 1) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t rr = __shfl_sync(0xffffffffu, row, 4 * t + (lane >> 3));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(tab + (size_t)rr * 32) + (lane & 7));
+        sts4(stage + (4 * t + (lane >> 3)) * 128 + (lane & 7) * 16, v);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float4 v = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); acc += v.x + v.w; }
+      __syncwarp();
+    } else if constexpr (MODE == 2) {
+      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4096u) : "memory");
+      __syncwarp();
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(stage + lane * 128), "l"(tab + (size_t)row * 32), "r"(128u), "r"(bar) : "memory");
+      mbar_wait(bar, phase); phase ^= 1;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float4 v = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); acc += v.x + v.w; }
+      __syncwarp();
+    } else if constexpr (MODE == 3) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sts4(stage + lane * 128 + ((t + lane) & 7) * 16, a[t]);
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t rr = __shfl_sync(0xffffffffu, row, 4 * t + (lane >> 3));
+        const float4 v = lds4(stage + (4 * t + (lane >> 3)) * 128 + (lane & 7) * 16);
+        red4(out + (size_t)rr * 32 + (lane & 7) * 4, v);
+      }
+      __syncwarp();
+    } else if constexpr (MODE == 4) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sts4(stage + lane * 128 + ((t + lane) & 7) * 16, a[t]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                   :: "l"(out + (size_t)row * 32), "r"(stage + lane * 128), "r"(128u) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else if constexpr (MODE == 5) {
+      float* p = out + (size_t)row * 32;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) red4(p + ((t + lane) & 7) * 4, a[t]);
+    } else {
+      // inner loop: 16 steps per round, one random tile row (of n_rows resident in smem) per lane
+      uint32_t x = row;
+#pragma unroll 1
+      for (int s = 0; s < 16; ++s) {
+        x = x * 1664525u + 1013904223u;
+        const uint32_t base = smem_u32(smem) + ((x >> 8) % (uint32_t)n_rows) * 128;
+        float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 v = lds4(base + (((t + lane) & 7) << 4));
+          c0.x = fmaf(a[t].x, v.x, c0.x); c0.y = fmaf(a[t].y, v.y, c0.y);
+          c1.x = fmaf(a[t].z, v.z, c1.x); c1.y = fmaf(a[t].w, v.w, c1.y);
+        }
+        acc += c0.x + c0.y + c1.x + c1.y;
+      }
+    }
+  }
+  if constexpr (MODE == 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (acc == 123.456f) *sink = acc;
+}
+
+template <int MODE>
+static void run(const char* name, const float* tab, float* out, const uint32_t* rows, int rounds,
+                int sms, double rows_per_round, int n_rows, size_t smem, float* sink) {
+  CK(cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    CK(cudaEventRecord(e0));
+    k<MODE><<<sms, THREADS, smem>>>(tab, out, rows, rounds, n_rows, sink);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (it && ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  const double n = (double)sms * WARPS * rounds * rows_per_round;
+  printf("%-44s %8.3f ms  %7.2f ns/row/SM  = %6.2f clk/row/SM @1.965GHz\n", name, best,
+         best * 1e6 / (n / sms), best * 1e6 / (n / sms) * 1.965);
+}
+
+int main() {
+  int dev = 0, sms = 0; CK(cudaSetDevice(dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tab = 200000, rounds = 400;
+  float *tab, *out, *sink; uint32_t* rows;
+  CK(cudaMalloc(&tab, (size_t)n_tab * 128)); CK(cudaMalloc(&out, (size_t)n_tab * 128)); CK(cudaMalloc(&sink, 4));
+  CK(cudaMemset(tab, 0, (size_t)n_tab * 128)); CK(cudaMemset(out, 0, (size_t)n_tab * 128));
+  const size_t nr = (size_t)sms * WARPS * rounds * 32;
+  std::vector<uint32_t> h(nr);
+  uint64_t s = 88172645463325252ull;
+  for (size_t t = 0; t < nr; ++t) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; h[t] = (uint32_t)(s % n_tab); }
+  CK(cudaMalloc(&rows, nr * 4)); CK(cudaMemcpy(rows, h.data(), nr * 4, cudaMemcpyHostToDevice));
+  const size_t stage = WARPS * 4096;
+  run<0>("fetch A: per-lane LDG.128 x8", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  run<1>("fetch B: coalesced LDG -> STS -> LDS", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  run<2>("fetch C: per-lane cp.async.bulk 128B -> LDS", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  run<3>("flush D: STS -> LDS -> coalesced RED.v4", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  run<4>("flush E: STS -> per-lane cp.reduce.async.bulk", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  run<5>("flush F: per-lane RED.v4 x8", tab, out, rows, rounds, sms, 32, 0, stage, sink);
+  const int tile_rows = 1664;
+  run<6>("inner G: 8 LDS.128 + 16 FFMA / lane / step", tab, out, rows, rounds, sms, 32 * 16, tile_rows,
+         (size_t)tile_rows * 128, sink);
+  return 0;
+}

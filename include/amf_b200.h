@@ -204,13 +204,18 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
  * NaN value never win; out = {0, -1} if none does.  recs_d and out_d may not alias. */
 int amf_best_reduce(const amf_best_t* recs_d, int n, int maximize, amf_best_t* out_d, void* stream);
 
-/* Candidate pool handle: the pool bucketed once by item tile (tile_rows items),
- * each candidate packed into 4 bytes (i << ceil(log2(tile_rows)) | j % tile_rows; needs
- * bits(n_users) + ceil(log2(tile_rows)) <= 32), sorted by user inside a tile.  The scoring kernel keeps
- * the tile of V resident in shared memory (TMA bulk copies), holds the user row in registers and
- * re-fetches it only when the user changes; built from the caller's (i, j) arrays, remembers the
- * caller's order.  Replaces the `pool` list / `unrated` set iterated in
- * active_pmf.py:725-770 when the same pool is scored repeatedly (every active-learning step). */
+/* Candidate pool handle: the pool bucketed once by item tile (tile_rows items) in the "bundled
+ * runs" layout: the candidates one user has inside one tile are a run, one lane of the scoring
+ * kernel owns a run segment (<= 64 candidates) with the whole user row in registers, and 32
+ * equally long segments form the bundle a warp works on.  A candidate is stored as its 16-bit row
+ * inside the tile (tile_rows <= 65535).  The kernel keeps the tile of V resident in shared memory
+ * (TMA bulk copies) and reads one item row per candidate from there -- one shared-memory wavefront
+ * per candidate at d = 32 fp32; built from the caller's (i, j) arrays, remembers the caller's
+ * order.  Replaces the `pool` list / `unrated` set iterated in active_pmf.py:725-770 when the same
+ * pool is scored repeatedly (every active-learning step).
+ * amf_pool_max_tile_rows: the tallest tile the scoring kernel can hold for padded factor rows of
+ * row_bytes (16, 32, 64, 128 or 256; 0 = width not supported by the pool kernel). */
+int amf_pool_max_tile_rows(int row_bytes);
 typedef struct amf_pool amf_pool_t;
 int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const int32_t* cj_d,
                     int32_t n_users, int32_t n_items, int tile_rows, void* stream);

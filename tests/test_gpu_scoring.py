@@ -63,7 +63,8 @@ def test_pred_large_random(S, dtype, tol):
 @pytest.mark.parametrize("n,m,d,nc,tile_bytes", [(3000, 2000, 32, 300_000, 64 * 1024),
                                                   (500, 777, 10, 50_000, 4096),
                                                   (64, 50, 5, 3000, 64 * 1024),
-                                                  (200, 1500, 48, 20_000, 16 * 1024),
+                                                  (200, 1500, 30, 20_000, 16 * 1024),
+                                                  (20, 300, 7, 5000, 64 * 1024),     # runs longer than a segment
                                                   (300, 9000, 32, 400_000, 64 * 1024),
                                                   (30, 20, 2, 600, 1024)])
 def test_tiled_pool_matches_flat_and_oracle(S, n, m, d, nc, tile_bytes, dtype, tol):
@@ -90,6 +91,11 @@ def test_tiled_pool_matches_flat_and_oracle(S, n, m, d, nc, tile_bytes, dtype, t
     _, best = pool.score_pred(Ut, Vt, want_scores=False, index_base=1000)
     assert S.unpack_best(best)[1] == fi + 1000
     pool.close()
+
+
+def test_tiled_pool_rejects_rows_wider_than_256_bytes(S):
+    with pytest.raises(ValueError):
+        S.Pool(np.array([0]), np.array([0]), 4, 4, "f64", 48)
 
 
 def test_tiled_pool_ties_and_empty(S):

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libamf_b200.so")
+# AMF_B200_LIB: an alternative build of the same library (kernel-variant timing, benchmarks/variant_lib.sh)
+LIB_PATH = os.environ.get("AMF_B200_LIB") or os.path.join(HERE, "csrc", "libamf_b200.so")
 
 F32, F64 = 0, 1
 CRIT_PRED, CRIT_APPROX_MEAN, CRIT_PRED_VARIANCE, CRIT_PROB_GE = 0, 1, 2, 3

@@ -11,6 +11,7 @@
 // The permutation back to the caller's order is kept, so scores and the winner are reported
 // exactly as the unbucketed path would.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "runs.cuh"
@@ -29,10 +30,13 @@ int acquire_partials(Best** out, cudaStream_t s);
 
 constexpr int64_t POOL_BUNDLE_COST = 5;      // row fetch of a bundle, in entry steps (micro_visit.cu)
 
-template <int NVEC> constexpr int pool_threads() { return NVEC >= 16 ? 256 : 512; }
+// threads per CTA (512 / 640 / 768 measured equal at C5: the kernel is bound by the
+// load-store pipe, not by latency; fewer warps leave more shared memory to the tile)
+constexpr int POOL_THREADS_NARROW = 512, POOL_THREADS_WIDE = 256;
+template <int NVEC> constexpr int pool_threads() { return NVEC >= 16 ? POOL_THREADS_WIDE : POOL_THREADS_NARROW; }
 // dynamic shared memory: [per-warp staging][tile rows][one NaN row for the padding index]
-template <int NVEC> constexpr size_t pool_stage_total() {
-  return (size_t)(pool_threads<NVEC>() / 32) * runs_stage_bytes<NVEC>();
+template <int NVEC, int THREADS = pool_threads<NVEC>()> constexpr size_t pool_stage_total() {
+  return (size_t)(THREADS / 32) * runs_stage_bytes<NVEC>();
 }
 constexpr size_t POOL_SMEM_BUDGET = 227 * 1024 - 1024;   // static buffers of the kernel fit the rest
 
@@ -76,8 +80,8 @@ __device__ __forceinline__ void st_scores4(double* p, const double (&v)[4]) {
 // the next bundle is fetched while the current one is scored).  A lane scores one candidate per
 // step with its user row in registers; the fused arg-best compares once per group of four steps
 // and looks up the caller's position only for scores that reach the warp's running best.
-template <typename T, int NVEC, bool MAX>
-__global__ void __launch_bounds__(pool_threads<NVEC>(), 1)
+template <typename T, int NVEC, bool MAX, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ orig,
                  const uint32_t* __restrict__ rowid, const int2* __restrict__ binfo,
                  const int64_t* __restrict__ tile_bstart, int n_tiles, int64_t n_bundles,
@@ -85,13 +89,12 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
                  T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
   using V = typename Vec<T>::type;
   constexpr uint32_t ROW_BYTES = NVEC * 16;
-  constexpr int THREADS = pool_threads<NVEC>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_v;
   __shared__ unsigned int s_ctr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t stage = smem_u32(smem_raw) + warp * runs_stage_bytes<NVEC>();
-  unsigned char* tile_ptr = smem_raw + pool_stage_total<NVEC>();
+  unsigned char* tile_ptr = smem_raw + pool_stage_total<NVEC, THREADS>();
   const uint32_t tile0 = smem_u32(tile_ptr) | runs_lane_rot<NVEC>(lane);
   const unsigned char* Ub = reinterpret_cast<const unsigned char*>(U);
 
@@ -146,23 +149,29 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
     int64_t b = grab();
     int2 info = make_int2(0, 0);
     uint32_t rid = RUNS_NONE;
-    if (b < seg_end) { info = binfo[b]; rid = rowid[b * 32 + lane]; }
+    uint2 w = make_uint2(0u, 0u);
+    if (b < seg_end) {
+      info = binfo[b]; rid = rowid[b * 32 + lane];
+      w = __ldcs(reinterpret_cast<const uint2*>(idx) + (int64_t)info.x * 32 + lane);
+    }
     while (b < seg_end) {
+      // the next bundle: its metadata now, its first group of indices once the metadata is here
       const int64_t nb = grab();
       int2 ninfo = make_int2(0, 0);
       uint32_t nrid = RUNS_NONE;
       if (nb < seg_end) { ninfo = binfo[nb]; nrid = rowid[nb * 32 + lane]; }
+      uint2 w_next = make_uint2(0u, 0u);
 
       AMF_DBG_ASSERT(rid == RUNS_NONE || rid < 0x7fffffffu);
       V a[NVEC];
       fetch_rows<V, NVEC>(Ub, rid, stage, lane, a);
       const int L = info.y, G = (L + 3) >> 2;
       const uint2* ip = reinterpret_cast<const uint2*>(idx) + (int64_t)info.x * 32 + lane;
-      uint2 w = __ldcs(ip);
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
         uint2 wn = w;
         if (g + 1 < G) wn = __ldcs(ip + (g + 1) * 32);
+        else if (nb < seg_end) w_next = __ldcs(reinterpret_cast<const uint2*>(idx) + (int64_t)ninfo.x * 32 + lane);
         const int ns = L - 4 * g;
         const uint32_t j4[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
         T p[4] = {worst, worst, worst, worst};
@@ -208,7 +217,7 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
         }
         w = wn;
       }
-      b = nb; info = ninfo; rid = nrid;
+      b = nb; info = ninfo; rid = nrid; w = w_next;
     }
     c = seg_end;
   }
@@ -227,8 +236,14 @@ __global__ void unpermute_kernel(const T* __restrict__ in, const uint32_t* __res
   }
 }
 
-template <int NVEC> static size_t pool_smem(int tile_rows) {
-  return pool_stage_total<NVEC>() + ((size_t)tile_rows + 1) * NVEC * 16;
+template <int NVEC, int THREADS> static size_t pool_smem(int tile_rows) {
+  return pool_stage_total<NVEC, THREADS>() + ((size_t)tile_rows + 1) * NVEC * 16;
+}
+// AMF_POOL_THREADS = 512 / 640 / 768: tuning knob of benchmarks/pool_variants.py (narrow rows only)
+static int pool_threads_narrow() {
+  const char* e = getenv("AMF_POOL_THREADS");
+  const int t = e ? atoi(e) : POOL_THREADS_NARROW;
+  return (t == 640 || t == 768) ? t : POOL_THREADS_NARROW;
 }
 
 template <typename T, bool MAX>
@@ -237,28 +252,33 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
   constexpr int N = Vec<T>::N;
   const int nvec = ld / N;
   const amf_runs* r = &h->runs;
-#define POOL(NVEC_)                                                                             \
+#define POOL_T(NVEC_, THREADS_)                                                                 \
   do {                                                                                          \
-    const size_t smem = pool_smem<NVEC_>(r->tile_rows);                                         \
+    const size_t smem = pool_smem<NVEC_, THREADS_>(r->tile_rows);                               \
     AMF_REQUIRE(smem <= POOL_SMEM_BUDGET, "item tile (%d rows of %d) does not fit shared "      \
                 "memory: build the pool with amf_pool_max_tile_rows", r->tile_rows, ld);        \
-    AMF_CUDA(cudaFuncSetAttribute(pool_pred_kernel<T, NVEC_, MAX>,                              \
+    AMF_CUDA(cudaFuncSetAttribute(pool_pred_kernel<T, NVEC_, MAX, THREADS_>,                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    pool_pred_kernel<T, NVEC_, MAX><<<grid, pool_threads<NVEC_>(), smem, s>>>(                  \
+    pool_pred_kernel<T, NVEC_, MAX, THREADS_><<<grid, THREADS_, smem, s>>>(                     \
         r->idx, r->orig, r->rowid, r->binfo, r->tile_bstart, r->n_tiles, r->n_bundles,          \
         r->tile_rows, h->n_items, U, V, scores_tmp, index_base, part);                          \
   } while (0)
+#define POOL(NVEC_) POOL_T(NVEC_, POOL_THREADS_NARROW)
+  const int narrow = pool_threads_narrow();
   switch (nvec) {            // the row width is a compile-time constant of the kernel
     case 1: POOL(1); break;
     case 2: POOL(2); break;
     case 4: POOL(4); break;
-    case 8: POOL(8); break;
-    case 16: POOL(16); break;
+    case 8:
+      if (narrow == 768) POOL_T(8, 768); else if (narrow == 640) POOL_T(8, 640); else POOL(8);
+      break;
+    case 16: POOL_T(16, POOL_THREADS_WIDE); break;
     default:
       set_error("bucketed pool needs a padded row of 1, 2, 4, 8 or 16 16-byte vectors (ld=%d)", ld);
       return AMF_ERR_UNSUPPORTED;
   }
 #undef POOL
+#undef POOL_T
   AMF_LAUNCH_CHECK();
   return AMF_OK;
 }
@@ -276,7 +296,7 @@ int amf_pool_max_tile_rows(int row_bytes) {
     case 16: stage = pool_stage_total<1>(); break;
     case 32: stage = pool_stage_total<2>(); break;
     case 64: stage = pool_stage_total<4>(); break;
-    case 128: stage = pool_stage_total<8>(); break;
+    case 128: stage = (size_t)(pool_threads_narrow() / 32) * runs_stage_bytes<8>(); break;
     case 256: stage = pool_stage_total<16>(); break;
     default: return 0;
   }

@@ -131,6 +131,44 @@ __device__ __forceinline__ void flush_rows(unsigned char* __restrict__ table, ui
   }
 }
 
+// Same through the TMA: every lane stores its accumulated row into its staging slot and issues
+// one bulk reduction (cp.reduce.async.bulk .add, UBLKRED) of that row into global memory -- the
+// adds are done by the copy engine / L2, the load-store pipe only sees the eight STS.  The slot
+// is free again once the engine has read it (wait_group.read), which the issuing lanes wait for
+// before the next quarter overwrites the buffer.
+__device__ __forceinline__ void bulk_red_add(float* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_red_add(double* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+template <typename T, typename V, int NVEC>
+__device__ __forceinline__ void flush_rows_tma(unsigned char* __restrict__ table, uint32_t rid,
+                                               uint32_t stage, int lane, const V (&acc)[NVEC]) {
+  constexpr uint32_t ROW_BYTES = NVEC * 16;
+  const uint32_t rot = runs_lane_rot<NVEC>(lane);
+  const uint32_t slot = stage + (lane & 7) * ROW_BYTES;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if ((lane >> 3) == q) {
+#pragma unroll
+      for (int t = 0; t < NVEC; ++t) sts_v((slot | rot) ^ (uint32_t)(t << 4), acc[t]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (rid != RUNS_NONE) {
+        AMF_DBG_WRITE(table + (uint64_t)rid * ROW_BYTES, ROW_BYTES);
+        bulk_red_add(reinterpret_cast<T*>(table + (uint64_t)rid * ROW_BYTES), slot, ROW_BYTES);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+  }
+}
+
 // first bundle whose cost prefix reaches `target`; cost(b) = 4 * first_group(b) + c0 * b
 // (entries streamed + a fixed price per bundle for the row fetch / flush)
 __device__ __forceinline__ int64_t runs_cost(const int2* __restrict__ binfo, int64_t b, int64_t c0) {

@@ -24,8 +24,11 @@ constexpr int64_t TILED_AUTO_MIN_NNZ = 1ll << 20;
 constexpr int64_t TILED_BUNDLE_COST = 10;   // row fetch + flush of a bundle, in entry steps (micro_visit.cu)
 constexpr size_t TILED_SMEM_BUDGET = 227 * 1024 - 1024;
 
+#ifndef AMF_TILED_THREADS
+#define AMF_TILED_THREADS 384                        // measured best of 256 / 384 / 512 (benchmarks/variant_lib.sh)
+#endif
 template <typename T, int NVEC> constexpr int tiled_threads() {
-  return NVEC * 16 * 3 / 4 > 96 ? 256 : 512;         // 3 rows of registers per lane: 96 of 128 at most
+  return NVEC * 12 > 96 ? 256 : AMF_TILED_THREADS;   // three rows of registers per lane (own, accumulator, tile row)
 }
 template <typename T, int NVEC> constexpr size_t tiled_stage_total() {
   return (size_t)(tiled_threads<T, NVEC>() / 32) * runs_stage_bytes<NVEC>();
@@ -84,7 +87,7 @@ __device__ __forceinline__ void ld_vals4(const double* p, double (&out)[4]) {
 // One side of the fused loss + gradient on the bundled-runs list.  Own = the matrix whose rows
 // stream (row + gradient accumulator in registers), Tile = the matrix whose tile sits in shared
 // memory.  Work distribution and tile loading are those of pool_pred_kernel.
-template <typename T, int NVEC, bool GRAD>
+template <typename T, int NVEC, bool GRAD, bool FLUSH_TMA>
 __global__ void __launch_bounds__(tiled_threads<T, NVEC>(), 1)
 tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
                   const uint32_t* __restrict__ rowid, const uint8_t* __restrict__ seglen,
@@ -200,7 +203,10 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
 #pragma unroll
         for (int q = 0; q < 4; ++q) r4[q] = rn[q];
       }
-      if (GRAD) flush_rows<T, V, NVEC>(down_b, rid, stage, lane, acc);
+      if (GRAD) {
+        if (FLUSH_TMA) flush_rows_tma<T, V, NVEC>(down_b, rid, stage, lane, acc);
+        else flush_rows<T, V, NVEC>(down_b, rid, stage, lane, acc);
+      }
       local_sq += (double)sq;
       b = nb; info = ninfo; rid = nrid; mylen = nlen;
     }
@@ -243,15 +249,19 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
   if (max_ctas > 0 && grid64 > max_ctas) grid64 = max_ctas;   // leave SMs to a concurrent collective
   if (grid64 > r->n_bundles) grid64 = r->n_bundles > 0 ? r->n_bundles : 1;
   const int grid = (int)grid64;
+  // AMF_TILED_FLUSH=tma: bulk reductions of the TMA (UBLKRED) instead of vector RED.ADD from the
+  // lanes.  Measured equal at C5 (the engine's read-back wait per quarter costs what the three
+  // load-store wavefronts per row save), so the simpler path is the default.
+  static const bool tma_flush = getenv("AMF_TILED_FLUSH") && !strcmp(getenv("AMF_TILED_FLUSH"), "tma");
   if (GRAD) AMF_DBG_RANGE(0, dOwn, (size_t)(side == 0 ? h->n_users : h->n_items) * nvec * 16, s);
 #define TILED(NVEC_)                                                                              \
   do {                                                                                            \
     const size_t smem = tiled_smem<T, NVEC_>(r->tile_rows);                                       \
     AMF_REQUIRE(smem <= TILED_SMEM_BUDGET, "tiled rating list: tile of %d rows does not fit",     \
                 r->tile_rows);                                                                    \
-    AMF_CUDA(cudaFuncSetAttribute(tiled_side_kernel<T, NVEC_, GRAD>,                              \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    tiled_side_kernel<T, NVEC_, GRAD><<<grid, tiled_threads<T, NVEC_>(), smem, s>>>(              \
+    auto kern = tma_flush ? tiled_side_kernel<T, NVEC_, GRAD, GRAD> : tiled_side_kernel<T, NVEC_, GRAD, false>; \
+    AMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, tiled_threads<T, NVEC_>(), smem, s>>>(                                           \
         r->idx, (const T*)r->val, r->rowid, r->seglen, r->binfo, r->tile_bstart, r->n_tiles,      \
         r->n_bundles, r->tile_rows, tile_side_rows, Own, Tile, inv_sigma, mean_offset, dOwn,      \
         sq_err);                                                                                  \

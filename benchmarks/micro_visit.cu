@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e)); exit(1);} } while (0)
 
@@ -32,7 +33,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
 
-// mode: 0 A, 1 B, 2 C, 3 D, 4 E, 5 F, 6 G
+// mode: 0 A, 1 B, 2 C, 3 D, 4 E, 5 F, 6 G, 7 = B + 9 steps of G + D, 8 = C + 9 steps of G + E
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 k(const float* __restrict__ tab, float* __restrict__ out, const uint32_t* __restrict__ rows,
@@ -55,11 +56,20 @@ k(const float* __restrict__ tab, float* __restrict__ out, const uint32_t* __rest
   const int gw = blockIdx.x * WARPS + w;
   for (int r = 0; r < rounds; ++r) {
     const uint32_t row = rows[((size_t)gw * rounds + r) * 32 + lane];
+    constexpr bool FB = MODE == 1 || MODE == 7, FC = MODE == 2 || MODE == 8;
+    constexpr bool LD = MODE == 3 || MODE == 7, LE = MODE == 4 || MODE == 8;
+    constexpr bool INNER = MODE >= 6;
+    const uint32_t tile0 = smem_u32(smem) + WARPS * 4096;
     if constexpr (MODE == 0) {
       const float4* p = reinterpret_cast<const float4*>(tab + (size_t)row * 32);
 #pragma unroll
       for (int t = 0; t < 8; ++t) { const float4 v = __ldg(p + ((t + lane) & 7)); acc += v.x + v.w; }
-    } else if constexpr (MODE == 1) {
+    }
+    if constexpr (LE) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+      __syncwarp();
+    }
+    if constexpr (FB) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const uint32_t rr = __shfl_sync(0xffffffffu, row, 4 * t + (lane >> 3));
@@ -68,18 +78,40 @@ k(const float* __restrict__ tab, float* __restrict__ out, const uint32_t* __rest
       }
       __syncwarp();
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { const float4 v = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); acc += v.x + v.w; }
+      for (int t = 0; t < 8; ++t) { a[t] = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); }
       __syncwarp();
-    } else if constexpr (MODE == 2) {
+    }
+    if constexpr (FC) {
       if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4096u) : "memory");
       __syncwarp();
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    :: "r"(stage + lane * 128), "l"(tab + (size_t)row * 32), "r"(128u), "r"(bar) : "memory");
       mbar_wait(bar, phase); phase ^= 1;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { const float4 v = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); acc += v.x + v.w; }
+      for (int t = 0; t < 8; ++t) { a[t] = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); }
       __syncwarp();
-    } else if constexpr (MODE == 3) {
+    }
+    if constexpr (INNER) {
+      uint32_t x = row;
+      const int steps = MODE == 6 ? 16 : 9;
+#pragma unroll 1
+      for (int s = 0; s < steps; ++s) {
+        x = x * 1664525u + 1013904223u;
+        const uint32_t base = tile0 + ((x >> 8) % (uint32_t)n_rows) * 128;
+        float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 v = lds4(base + (((t + lane) & 7) << 4));
+          c0.x = fmaf(a[t].x, v.x, c0.x); c0.y = fmaf(a[t].y, v.y, c0.y);
+          c1.x = fmaf(a[t].z, v.z, c1.x); c1.y = fmaf(a[t].w, v.w, c1.y);
+        }
+        acc += c0.x + c0.y + c1.x + c1.y;
+      }
+    } else if constexpr (FB || FC) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc += a[t].x + a[t].w;
+    }
+    if constexpr (LD) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) sts4(stage + lane * 128 + ((t + lane) & 7) * 16, a[t]);
       __syncwarp();
@@ -90,38 +122,67 @@ k(const float* __restrict__ tab, float* __restrict__ out, const uint32_t* __rest
         red4(out + (size_t)rr * 32 + (lane & 7) * 4, v);
       }
       __syncwarp();
-    } else if constexpr (MODE == 4) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
-      __syncwarp();
+    }
+    if constexpr (LE) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) sts4(stage + lane * 128 + ((t + lane) & 7) * 16, a[t]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                    :: "l"(out + (size_t)row * 32), "r"(stage + lane * 128), "r"(128u) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    } else if constexpr (MODE == 5) {
+    }
+    if constexpr (MODE == 5) {
       float* p = out + (size_t)row * 32;
 #pragma unroll
       for (int t = 0; t < 8; ++t) red4(p + ((t + lane) & 7) * 4, a[t]);
-    } else {
-      // inner loop: 16 steps per round, one random tile row (of n_rows resident in smem) per lane
-      uint32_t x = row;
-#pragma unroll 1
-      for (int s = 0; s < 16; ++s) {
-        x = x * 1664525u + 1013904223u;
-        const uint32_t base = smem_u32(smem) + ((x >> 8) % (uint32_t)n_rows) * 128;
-        float2 c0 = make_float2(0.f, 0.f), c1 = c0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 v = lds4(base + (((t + lane) & 7) << 4));
-          c0.x = fmaf(a[t].x, v.x, c0.x); c0.y = fmaf(a[t].y, v.y, c0.y);
-          c1.x = fmaf(a[t].z, v.z, c1.x); c1.y = fmaf(a[t].w, v.w, c1.y);
-        }
-        acc += c0.x + c0.y + c1.x + c1.y;
-      }
     }
   }
-  if constexpr (MODE == 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if constexpr (MODE == 4 || MODE == 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (acc == 123.456f) *sink = acc;
+}
+
+// fetch H: TMA gather4 -- eight ops of four 128-byte rows each per bundle of 32 rows, then LDS.
+// VERIFY: rows are compared with a direct load (err counts mismatching floats).
+__global__ void __launch_bounds__(THREADS, 1)
+kg4(const __grid_constant__ CUtensorMap map, const float* __restrict__ tab, const uint32_t* __restrict__ rows,
+    int rounds, float* sink, unsigned* err, int verify) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t stage = smem_u32(smem) + w * 4096;
+  const uint32_t bar = smem_u32(&bars[w]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float acc = 0.f;
+  uint32_t phase = 0;
+  const int gw = blockIdx.x * WARPS + w;
+  for (int r = 0; r < rounds; ++r) {
+    const uint32_t row = rows[((size_t)gw * rounds + r) * 32 + lane];
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4096u) : "memory");
+    __syncwarp();
+    const int r0 = __shfl_sync(0xffffffffu, row, (lane & 7) * 4 + 0), r1 = __shfl_sync(0xffffffffu, row, (lane & 7) * 4 + 1);
+    const int r2 = __shfl_sync(0xffffffffu, row, (lane & 7) * 4 + 2), r3 = __shfl_sync(0xffffffffu, row, (lane & 7) * 4 + 3);
+    if (lane < 8)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                   :: "r"(stage + lane * 512), "l"(&map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+    mbar_wait(bar, phase); phase ^= 1;
+    float4 a[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { a[t] = lds4(stage + lane * 128 + ((t + lane) & 7) * 16); acc += a[t].x + a[t].w; }
+    if (verify) {
+      unsigned bad = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(tab + (size_t)row * 32) + ((t + lane) & 7));
+        bad += (v.x != a[t].x) + (v.y != a[t].y) + (v.z != a[t].z) + (v.w != a[t].w);
+      }
+      if (bad) atomicAdd(err, bad);
+    }
+    __syncwarp();
+  }
   if (acc == 123.456f) *sink = acc;
 }
 
@@ -149,7 +210,12 @@ int main() {
   const int n_tab = 200000, rounds = 400;
   float *tab, *out, *sink; uint32_t* rows;
   CK(cudaMalloc(&tab, (size_t)n_tab * 128)); CK(cudaMalloc(&out, (size_t)n_tab * 128)); CK(cudaMalloc(&sink, 4));
-  CK(cudaMemset(tab, 0, (size_t)n_tab * 128)); CK(cudaMemset(out, 0, (size_t)n_tab * 128));
+  {
+    std::vector<float> ht((size_t)n_tab * 32);
+    for (size_t t = 0; t < ht.size(); ++t) ht[t] = (float)(t % 100003) * 0.5f;
+    CK(cudaMemcpy(tab, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemset(out, 0, (size_t)n_tab * 128));
   const size_t nr = (size_t)sms * WARPS * rounds * 32;
   std::vector<uint32_t> h(nr);
   uint64_t s = 88172645463325252ull;
@@ -162,8 +228,47 @@ int main() {
   run<3>("flush D: STS -> LDS -> coalesced RED.v4", tab, out, rows, rounds, sms, 32, 0, stage, sink);
   run<4>("flush E: STS -> per-lane cp.reduce.async.bulk", tab, out, rows, rounds, sms, 32, 0, stage, sink);
   run<5>("flush F: per-lane RED.v4 x8", tab, out, rows, rounds, sms, 32, 0, stage, sink);
-  const int tile_rows = 1664;
-  run<6>("inner G: 8 LDS.128 + 16 FFMA / lane / step", tab, out, rows, rounds, sms, 32 * 16, tile_rows,
-         (size_t)tile_rows * 128, sink);
+  const int tile_rows = 1200;
+  const size_t big = stage + (size_t)tile_rows * 128;
+  run<6>("inner G: 8 LDS.128 + 16 FFMA / lane / step", tab, out, rows, rounds, sms, 32 * 16, tile_rows, big, sink);
+  run<7>("visit B + 9 steps + D (per step)", tab, out, rows, rounds, sms, 32 * 9, tile_rows, big, sink);
+  run<8>("visit C + 9 steps + E, TMA (per step)", tab, out, rows, rounds, sms, 32 * 9, tile_rows, big, sink);
+  {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    EncodeTiledFn fn = (EncodeTiledFn)p;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)n_tab};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, tab, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("encode gather4 map: %d\n", (int)cr);
+    if (cr == CUDA_SUCCESS) {
+      unsigned* err; CK(cudaMalloc(&err, 4)); CK(cudaMemset(err, 0, 4));
+      CK(cudaFuncSetAttribute(kg4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+      kg4<<<sms, THREADS, stage>>>(map, tab, rows, 4, sink, err, 1);
+      cudaError_t e = cudaDeviceSynchronize();
+      unsigned herr = 0; if (e == cudaSuccess) CK(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+      printf("gather4 verify: %s, mismatching floats = %u\n", cudaGetErrorString(e), herr);
+      if (e == cudaSuccess) {
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int it = 0; it < 4; ++it) {
+          CK(cudaEventRecord(e0));
+          kg4<<<sms, THREADS, stage>>>(map, tab, rows, rounds, sink, err, 0);
+          CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+          float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (it && ms < best) best = ms;
+        }
+        const double n = (double)WARPS * rounds * 32;
+        printf("%-44s %8.3f ms  %7.2f ns/row/SM  = %6.2f clk/row/SM @1.965GHz\n", "fetch H: TMA gather4 (8 ops / 32 rows) -> LDS", best,
+               best * 1e6 / n, best * 1e6 / n * 1.965);
+      }
+    }
+  }
   return 0;
 }

@@ -8,7 +8,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     import torch
     import bench
     from active_matrix_factorization_b200 import _native as N, device as D
-    a = types.SimpleNamespace(users=200_000, items=50_000, latent_d=32, nnz=50_000_000, ncand=1_000_000, dtype="f32")
+    a = types.SimpleNamespace(users=int(os.environ.get("TV_USERS", 200_000)), items=int(os.environ.get("TV_ITEMS", 50_000)),
+                              latent_d=32, nnz=50_000_000, ncand=1_000_000, dtype="f32")
     torch.cuda.set_device(0)
     p = bench.make_problem(a, 0, torch)
     rat = D.Ratings(a.users, a.items, p["ri"], p["rj"], p["r"], "f32")

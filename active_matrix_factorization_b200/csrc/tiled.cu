@@ -249,10 +249,13 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
   if (max_ctas > 0 && grid64 > max_ctas) grid64 = max_ctas;   // leave SMs to a concurrent collective
   if (grid64 > r->n_bundles) grid64 = r->n_bundles > 0 ? r->n_bundles : 1;
   const int grid = (int)grid64;
-  // AMF_TILED_FLUSH=tma: bulk reductions of the TMA (UBLKRED) instead of vector RED.ADD from the
-  // lanes.  Measured equal at C5 (the engine's read-back wait per quarter costs what the three
-  // load-store wavefronts per row save), so the simpler path is the default.
-  static const bool tma_flush = getenv("AMF_TILED_FLUSH") && !strcmp(getenv("AMF_TILED_FLUSH"), "tma");
+  // How the accumulated rows reach global memory: vector RED.ADD from the lanes, or bulk reductions
+  // of the TMA (UBLKRED).  Measured at C5: equal in fp32 (the engine's read-back wait per quarter
+  // costs what the three load-store wavefronts per row save: 0.95 ms both), 3.03 against 3.51 ms in
+  // fp64, where a RED carries 8 bytes and a bulk reduction a whole 256-byte row.  AMF_TILED_FLUSH=
+  // red / tma overrides.
+  const char* fl = getenv("AMF_TILED_FLUSH");
+  const bool tma_flush = fl ? !strcmp(fl, "tma") : sizeof(T) == 8;
   if (GRAD) AMF_DBG_RANGE(0, dOwn, (size_t)(side == 0 ? h->n_users : h->n_items) * nvec * 16, s);
 #define TILED(NVEC_)                                                                              \
   do {                                                                                            \

@@ -9,10 +9,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     import bench
     from active_matrix_factorization_b200 import _native as N, device as D
     a = types.SimpleNamespace(users=int(os.environ.get("TV_USERS", 200_000)), items=int(os.environ.get("TV_ITEMS", 50_000)),
-                              latent_d=32, nnz=50_000_000, ncand=1_000_000, dtype="f32")
+                              latent_d=32, nnz=50_000_000, ncand=1_000_000, dtype=os.environ.get("TV_DTYPE", "f32"))
     torch.cuda.set_device(0)
     p = bench.make_problem(a, 0, torch)
-    rat = D.Ratings(a.users, a.items, p["ri"], p["rj"], p["r"], "f32")
+    rat = D.Ratings(a.users, a.items, p["ri"], p["rj"], p["r"], a.dtype)
     rat.set_layout(sys.argv[2])
     lib = N.require_device()
     U, V = p["U"], p["V"]
@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sums = torch.zeros(3, dtype=torch.float64, device="cuda")
     params = D.pmf_params(1.0, 10.0, 10.0, 0.0)
     def run():
-        N.check(lib.amf_pmf_loss_grad(rat.handle, N.F32, 32, 32, D.ptr(U), D.ptr(V), C.byref(params),
+        N.check(lib.amf_pmf_loss_grad(rat.handle, D.code(a.dtype), 32, 32, D.ptr(U), D.ptr(V), C.byref(params),
                                       D.ptr(dU), D.ptr(dV), D.ptr(sums), D.stream_ptr()))
     for _ in range(3): run()
     torch.cuda.synchronize()

@@ -65,10 +65,10 @@ def workload_name(a):
 def measured_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
     kernels, from the committed `ncu --set full` capture of this same command
-    (profiles/r02_main_ncu_full_raw.csv, recipe benchmarks/profile_step.sh); {} if the summary file is
+    (profiles/r03_main_ncu_full_raw.csv, recipe benchmarks/profile_step.sh); {} if the summary file is
     missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r03_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return {}
@@ -605,12 +605,12 @@ def run_ours(a):
             "pmf_loss_grad": {"ms": grad_ms / a.steps, "ratings_per_sec_iter": nnz_all / (grad_ms / a.steps * 1e-3), "nnz_total": nnz_all},
             "score_pred": {"ms": score_ms / a.steps, "candidates_per_sec": ncand_all / (score_ms / a.steps * 1e-3), "ncand_total": ncand_all},
         },
-        "roofline": {"kernel": "pool_pred_kernel (V tile in shared memory via TMA, U row in registers)" if a.pool == "tiled" else "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
+        "roofline": {"kernel": "pool_pred_kernel (bundled runs: V tile in shared memory via TMA, one lane per (user, tile) run, whole U row in registers)" if a.pool == "tiled" else "score_pred_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak,
                      "peak_source": peak_kind, "unit": "GB/s", "frac": score_gbs / hbm_peak,
                      "algorithmic_bytes": score_bytes, "kernel_ms": scorek_ms,
                      "traffic": traffic.get("pool_pred_kernel" if a.pool == "tiled" else "score_pred_kernel"),
                      "flat_kernel_ms": score_flat_ms, "pool_build_ms": pool_ms},
-        "roofline_gradient": {"kernel": ("tiled_side_kernel x2" if tiled_grad else "side_pass_kernel x2") + " + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
+        "roofline_gradient": {"kernel": ("tiled_side_kernel x2 (bundled runs: own row + accumulator in registers, other side's tile in shared memory)" if tiled_grad else "side_pass_kernel x2") + " + prior_kernel x2", "bound": "hbm", "achieved": grad_gbs,
                               "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s", "frac": grad_gbs / hbm_peak,
                               "algorithmic_bytes": grad_bytes, "kernel_ms": side_ms,
                               "traffic": traffic.get("tiled_side_kernel_x2" if tiled_grad else "side_pass_kernel_x2")},

@@ -86,12 +86,13 @@ def test_tiled_matches_oracle_and_rows(env, n, m, d, nnz, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 2e-5)])
-def test_tiled_ragged(env, dtype, tol):
-    """users/items with no ratings, one item rated by everyone, one heavy user, duplicate cells,
-    a last tile with a single row"""
+def test_tiled_ragged(env, dtype, tol, monkeypatch):
+    """users/items with no ratings, one item rated by everyone and one heavy user (runs far longer
+    than a 64-entry segment), duplicate cells, a last tile with a single row"""
     N, D, torch = env
     rng = np.random.RandomState(1)
-    n, m, d = 1793, 3585, 32          # 1792-row tiles at 128-byte rows: last tiles hold 1 row
+    monkeypatch.setenv("AMF_TILED_KB", "64")   # 512-row (fp32) / 256-row (fp64) tiles
+    n, m, d = 1537, 3585, 32          # both 1 mod 512: the last tile of either side holds 1 row
     rows = [(i, 7, rng.normal()) for i in range(n)]
     rows += [(3, j, rng.normal()) for j in range(0, m, 3) if j != 7]
     rows += [(n - 1, m - 1, 1.0), (n - 1, m - 1, 2.0), (0, m - 1, -1.0)]

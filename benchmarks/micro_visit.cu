@@ -186,6 +186,91 @@ kg4(const __grid_constant__ CUtensorMap map, const float* __restrict__ tab, cons
   if (acc == 123.456f) *sink = acc;
 }
 
+__device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const float2& c) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<const unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// inner loop variants: VAR 0 = scalar FFMA dot; 1 = FFMA2 dot (pool_pred_kernel's step);
+// 2 = FFMA2 dot + FFMA2 rank-one update (tiled_side_kernel's step); 3 = as 2 with scalar FFMA
+template <int VAR, int TH>
+__global__ void __launch_bounds__(TH, 1)
+kin(const uint32_t* __restrict__ rows, int rounds, int n_rows, float* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 a[8], acc4[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { a[t] = make_float4(1.f + lane, 2.f, 3.f + t, 4.f); acc4[t] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  float acc = 0.f;
+  const int gw = blockIdx.x * (TH / 32) + w;
+  const uint32_t tile0 = smem_u32(smem) | ((lane & 7) << 4);
+  for (int r = 0; r < rounds; ++r) {
+    uint32_t x = rows[((size_t)gw * rounds + r) * 32 + lane];
+#pragma unroll 1
+    for (int s = 0; s < 16; ++s) {
+      x = x * 1664525u + 1013904223u;
+      const uint32_t base = tile0 + ((x >> 8) % (uint32_t)n_rows) * 128;
+      float4 v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = lds4(base ^ (t << 4));
+      float d;
+      if (VAR == 0 || VAR == 3) {
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { c0 = fmaf(a[t].x, v[t].x, c0); c1 = fmaf(a[t].y, v[t].y, c1); c2 = fmaf(a[t].z, v[t].z, c2); c3 = fmaf(a[t].w, v[t].w, c3); }
+        d = (c0 + c1) + (c2 + c3);
+      } else {
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (t & 1) { s2 = fma2(make_float2(a[t].x, a[t].y), make_float2(v[t].x, v[t].y), s2); s3 = fma2(make_float2(a[t].z, a[t].w), make_float2(v[t].z, v[t].w), s3); }
+          else { s0 = fma2(make_float2(a[t].x, a[t].y), make_float2(v[t].x, v[t].y), s0); s1 = fma2(make_float2(a[t].z, a[t].w), make_float2(v[t].z, v[t].w), s1); }
+        }
+        d = ((s0.x + s1.x) + (s2.x + s3.x)) + ((s0.y + s1.y) + (s2.y + s3.y));
+      }
+      if (VAR >= 2) {
+        const float e = 0.5f - d;
+        if (VAR == 2) {
+          const float2 e2 = make_float2(e, e);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float2 lo = fma2(e2, make_float2(v[t].x, v[t].y), make_float2(acc4[t].x, acc4[t].y));
+            const float2 hi = fma2(e2, make_float2(v[t].z, v[t].w), make_float2(acc4[t].z, acc4[t].w));
+            acc4[t] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { acc4[t].x = fmaf(e, v[t].x, acc4[t].x); acc4[t].y = fmaf(e, v[t].y, acc4[t].y); acc4[t].z = fmaf(e, v[t].z, acc4[t].z); acc4[t].w = fmaf(e, v[t].w, acc4[t].w); }
+        }
+      }
+      acc += d;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc += acc4[t].x + acc4[t].y + acc4[t].z + acc4[t].w;
+  if (acc == 123.456f) *sink = acc;
+}
+template <int VAR, int TH>
+static void run_in(const char* name, const uint32_t* rows, int rounds, int sms, int n_rows, float* sink) {
+  const size_t smem = (size_t)n_rows * 128;
+  CK(cudaFuncSetAttribute(kin<VAR, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  const int rr = rounds * 16 / (TH / 32);     // same number of row reads per SM for every TH
+  for (int it = 0; it < 4; ++it) {
+    CK(cudaEventRecord(e0));
+    kin<VAR, TH><<<sms, TH, smem>>>(rows, rr, n_rows, sink);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (it && ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  const double n = (double)(TH / 32) * rr * 32 * 16;
+  printf("%-52s %8.3f ms  = %6.2f clk/row/SM @1.965GHz\n", name, best, best * 1e6 / n * 1.965);
+}
+
 template <int MODE>
 static void run(const char* name, const float* tab, float* out, const uint32_t* rows, int rounds,
                 int sms, double rows_per_round, int n_rows, size_t smem, float* sink) {
@@ -233,6 +318,12 @@ int main() {
   run<6>("inner G: 8 LDS.128 + 16 FFMA / lane / step", tab, out, rows, rounds, sms, 32 * 16, tile_rows, big, sink);
   run<7>("visit B + 9 steps + D (per step)", tab, out, rows, rounds, sms, 32 * 9, tile_rows, big, sink);
   run<8>("visit C + 9 steps + E, TMA (per step)", tab, out, rows, rounds, sms, 32 * 9, tile_rows, big, sink);
+  run_in<0, 512>("inner: scalar FFMA dot, 512 thr", rows, rounds, sms, 1600, sink);
+  run_in<1, 512>("inner: FFMA2 dot (pool step), 512 thr", rows, rounds, sms, 1600, sink);
+  run_in<2, 512>("inner: FFMA2 dot + FFMA2 update (gradient step), 512 thr", rows, rounds, sms, 1600, sink);
+  run_in<3, 512>("inner: FFMA dot + FFMA update, 512 thr", rows, rounds, sms, 1600, sink);
+  run_in<2, 384>("inner: FFMA2 dot + FFMA2 update, 384 thr", rows, rounds, sms, 1600, sink);
+  run_in<1, 1024>("inner: FFMA2 dot, 1024 thr", rows, rounds, sms, 1600, sink);
   {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -281,10 +281,17 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
     rng_mode = 'host'
     device_seed = 0
 
-    def samples_device(self, num_gibbs=2, fit_first=False, seed=None):
+    # where the d x d Normal-Wishart draws of the fast-mode chain are made: 'device'
+    # (amf_gibbs_hyper_device: nothing of a sample touches the host) or 'host' (numpy, global stream)
+    hyper_mode = 'device'
+
+    def samples_device(self, num_gibbs=2, fit_first=False, seed=None, hyper=None):
         '''Fast-mode chain (bayes_pmf.py:227-302 in law): yields (user_sample, item_sample) as
         DEVICE tensors of the compute dtype; the criteria (`predict`, `pred_variance`, ...) take
-        them as they are.  Only the d x d hyper-parameter draws touch the host.'''
+        them as they are.  With hyper='device' (default, d <= 32) the whole sample -- moments of
+        the factor matrices, Normal-Wishart draws, half-sweeps -- is stream-ordered device work
+        and the host only enqueues; hyper='host' makes the d x d draws in numpy (one device->host
+        read and one host->device copy per sample).'''
         lib = N.require_device()
         name = self.dtype_name
         dt = D.np_dtype(name)
@@ -293,6 +300,11 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         if fit_first:
             self.do_fit()
         seed = int(self.device_seed if seed is None else seed)
+        hyper = self.hyper_mode if hyper is None else hyper
+        if hyper not in ('device', 'host'):
+            raise ValueError("hyper must be 'device' or 'host'")
+        if d > 32 or min(n, m) < 2:
+            hyper = 'host'
         users_t = D.to_device(self.users, dt)
         items_t = D.to_device(self.items, dt)
         tdt = D.torch_dtype(name)
@@ -300,6 +312,12 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
         sample_no = 0
         dd = d * d
         hyper_h = torch.empty(2 * (d + dd), dtype=tdt).pin_memory()
+        priors = []
+        if hyper == 'device':
+            for wi, b0, df, mu0 in (self.u_hyperparams, self.v_hyperparams):
+                pr = np.concatenate((np.linalg.inv(np.atleast_2d(wi)).reshape(-1),
+                                     np.atleast_1d(mu0).astype(float).reshape(-1), [float(b0), float(df)]))
+                priors.append(D.to_device(pr, np.float64))
 
         scratch = [torch.empty((n, d), dtype=tdt, device=users_t.device),
                    torch.empty((m, d), dtype=tdt, device=users_t.device)]
@@ -323,19 +341,29 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
             return mean, (c.T @ c) / (t.shape[0] - 1)
 
         while True:
-            # ONE device->host read per sample: means and covariances of both factor matrices
-            mu_m, mu_c = moments(users_t)
-            mv_m, mv_c = moments(items_t)
-            mom = torch.cat((mu_m, mu_c.reshape(-1), mv_m, mv_c.reshape(-1))).cpu().numpy()
-            sc_u = mom[d:d + dd].reshape(d, d) if d > 1 else np.array(float(mom[d]))
-            sc_v = mom[2 * d + dd:].reshape(d, d) if d > 1 else np.array(float(mom[2 * d + dd]))
-            mu_u, alpha_u = self._hyperparam_from_moments(n, mom[:d], sc_u, True)
-            mu_v, alpha_v = self._hyperparam_from_moments(m, mom[d + dd:2 * d + dd], sc_v, False)
-            # ... and ONE host->device copy of both sides' (mu, alpha)
-            hyper_h.copy_(torch.from_numpy(np.concatenate(
-                (np.atleast_1d(mu_u), np.atleast_2d(alpha_u).reshape(-1),
-                 np.atleast_1d(mu_v), np.atleast_2d(alpha_v).reshape(-1))).astype(dt)))
-            hyper_t = hyper_h.to(users_t.device, non_blocking=True)
+            if hyper == 'device':
+                hyper_t = torch.empty(2 * (d + dd), dtype=tdt, device=users_t.device)
+                for side, feats in ((0, users_t), (1, items_t)):
+                    o = side * (d + dd)
+                    N.check(lib.amf_gibbs_hyper_device(
+                        rat.handle, D.code(name), d, int(feats.shape[0]), D.ptr(feats),
+                        D.ptr(priors[side]), seed, (1 << 40) + stream_id, D.ptr(hyper_t[o:o + d]),
+                        D.ptr(hyper_t[o + d:o + d + dd]), D.stream_ptr()))
+                    stream_id += 1
+            else:
+                # ONE device->host read per sample: means and covariances of both factor matrices
+                mu_m, mu_c = moments(users_t)
+                mv_m, mv_c = moments(items_t)
+                mom = torch.cat((mu_m, mu_c.reshape(-1), mv_m, mv_c.reshape(-1))).cpu().numpy()
+                sc_u = mom[d:d + dd].reshape(d, d) if d > 1 else np.array(float(mom[d]))
+                sc_v = mom[2 * d + dd:].reshape(d, d) if d > 1 else np.array(float(mom[2 * d + dd]))
+                mu_u, alpha_u = self._hyperparam_from_moments(n, mom[:d], sc_u, True)
+                mu_v, alpha_v = self._hyperparam_from_moments(m, mom[d + dd:2 * d + dd], sc_v, False)
+                # ... and ONE host->device copy of both sides' (mu, alpha)
+                hyper_h.copy_(torch.from_numpy(np.concatenate(
+                    (np.atleast_1d(mu_u), np.atleast_2d(alpha_u).reshape(-1),
+                     np.atleast_1d(mu_v), np.atleast_2d(alpha_v).reshape(-1))).astype(dt)))
+                hyper_t = hyper_h.to(users_t.device, non_blocking=True)
             for r in range(num_gibbs):
                 users_t = half(0, items_t, hyper_t, n, r == num_gibbs - 1)
                 items_t = half(1, users_t, hyper_t, m, r == num_gibbs - 1)

@@ -579,14 +579,25 @@ int amf_pmf_loss_grad_host(const amf_ratings_t* hc, int dtype, int d, const void
   int rc;
   if ((rc = ensure_stage(h, 0, bu)) || (rc = ensure_stage(h, 1, bv))) return rc;
   if (dU_h && ((rc = ensure_stage(h, 2, bu)) || (rc = ensure_stage(h, 3, bv)))) return rc;
-  // two streams: dU goes back to the host while the second pass is still producing dV
+  // two streams: dU goes back to the host while the second pass is still producing dV.  They are
+  // cached per host thread and belong to ONE device: a thread that moves to another GPU gets new
+  // ones, and the handle must live on the current device.  Work the caller enqueued on its own
+  // streams for this handle (amf_ratings_append, ...) must be synchronised before this call.
   static thread_local cudaStream_t s = nullptr, s_copy = nullptr;
   static thread_local cudaEvent_t ev_dU = nullptr, ev_copied = nullptr;
-  if (!s) {
+  static thread_local int cached_dev = -1;
+  int dev = -1;
+  AMF_CUDA(cudaGetDevice(&dev));
+  AMF_REQUIRE(dev == h->device, "amf_pmf_loss_grad_host: the rating list lives on device %d, the "
+              "current device is %d", h->device, dev);
+  if (cached_dev != dev) {
+    if (s) { cudaStreamDestroy(s); cudaStreamDestroy(s_copy); cudaEventDestroy(ev_dU); cudaEventDestroy(ev_copied); }
+    s = s_copy = nullptr; ev_dU = ev_copied = nullptr;
     AMF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     AMF_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     AMF_CUDA(cudaEventCreateWithFlags(&ev_dU, cudaEventDisableTiming));
     AMF_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
+    cached_dev = dev;
   }
   if (ld != d) {
     AMF_CUDA(cudaMemsetAsync(h->stage[0], 0, bu, s));

@@ -106,6 +106,10 @@ static int build_side(amf_ratings* h, int side, const int32_t* key_d, const int3
   uint32_t *perm_in = nullptr, *perm_out = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
+  struct Temps {                            // released on every exit path (AMF_CUDA returns early)
+    int32_t*& a; uint32_t*& b; uint32_t*& c; void*& d;
+    ~Temps() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); }
+  } temps{keys_sorted, perm_in, perm_out, tmp};
   AMF_CUDA(cudaMalloc(&keys_sorted, sizeof(int32_t) * nnz));
   AMF_CUDA(cudaMalloc(&perm_in, sizeof(uint32_t) * nnz));
   AMF_CUDA(cudaMalloc(&perm_out, sizeof(uint32_t) * nnz));
@@ -125,7 +129,6 @@ static int build_side(amf_ratings* h, int side, const int32_t* key_d, const int3
   sub_row_kernel<<<grid, 256, 0, s>>>(h->ptr[side], rows, h->n_sub, h->sub_row[side]);
   AMF_LAUNCH_CHECK();
   AMF_CUDA(cudaStreamSynchronize(s));
-  cudaFree(keys_sorted); cudaFree(perm_in); cudaFree(perm_out); cudaFree(tmp);
   return AMF_OK;
 }
 
@@ -163,11 +166,17 @@ int ratings_compact(amf_ratings* h, cudaStream_t s) {
   AMF_CUDA(cudaMemcpyAsync(j_d + n0, h->tail_j, 4 * (size_t)n1, cudaMemcpyDeviceToDevice, s));
   AMF_CUDA(cudaMemcpyAsync((char*)r_d + es * n0, h->tail_r, es * (size_t)n1, cudaMemcpyDeviceToDevice, s));
   AMF_CUDA(cudaStreamSynchronize(s));
-  free_sides(h);
-  tiled_free(h);
+  // the merged lists are built beside the old ones and swapped in only on success: a failed
+  // build (out of memory) leaves the handle as it was, tail included
+  struct Sides { int64_t* ptr[2]; int32_t* idx[2]; void* val[2]; int32_t* sub_row[2]; } old_sides;
+  for (int t = 0; t < 2; ++t) {
+    old_sides.ptr[t] = h->ptr[t]; old_sides.idx[t] = h->idx[t];
+    old_sides.val[t] = h->val[t]; old_sides.sub_row[t] = h->sub_row[t];
+    h->ptr[t] = nullptr; h->idx[t] = nullptr; h->val[t] = nullptr; h->sub_row[t] = nullptr;
+  }
+  const int64_t old_nnz = h->nnz, old_sub = h->n_sub;
   h->nnz = total;
   h->n_sub = (total + AMF_SUB - 1) / AMF_SUB;
-  h->tail_n = 0;
   int rc;
   if (h->dtype == AMF_F32) {
     rc = build_side<float>(h, 0, i_d, j_d, (const float*)r_d, s);
@@ -177,7 +186,22 @@ int ratings_compact(amf_ratings* h, cudaStream_t s) {
     if (rc == AMF_OK) rc = build_side<double>(h, 1, j_d, i_d, (const double*)r_d, s);
   }
   cudaFree(i_d); cudaFree(j_d); cudaFree(r_d);
-  return rc;
+  if (rc != AMF_OK) {
+    free_sides(h);                          // whatever the failed build allocated
+    for (int t = 0; t < 2; ++t) {
+      h->ptr[t] = old_sides.ptr[t]; h->idx[t] = old_sides.idx[t];
+      h->val[t] = old_sides.val[t]; h->sub_row[t] = old_sides.sub_row[t];
+    }
+    h->nnz = old_nnz; h->n_sub = old_sub;
+    return rc;
+  }
+  for (int t = 0; t < 2; ++t) {
+    cudaFree(old_sides.ptr[t]); cudaFree(old_sides.idx[t]);
+    cudaFree(old_sides.val[t]); cudaFree(old_sides.sub_row[t]);
+  }
+  tiled_free(h);                            // the tiled copies are rebuilt on their next use
+  h->tail_n = 0;
+  return AMF_OK;
 }
 
 }  // namespace amf

@@ -284,6 +284,17 @@ int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype,
                                     double beta, double mean_offset, uint64_t seed,
                                     uint64_t stream_id, void* out_d, int32_t row_begin,
                                     int32_t row_end, void* stream);
+/* Fast mode of sample_hyperparam (bayes_pmf.py:158-186 with sample_wishart :41-59) on the device:
+ * mean and covariance of the factor rows feats_d (rows, d; tightly packed), the Normal-Wishart
+ * posterior and one draw of it -- mu_out_d (d) and alpha_out_d (d, d) in the compute type, ready
+ * for amf_gibbs_half_sweep_device_rng -- without a host round trip.  prior_d: device doubles
+ * [inv(W0) (d*d, row-major) | mu0 (d) | beta0 | dof0].  Same distributions as the reference's host
+ * code (including the scalar np.dot of bayes_pmf.py:176), Philox counters keyed by (seed,
+ * stream_id): use a stream_id no half-sweep of the chain uses.  A scale matrix that is not positive
+ * definite raises the handle's sticky failure flag (amf_gibbs_status).  d <= 32, rows >= 2. */
+int amf_gibbs_hyper_device(const amf_ratings_t* h, int dtype, int d, int64_t rows,
+                           const void* feats_d, const double* prior_d, uint64_t seed,
+                           uint64_t stream_id, void* mu_out_d, void* alpha_out_d, void* stream);
 /* `count` chains over the SAME rating list in one launch, chain p with one extra rating
  * (ex_row_d[p] = its row on the side being sampled, ex_col_d[p] = the row of `other` it pairs
  * with, ex_val_d[p] = its value; all NULL: none) -- the per-candidate, per-value models of the

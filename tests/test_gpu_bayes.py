@@ -305,6 +305,63 @@ def test_fast_chain_matches_host_chain_in_law(Bm, golden):
     assert isinstance(us, np.ndarray) and us.shape == (15, 3) and vs.shape == (12, 3)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("rows,d", [(400, 6), (37, 3), (5000, 15)])
+def test_device_hyperparameter_draws_follow_the_normal_wishart_posterior(Bm, dtype, rows, d):
+    """amf_gibbs_hyper_device against the posterior of bayes_pmf.py:158-186 in law: with W = inv(M),
+    nu = dof0 + n,  E[alpha] = nu W,  Var[alpha_kl] = nu (W_kl^2 + W_kk W_ll),  E[mu] = mu*,
+    Cov[mu] = inv(W) / ((b0 + n)(nu - d - 1)) -- each checked within Monte-Carlo error; one draw with
+    hyper='host' stream-for-stream is not expected to be equal."""
+    import ctypes as C
+    import torch
+    from active_matrix_factorization_b200 import _native as N, device as D
+    lib = N.require_device()
+    rng = np.random.RandomState(rows + d)
+    A = rng.normal(size=(d, d)) / np.sqrt(d)
+    feats = rng.normal(size=(rows, d)) @ (np.eye(d) + A) + rng.normal(size=d)
+    wi = np.eye(d) + 0.3 * (A @ A.T)
+    b0, df, mu0 = 2.0, float(d) + 0.7, rng.normal(size=d) * 0.3     # fractional dof: truncated
+    rat = D.Ratings(rows, 4, np.array([0], np.int32), np.array([0], np.int32), np.array([1.0]), dtype)
+    x = D.to_device(feats, D.np_dtype(dtype))
+    prior = D.to_device(np.concatenate((np.linalg.inv(wi).reshape(-1), mu0, [b0, df])), np.float64)
+    K = 4000
+    out = torch.empty((K, d + d * d), dtype=D.torch_dtype(dtype), device=x.device)
+    for k in range(K):
+        N.check(lib.amf_gibbs_hyper_device(rat.handle, D.code(dtype), d, rows, D.ptr(x), D.ptr(prior), 77, 1000 + k,
+                                           D.ptr(out[k, :d]), D.ptr(out[k, d:]), D.stream_ptr()))
+    failed = C.c_int(0)
+    N.check(lib.amf_gibbs_status(rat.handle, C.byref(failed), D.stream_ptr()))
+    assert failed.value == 0
+    o = out.double().cpu().numpy()
+    mus, alphas = o[:, :d], o[:, d:].reshape(K, d, d)
+    xs = feats.astype(D.np_dtype(dtype)).astype(float)
+    x_bar, s_bar, n = xs.mean(0), np.cov(xs, rowvar=0), rows
+    diff = mu0 - x_bar
+    W = np.linalg.inv(np.linalg.inv(wi) + n * s_bar + (b0 * n) / (b0 + n) * np.dot(diff, diff.T))
+    nu = int(df + n)
+    np.testing.assert_allclose(alphas, alphas.transpose(0, 2, 1), rtol=1e-5, atol=1e-7 * np.abs(alphas).max())
+    se = np.sqrt(nu * (W ** 2 + np.outer(np.diag(W), np.diag(W))) / K)
+    assert (np.abs(alphas.mean(0) - nu * W) < 5 * se).all()
+    assert np.abs(alphas.var(0) / (nu * (W ** 2 + np.outer(np.diag(W), np.diag(W)))) - 1).max() < 0.2
+    mu_star = (b0 * mu0 + n * x_bar) / (b0 + n)
+    cov_mu = np.linalg.inv(W) / ((b0 + n) * (nu - d - 1))
+    assert (np.abs(mus.mean(0) - mu_star) < 5 * np.sqrt(np.diag(cov_mu) / K)).all()
+    assert np.abs(np.diag(np.cov(mus, rowvar=0)) / np.diag(cov_mu) - 1).max() < 0.2
+    # all eigenvalues of every draw are positive
+    assert np.linalg.eigvalsh(alphas).min() > 0
+
+
+def test_fast_chain_with_host_hyperparameters_still_available(Bm, golden):
+    g = golden("gibbs_15x12_d3")
+    b = Bm.BayesianPMF(g["ratings"], 3, subtract_mean=True)
+    b.users, b.items = g["users"].copy(), g["items"].copy()
+    np.random.seed(3)
+    us, vs = next(b.samples_device(num_gibbs=1, hyper='host'))
+    assert us.shape == (15, 3) and vs.shape == (12, 3) and bool(us.isfinite().all())
+    with pytest.raises(ValueError):
+        next(b.samples_device(hyper='nowhere'))
+
+
 # ---- batched lookahead chains (fast mode) ------------------------------------------------------
 @pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 2e-4)])
 def test_batched_half_sweep_is_each_chains_own_conditional(dtype, tol):

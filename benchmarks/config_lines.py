@@ -244,6 +244,14 @@ def c4_bayes(hbm_peak):
         fs = time.perf_counter() - t0
         out["gibbs_200_samples_device_rng_s"] = fs
         out["row_conditionals_per_s_device_rng"] = S_ * 2 * (n + m) / fs
+        out["rng_device"] = "Philox in the kernels; Normal-Wishart hyper-parameters drawn on the device (amf_gibbs_hyper_device): no host round trip per sample"
+        del fast
+        list(islice(b.samples_device(num_gibbs=2, hyper='host'), 3))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fast = list(islice(b.samples_device(num_gibbs=2, hyper='host'), S_))
+        torch.cuda.synchronize()
+        out["gibbs_200_samples_device_rng_host_hyper_s"] = time.perf_counter() - t0
         del fast
     lib = N.require_device()
     for name, es in (("f64", 8), ("f32", 4)):

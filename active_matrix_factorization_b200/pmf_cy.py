@@ -607,33 +607,47 @@ class ProbabilisticMatrixFactorization(object):
             pass
 
     def predicted_matrix(self, u=None, v=None):
-        """Dense U V' (+ mean) (pmf_cy.pyx:410-420): a plain GEMM, done by cuBLAS in fp64."""
+        """Dense U V' (+ mean) (pmf_cy.pyx:410-420), fp64: dense_pred_kernel (csrc/dense.cu)."""
         u = self.users if u is None else u
         v = self.items if v is None else v
-        dev = D.device()
-        pred = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(dev) @ \
-            torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev).T
-        if self.subtract_mean:
-            pred += self.mean_rating
-        return pred.cpu().numpy()
+        lib = N.require_device()
+        ut, vt = D.to_device(u, np.float64), D.to_device(v, np.float64)
+        n, d = ut.shape
+        m = vt.shape[0]
+        out = torch.empty((n, m), dtype=torch.float64, device=ut.device)
+        N.check(lib.amf_predicted_matrix(N.F64, n, m, d, d, D.ptr(ut), D.ptr(vt),
+                                         float(self.mean_rating) if self.subtract_mean else 0.0,
+                                         D.ptr(out), D.stream_ptr()))
+        return out.cpu().numpy()
 
     def rmse(self, real, on=None):
-        """(pmf_cy.pyx:422-426) -- prediction, difference and mean on the device; C float result"""
-        dev = D.device()
-        u = torch.from_numpy(np.ascontiguousarray(self.users, dtype=np.float64)).to(dev)
-        v = torch.from_numpy(np.ascontiguousarray(self.items, dtype=np.float64)).to(dev)
-        pred = u @ v.T
-        if self.subtract_mean:
-            pred += self.mean_rating
-        diff = torch.from_numpy(np.ascontiguousarray(real, dtype=np.float64)).to(dev) - pred
+        """(pmf_cy.pyx:422-426): squared error summed over the selected cells by one fused kernel
+        (no N x M prediction matrix); C float result"""
+        lib = N.require_device()
+        real = np.ascontiguousarray(real, dtype=np.float64)
+        n, m = self.num_users, self.num_items
+        mask = None
         if on is not None:
-            on_arr = np.asarray(on)
-            if on_arr.dtype == bool and on_arr.shape == diff.shape:
-                diff = diff[torch.from_numpy(on_arr).to(dev)]
+            on_arr = np.asarray(on) if not isinstance(on, tuple) else None
+            if on_arr is not None and on_arr.dtype == bool and on_arr.shape == real.shape:
+                mask = on_arr
             else:
-                diff = diff[tuple(torch.as_tensor(np.asarray(x)).to(dev) for x in on)] \
-                    if isinstance(on, tuple) else diff[torch.as_tensor(on_arr).to(dev)]
-        return float(np.float32(torch.sqrt(torch.mean(diff * diff)).item()))
+                # index arrays may name a cell more than once: count cells the way real[on] does
+                picked = np.zeros(real.shape, dtype=np.int64)
+                np.add.at(picked, on, 1)
+                if picked.max(initial=0) > 1:
+                    pred = self.predicted_matrix()
+                    return float(np.float32(np.sqrt(np.mean((real[on] - pred[on]) ** 2))))
+                mask = picked.astype(bool)
+        ut, vt = D.to_device(self.users, np.float64), D.to_device(self.items, np.float64)
+        real_t = D.to_device(real, np.float64)
+        mask_t = D.to_device(mask.astype(np.uint8), np.uint8) if mask is not None else None
+        sums = torch.empty(2, dtype=torch.float64, device=ut.device)
+        N.check(lib.amf_sq_error_dense(N.F64, n, m, self.latent_d, self.latent_d, D.ptr(ut), D.ptr(vt),
+                                       float(self.mean_rating) if self.subtract_mean else 0.0,
+                                       D.ptr(real_t), D.ptr(mask_t), D.ptr(sums), D.stream_ptr()))
+        sq, cnt = sums.cpu().numpy()
+        return float(np.float32(np.sqrt(sq / cnt)))
 
     def print_latent_vectors(self):
         print("Users:")

@@ -204,6 +204,16 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
  * NaN value never win; out = {0, -1} if none does.  recs_d and out_d may not alias. */
 int amf_best_reduce(const amf_best_t* recs_d, int n, int maximize, amf_best_t* out_d, void* stream);
 
+/* predicted_matrix (pmf_cy.pyx:410-420): out_d (n, m) row-major = U V' + offset, in the compute type. */
+int amf_predicted_matrix(int dtype, int32_t n, int32_t m, int d, int ld, const void* U_d,
+                         const void* V_d, double offset, void* out_d, void* stream);
+/* The sums behind rmse / rmse_on (pmf_cy.pyx:25-29, 422-426) without the N x M matrix:
+ * sums_d[0] = sum over the selected cells of (real_d[i*m+j] - U_i.V_j - offset)^2, sums_d[1] = their
+ * number; mask_d (n*m bytes, nonzero = selected) may be NULL for all cells; real_d is fp64. */
+int amf_sq_error_dense(int dtype, int32_t n, int32_t m, int d, int ld, const void* U_d,
+                       const void* V_d, double offset, const double* real_d,
+                       const unsigned char* mask_d, double* sums_d, void* stream);
+
 /* Candidate pool handle: the pool bucketed once by item tile (tile_rows items) in the "bundled
  * runs" layout: the candidates one user has inside one tile are a run, one lane of the scoring
  * kernel owns a run segment (<= 64 candidates) with the whole user row in registers, and 32

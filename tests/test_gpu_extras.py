@@ -82,6 +82,27 @@ def test_minibatch_validation_and_dense_outputs(amf, g, sm):
     assert np.isfinite(r.users).all() and not np.allclose(r.users, g["users0"] * .3)
 
 
+def test_rmse_selection_forms_match_numpy_indexing(amf):
+    """rmse(real, on) for every form of `on` the reference's real[on] accepts (pmf_cy.pyx:28-29,
+    422-426): boolean mask, row indices, (rows, cols) index arrays -- also with a repeated cell,
+    which real[on] counts twice -- on a matrix that is not a multiple of the kernel's 64 x 64 tile"""
+    rng = np.random.RandomState(5)
+    n, m, d = 70, 131, 5
+    R = np.column_stack((rng.randint(0, n, 300), rng.randint(0, m, 300), rng.normal(3, 1, 300)))
+    R[0, 0], R[1, 1] = n - 1, m - 1
+    p = amf.ProbabilisticMatrixFactorization(R, d, subtract_mean=True)
+    real = rng.normal(3, 1, (n, m))
+    pred = p.users @ p.items.T + p.mean_rating
+    np.testing.assert_allclose(p.predicted_matrix(), pred, rtol=1e-12, atol=1e-13)
+    mask = rng.rand(n, m) < .3
+    rows = np.array([3, 69, 0])
+    cells = (rng.randint(0, n, 50), rng.randint(0, m, 50))
+    twice = (np.array([1, 1, 2]), np.array([5, 5, 130]))
+    for on in (None, mask, rows, cells, twice):
+        want = np.sqrt(np.mean((real - pred) ** 2)) if on is None else np.sqrt(np.mean((real[on] - pred[on]) ** 2))
+        assert p.rmse(real, on) == pytest.approx(float(np.float32(want)), rel=1e-6)
+
+
 def test_bayes_rmse(amf, g):
     from active_matrix_factorization_b200 import bayes_pmf
     b = bayes_pmf.BayesianPMF(g["ratings"].copy(), 4)

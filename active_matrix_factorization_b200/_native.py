@@ -105,6 +105,8 @@ PROTOTYPES = {
     "amf_ratings_append": [_P, _I64, _P, _P, _P, _P],
     "amf_ratings_compact": [_P, _P],
     "amf_best_reduce": [_P, _INT, _INT, _P, _P],
+    "amf_pred_covs": [_I32, _I32, _INT, _INT, _P, _P, _P, _P],
+    "amf_slogdet_batched": [_INT, _INT, _P, _P, _P, _P],
     "amf_predicted_matrix": [_INT, _I32, _I32, _INT, _INT, _P, _P, _F64, _P, _P],
     "amf_sq_error_dense": [_INT, _I32, _I32, _INT, _INT, _P, _P, _F64, _P, _P, _P, _P],
     "amf_pool_max_tile_rows": [_INT],

@@ -430,12 +430,7 @@ class ActivePMF(ProbabilisticMatrixFactorization):
     def _pred_entropy_bound(self):
         '''(active_pmf.py:559-574)'''
         s, logdet = _slogdet(self.approx_pred_covs())
-        if s != 1:
-            if s == -1 and logdet < -50:
-                return -1000
-            m = "prediction cov has det with sign {}, log {}"
-            raise ValueError(m.format(s, logdet))
-        return logdet
+        return _entropy_bound_from(s, logdet)
 
     @_criterion("E[Pred Entropy Bound] (MAP)", True, True, min)
     def exp_pred_entropy_bound(self, ij):
@@ -521,6 +516,13 @@ class ActivePMF(ProbabilisticMatrixFactorization):
                 out[s:e] = res['entropy']
             elif what == 'total_variance':
                 out[s:e] = res['total_variance']
+            elif what == 'pred_entropy_bound':
+                # all re-fits of the chunk at once, where they are: Isserlis covariances of the
+                # predictions and their log-determinants, both on the device
+                pc = _pred_covs_device(batch.mean, batch.cov, self.num_users, self.num_items,
+                                       self.latent_d)
+                sg, ld = _slogdet_device(pc)
+                out[s:e] = [_entropy_bound_from(int(a), float(b)) for a, b in zip(sg, ld)]
             else:
                 means, covs = batch.means(), batch.covs()
                 for b in range(nb):
@@ -533,11 +535,7 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         n, m, d = self.num_users, self.num_items, self.latent_d
         if what == 'pred_entropy_bound':
             s, logdet = _slogdet(_pred_covs(mean, cov, n, m, d))
-            if s != 1:
-                if s == -1 and logdet < -50:
-                    return -1000
-                raise ValueError("prediction cov has det with sign {}, log {}".format(s, logdet))
-            return logdet
+            return _entropy_bound_from(s, logdet)
         if isinstance(what, tuple) and what[0] == 'fn':
             apmf = deepcopy(self)
             apmf.add_rating(ij[0], ij[1], v)
@@ -812,44 +810,56 @@ def _argbest(vals, maximize_):
     return float(vals[idx]), idx
 
 
-def _slogdet(mat):
-    '''np.linalg.slogdet semantics, computed on the device (cuSOLVER LU through torch)'''
+def _slogdet_device(mats_t):
+    '''np.linalg.slogdet of a (B, k, k) device tensor (overwritten): slogdet_kernel, LU with
+    partial pivoting, one CTA per matrix.  Returns host arrays (sign, logdet).'''
     import torch
     from . import device as D
-    s, ld = torch.linalg.slogdet(torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float64)).to(D.device()))
-    return float(s.item()), float(ld.item())
+    lib = N.require_device()
+    B, k = int(mats_t.shape[0]), int(mats_t.shape[1])
+    sign = torch.empty(B, dtype=torch.int32, device=mats_t.device)
+    logdet = torch.empty(B, dtype=torch.float64, device=mats_t.device)
+    N.check(lib.amf_slogdet_batched(k, B, D.ptr(mats_t), D.ptr(sign), D.ptr(logdet), D.stream_ptr()))
+    return sign.cpu().numpy(), logdet.cpu().numpy()
+
+
+def _slogdet(mat):
+    '''np.linalg.slogdet semantics, computed on the device'''
+    from . import device as D
+    s, ld = _slogdet_device(D.to_device(np.asarray(mat, dtype=np.float64)[None], np.float64))
+    return float(s[0]), float(ld[0])
+
+
+def _pred_covs_device(means_t, covs_t, n, m, d):
+    '''(active_pmf.py:324-390) for a batch: device tensors (B, k), (B, k, k) -> (B, NM, NM).
+
+    With X = [vec U; vec V] ~ N(mean, cov) every entry is a sum of 4th moments minus a product of
+    2nd moments; by Isserlis (x1 = U_ki, x2 = V_kj, x3 = U_la, x4 = V_lb)
+      Cov(x1 x2, x3 x4) = m1 m3 C24 + m1 m4 C23 + m2 m3 C14 + m2 m4 C13 + C13 C24 + C14 C23,
+    summed over k, l by pred_covs_kernel (csrc/predcov.cu), one thread per entry.'''
+    import torch
+    from . import device as D
+    lib = N.require_device()
+    B = int(means_t.shape[0])
+    out = torch.empty((B, n * m, n * m), dtype=torch.float64, device=means_t.device)
+    N.check(lib.amf_pred_covs(n, m, d, B, D.ptr(means_t), D.ptr(covs_t), D.ptr(out), D.stream_ptr()))
+    return out
 
 
 def _pred_covs(mean, cov, n, m, d):
-    '''(active_pmf.py:324-390) as batched tensor algebra on the device.
-
-    With X = [vec U; vec V] ~ N(mean, cov) every entry is a sum of 4th moments minus a product of
-    2nd moments; by Isserlis  Cov(UiVj, UaVb) = sum_kl  m m C + ... , evaluated here with einsum
-    over the (n,d)/(m,d) blocks of cov.  The diagonal uses the same closed form as pred_variance.
-    '''
-    import torch
     from . import device as D
-    dev = D.device()
-    mean_t = torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float64)).to(dev)
-    cov_t = torch.from_numpy(np.ascontiguousarray(cov, dtype=np.float64)).to(dev)
-    nu = n * d
-    mu = mean_t[:nu].reshape(n, d)
-    mv = mean_t[nu:].reshape(m, d)
-    Suu = cov_t[:nu, :nu].reshape(n, d, n, d)      # [i,k,a,l] = Cov(U_ki, U_la)
-    Svv = cov_t[nu:, nu:].reshape(m, d, m, d)      # [j,k,b,l]
-    Suv = cov_t[:nu, nu:].reshape(n, d, m, d)      # [i,k,b,l] = Cov(U_ki, V_lb)
-    # Cov(sum_k Uki Vkj, sum_l Ula Vlb) over independent-looking index pairs, Isserlis:
-    # E[x1 x2 x3 x4] - E[x1 x2]E[x3 x4] = m1 m3 C24 + m1 m4 C23 + m2 m3 C14 + m2 m4 C13
-    #                                      + C13 C24 + C14 C23     with x1=Uki x2=Vkj x3=Ula x4=Vlb
-    e = torch.einsum
-    t1 = e('ik,al,jkbl->ijab', mu, mu, Svv)                   # m1 m3 C24
-    t2 = e('ik,bl,aljk->ijab', mu, mv, Suv)                   # m1 m4 C23 = Cov(Vkj, Ula)
-    t3 = e('jk,al,ikbl->ijab', mv, mu, Suv)                   # m2 m3 C14 = Cov(Uki, Vlb)
-    t4 = e('jk,bl,ikal->ijab', mv, mv, Suu)                   # m2 m4 C13
-    t5 = e('ikal,jkbl->ijab', Suu, Svv)                       # C13 C24
-    t6 = e('ikbl,aljk->ijab', Suv, Suv)                       # C14 C23
-    out = (t1 + t2 + t3 + t4 + t5 + t6).reshape(n * m, n * m)
-    return out.cpu().numpy()
+    out = _pred_covs_device(D.to_device(np.asarray(mean, dtype=np.float64)[None], np.float64),
+                            D.to_device(np.asarray(cov, dtype=np.float64)[None], np.float64), n, m, d)
+    return out[0].cpu().numpy()
+
+
+def _entropy_bound_from(sign, logdet):
+    '''the sign logic of _pred_entropy_bound (active_pmf.py:559-574)'''
+    if sign != 1:
+        if sign == -1 and logdet < -50:
+            return -1000
+        raise ValueError("prediction cov has det with sign {}, log {}".format(sign, logdet))
+    return logdet
 
 
 ################################################################################

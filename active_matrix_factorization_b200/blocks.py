@@ -148,12 +148,15 @@ class BlockPosterior(object):
             old_u, old_v = self.mean_u.clone(), self.mean_v.clone()
             self.half_sweep(rat, 0, cov_term, update_mean)
             self.half_sweep(rat, 1, cov_term, update_mean)
-            self._check()
+            # ONE device->host read per sweep: the failure flag and the largest move of a mean
+            state = torch.stack(((self._fail != 0).any().to(torch.float64),
+                                 (self.mean_u - old_u).abs().max(),
+                                 (self.mean_v - old_v).abs().max())).cpu().numpy()
+            if state[0]:
+                self._fail.zero_()
+                raise np.linalg.LinAlgError("a block precision is not positive definite")
             yield kl_of(self) if kl_of is not None else None
-            if not update_mean:
-                continue
-            move = max(float((self.mean_u - old_u).abs().max()), float((self.mean_v - old_v).abs().max()))
-            if move < tol:
+            if update_mean and max(state[1], state[2]) < tol:
                 break
 
     # ---------------------------------------------------------------- scalar summaries --------

@@ -204,6 +204,18 @@ int amf_score_candidates(int criterion, int dtype, int64_t ncand, const int32_t*
  * NaN value never win; out = {0, -1} if none does.  recs_d and out_d may not alias. */
 int amf_best_reduce(const amf_best_t* recs_d, int n, int maximize, amf_best_t* out_d, void* stream);
 
+/* approx_pred_covs (active_pmf.py:324-390) for `count` Gaussian approximations at once: mean_d
+ * (count, k), cov_d (count, k, k), k = (n + m) d, the reference's layout (active_pmf.py:136-142);
+ * out_d (count, n*m, n*m) = covariance between all pairs of predicted cells (Isserlis).  Exact mode
+ * sizes only. */
+int amf_pred_covs(int32_t n, int32_t m, int d, int count, const double* mean_d,
+                  const double* cov_d, double* out_d, void* stream);
+/* np.linalg.slogdet of `count` k x k matrices a_d (count, k, k; overwritten by their LU factors):
+ * LU with partial pivoting, one CTA per matrix; sign_d in {-1, 0, 1}, logdet_d = log|det| (-inf
+ * for a singular matrix).  The log det of _approx_entropy and _pred_entropy_bound
+ * (active_pmf.py:526-530, 559-574). */
+int amf_slogdet_batched(int k, int count, double* a_d, int* sign_d, double* logdet_d, void* stream);
+
 /* predicted_matrix (pmf_cy.pyx:410-420): out_d (n, m) row-major = U V' + offset, in the compute type. */
 int amf_predicted_matrix(int dtype, int32_t n, int32_t m, int d, int ld, const void* U_d,
                          const void* V_d, double offset, void* out_d, void* stream);

@@ -259,6 +259,8 @@ struct amf_ratings {
   // staging for *_host entry points (grown on demand)
   void* stage[8];
   size_t stage_bytes[8];
+  // [0..3) objective sums, [4] rating sum, [6] sticky Gibbs failure flag (int), [8 .. 8 + 1056)
+  // moment workspace of amf_gibbs_hyper_device (d <= 32): calls on one handle are stream-ordered
   double* sums_d;
   int device;
   // side 0: users stream past item tiles (dU); side 1: items stream past user tiles (dV)
@@ -284,3 +286,4 @@ void runs_free(amf_runs* r);
 }  // namespace amf
 
 #define AMF_SUB 32
+#define AMF_SUMS_DOUBLES (8 + 32 * 32 + 32)

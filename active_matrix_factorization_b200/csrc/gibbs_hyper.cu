@@ -165,9 +165,9 @@ template <typename T>
 int hyper_launch(const amf_ratings* h, int d, int64_t rows, const T* x, const double* prior,
                  unsigned long long seed, unsigned long long stream_id, T* mu, T* alpha,
                  cudaStream_t s) {
-  double* work = nullptr;
+  // the handle's own workspace: no allocation per draw (a chain makes two draws per sample)
+  double* work = h->sums_d + 8;
   const size_t wbytes = sizeof(double) * (size_t)(d * d + d);
-  AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&work), wbytes, s));
   AMF_CUDA(cudaMemsetAsync(work, 0, wbytes, s));
   int64_t slabs = (rows + HYPER_SLAB - 1) / HYPER_SLAB;
   const int grid = (int)(slabs < num_sms() ? slabs : num_sms());
@@ -176,7 +176,6 @@ int hyper_launch(const amf_ratings* h, int d, int64_t rows, const T* x, const do
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);   // the handle's sticky Gibbs failure flag
   hyper_draw_kernel<T><<<1, 32, 0, s>>>(x, rows, d, work, prior, seed, stream_id, mu, alpha, fail);
   AMF_LAUNCH_CHECK();
-  AMF_CUDA(cudaFreeAsync(work, s));
   return AMF_OK;
 }
 

@@ -254,8 +254,8 @@ int amf_ratings_create(amf_ratings_t** out, int32_t n_users, int32_t n_items, in
     rc = build_side<double>(h, 0, i_d, j_d, (const double*)r_d, s);
     if (rc == AMF_OK) rc = build_side<double>(h, 1, j_d, i_d, (const double*)r_d, s);
   }
-  if (rc == AMF_OK && cudaMalloc(&h->sums_d, sizeof(double) * 8) != cudaSuccess) rc = AMF_ERR_CUDA;
-  if (rc == AMF_OK && cudaMemsetAsync(h->sums_d, 0, sizeof(double) * 8, s) != cudaSuccess) rc = AMF_ERR_CUDA;
+  if (rc == AMF_OK && cudaMalloc(&h->sums_d, sizeof(double) * AMF_SUMS_DOUBLES) != cudaSuccess) rc = AMF_ERR_CUDA;
+  if (rc == AMF_OK && cudaMemsetAsync(h->sums_d, 0, sizeof(double) * AMF_SUMS_DOUBLES, s) != cudaSuccess) rc = AMF_ERR_CUDA;
   if (rc != AMF_OK) { amf_ratings_destroy(h); return rc; }
   *out = h;
   return AMF_OK;

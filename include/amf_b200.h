@@ -313,7 +313,8 @@ int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype,
  * [inv(W0) (d*d, row-major) | mu0 (d) | beta0 | dof0].  Same distributions as the reference's host
  * code (including the scalar np.dot of bayes_pmf.py:176), Philox counters keyed by (seed,
  * stream_id): use a stream_id no half-sweep of the chain uses.  A scale matrix that is not positive
- * definite raises the handle's sticky failure flag (amf_gibbs_status).  d <= 32, rows >= 2. */
+ * definite raises the handle's sticky failure flag (amf_gibbs_status).  The moment sums live in
+ * the handle: draws on one handle must be stream-ordered (one chain per handle).  d <= 32, rows >= 2. */
 int amf_gibbs_hyper_device(const amf_ratings_t* h, int dtype, int d, int64_t rows,
                            const void* feats_d, const double* prior_d, uint64_t seed,
                            uint64_t stream_id, void* mu_out_d, void* alpha_out_d, void* stream);

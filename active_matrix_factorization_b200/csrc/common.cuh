@@ -244,6 +244,7 @@ struct amf_runs {
   uint8_t* seglen;        // [n_bundles * 32] entries of every lane's segment
   int2* binfo;            // [n_bundles + 1] {first group, longest segment}; the last one = {n_groups, 0}
   int64_t* tile_bstart;   // [n_tiles + 1] first bundle of every tile
+  uint32_t* tile_ctr;     // [n_tiles] bundles of the tile handed out in the running launch (zeroed per launch)
 };
 
 struct amf_ratings {

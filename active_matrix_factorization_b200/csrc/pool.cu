@@ -74,24 +74,25 @@ __device__ __forceinline__ void st_scores4(double* p, const double (&v)[4]) {
   __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
 }
 
-// PRED over a pool in the bundled-runs layout.  One CTA per SM owns a contiguous range of
-// bundles (equal cost); for every item tile that range touches, the tile is brought into shared
-// memory by TMA and the warps grab bundles of that tile from a shared counter (the metadata of
-// the next bundle is fetched while the current one is scored).  A lane scores one candidate per
+// PRED over a pool in the bundled-runs layout.  One CTA per SM; it starts at the item tile an
+// equal-cost split puts it on, brings the tile into shared memory by TMA, and its warps take
+// bundles of that tile from the tile's global counter until the tile is dry, then it moves to
+// the next tile with work left (runs_next_tile: CTAs that finish early help where work remains).
+// The metadata of the next bundle is fetched while the current one is scored.  A lane scores one candidate per
 // step with its user row in registers; the fused arg-best compares once per group of four steps
 // and looks up the caller's position only for scores that reach the warp's running best.
 template <typename T, int NVEC, bool MAX, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ orig,
                  const uint32_t* __restrict__ rowid, const int2* __restrict__ binfo,
-                 const int64_t* __restrict__ tile_bstart, int n_tiles, int64_t n_bundles,
+                 const int64_t* __restrict__ tile_bstart, uint32_t* tile_ctr, int n_tiles, int64_t n_bundles,
                  int tile_rows, int n_items, const T* __restrict__ U, const T* __restrict__ Vm,
                  T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
   using V = typename Vec<T>::type;
   constexpr uint32_t ROW_BYTES = NVEC * 16;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_v;
-  __shared__ unsigned int s_ctr;
+  __shared__ int s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t stage = smem_u32(smem_raw) + warp * runs_stage_bytes<NVEC>();
   unsigned char* tile_ptr = smem_raw + pool_stage_total<NVEC, THREADS>();
@@ -100,10 +101,6 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
 
   const int64_t total = runs_cost(binfo, n_bundles, POOL_BUNDLE_COST);
   const int64_t b_lo = runs_split(binfo, n_bundles, POOL_BUNDLE_COST, total * blockIdx.x / gridDim.x);
-  const int64_t b_hi = blockIdx.x + 1 == gridDim.x
-                           ? n_bundles
-                           : runs_split(binfo, n_bundles, POOL_BUNDLE_COST,
-                                        total * (blockIdx.x + 1) / gridDim.x);
   if (threadIdx.x == 0) mbar_init(&bar_v, 1);
   // the row behind the tile: what padding entries read.  NaN scores never win.
   for (int t = threadIdx.x; t < (int)(ROW_BYTES / sizeof(T)); t += THREADS)
@@ -122,18 +119,20 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
   int64_t best_o = -1;
   uint32_t phase_v = 0;
 
-  for (int64_t c = b_lo; c < b_hi;) {
-    while (t_cur + 1 < n_tiles && tile_bstart[t_cur + 1] <= c) ++t_cur;
-    const int64_t seg_end = min(b_hi, tile_bstart[t_cur + 1]);
-    __syncthreads();                                  // previous tile and counter are done with
+  for (int hop = 0; hop < n_tiles;) {
+    const int r_hop = runs_next_tile(tile_ctr, tile_bstart, n_tiles, t_cur + hop, n_tiles - hop, &s_next);
+    if (r_hop < 0) break;
+    hop += r_hop;
+    const int t_now = (t_cur + hop) % n_tiles;
+    ++hop;
+    const int64_t c = tile_bstart[t_now], seg_end = tile_bstart[t_now + 1];
     if (threadIdx.x == 0) {
-      s_ctr = 0;
-      const int rows = min(tile_rows, n_items - t_cur * tile_rows);
+      const int rows = min(tile_rows, n_items - t_now * tile_rows);
       const uint32_t bytes = (uint32_t)rows * ROW_BYTES;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bar_v, bytes);
       const unsigned char* src =
-          reinterpret_cast<const unsigned char*>(Vm) + (int64_t)t_cur * tile_rows * ROW_BYTES;
+          reinterpret_cast<const unsigned char*>(Vm) + (int64_t)t_now * tile_rows * ROW_BYTES;
       for (uint32_t o = 0; o < bytes; o += 32768u)
         tma_load_1d(tile_ptr + o, src + o, min(bytes - o, 32768u), &bar_v);
     }
@@ -141,9 +140,9 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
     mbar_wait(&bar_v, phase_v);
     phase_v ^= 1;
 
-    auto grab = [&]() -> int64_t {
+    auto grab = [&]() -> int64_t {                    // the tile's global counter: shared by all CTAs on it
       unsigned int g = 0;
-      if (lane == 0) g = atomicAdd(&s_ctr, 1u);
+      if (lane == 0) g = atomicAdd(tile_ctr + t_now, 1u);
       return c + (int64_t)__shfl_sync(0xffffffffu, g, 0);
     };
     int64_t b = grab();
@@ -219,7 +218,6 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
       }
       b = nb; info = ninfo; rid = nrid; w = w_next;
     }
-    c = seg_end;
   }
   Best best{(double)best_v, best_o < 0 ? -1 : best_o + index_base};
   best = block_best<MAX>(best);
@@ -252,6 +250,7 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
   constexpr int N = Vec<T>::N;
   const int nvec = ld / N;
   const amf_runs* r = &h->runs;
+  AMF_CUDA(cudaMemsetAsync(r->tile_ctr, 0, 4 * (size_t)r->n_tiles, s));   // bundles handed out: none yet
 #define POOL_T(NVEC_, THREADS_)                                                                 \
   do {                                                                                          \
     const size_t smem = pool_smem<NVEC_, THREADS_>(r->tile_rows);                               \
@@ -260,7 +259,7 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
     AMF_CUDA(cudaFuncSetAttribute(pool_pred_kernel<T, NVEC_, MAX, THREADS_>,                    \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     pool_pred_kernel<T, NVEC_, MAX, THREADS_><<<grid, THREADS_, smem, s>>>(                     \
-        r->idx, r->orig, r->rowid, r->binfo, r->tile_bstart, r->n_tiles, r->n_bundles,          \
+        r->idx, r->orig, r->rowid, r->binfo, r->tile_bstart, r->tile_ctr, r->n_tiles, r->n_bundles,          \
         r->tile_rows, h->n_items, U, V, scores_tmp, index_base, part);                          \
   } while (0)
 #define POOL(NVEC_) POOL_T(NVEC_, POOL_THREADS_NARROW)

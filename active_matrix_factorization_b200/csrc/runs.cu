@@ -161,7 +161,7 @@ __global__ void runs_scatter_kernel(const uint64_t* __restrict__ keys,
 
 void runs_free(amf_runs* r) {
   cudaFree(r->idx); cudaFree(r->val); cudaFree(r->orig); cudaFree(r->pos_of); cudaFree(r->rowid);
-  cudaFree(r->seglen); cudaFree(r->binfo); cudaFree(r->tile_bstart);
+  cudaFree(r->seglen); cudaFree(r->binfo); cudaFree(r->tile_bstart); cudaFree(r->tile_ctr);
   memset(r, 0, sizeof(*r));
 }
 
@@ -203,6 +203,7 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     int64_t *seg_start = nullptr, *nb = nullptr, *bundle_g = nullptr, *gstart = nullptr;
     int32_t* bundle_len = nullptr;
     RUNS_CUDA(cudaMalloc(&r->tile_bstart, 8 * (size_t)(nt + 1)));
+    RUNS_CUDA(cudaMalloc(&r->tile_ctr, 4 * (size_t)nt));
     if (n == 0) {
       RUNS_CUDA(cudaMemsetAsync(r->tile_bstart, 0, 8 * (size_t)(nt + 1), s));
       RUNS_CUDA(cudaMalloc(&r->binfo, sizeof(int2)));

@@ -264,4 +264,34 @@ __device__ __forceinline__ int64_t runs_split(const int2* __restrict__ binfo, in
   return lo;
 }
 
+// Dynamic work distribution of the tile kernels.  A CTA starts at its HOME tile (where an equal-cost
+// static split would put it) and its warps take bundles of that tile from the tile's GLOBAL
+// counter, which all CTAs on the tile share; when the tile runs dry the CTA moves on, cyclically,
+// to the next tile that still has bundles nobody took -- so CTAs that finish early help on the
+// tiles that are behind, at the price of one more tile load.  runs_next_tile: hops (>= 0) from
+// `from` to that tile, -1 if none within `hops_left`; called by all threads of the CTA (it
+// synchronises the CTA: the previous tile is done with when it returns).
+__device__ __forceinline__ uint32_t runs_tile_bundles(const int64_t* __restrict__ tile_bstart, int t) {
+  return (uint32_t)(tile_bstart[t + 1] - tile_bstart[t]);
+}
+__device__ __forceinline__ int runs_next_tile(const uint32_t* tile_ctr,
+                                              const int64_t* __restrict__ tile_bstart, int n_tiles,
+                                              int from, int hops_left, int* s_next) {
+  for (int h0 = 0; h0 < hops_left; h0 += (int)blockDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_next = 0x7fffffff;
+    __syncthreads();
+    const int h = h0 + (int)threadIdx.x;
+    if (h < hops_left) {
+      const int t = (from + h) % n_tiles;
+      const uint32_t taken = *reinterpret_cast<const volatile uint32_t*>(tile_ctr + t);
+      if (taken < runs_tile_bundles(tile_bstart, t)) atomicMin(s_next, h);
+    }
+    __syncthreads();
+    const int r = *s_next;
+    if (r != 0x7fffffff) return r;
+  }
+  return -1;
+}
+
 }  // namespace amf

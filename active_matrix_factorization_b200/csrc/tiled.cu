@@ -86,13 +86,14 @@ __device__ __forceinline__ void ld_vals4(const double* p, double (&out)[4]) {
 
 // One side of the fused loss + gradient on the bundled-runs list.  Own = the matrix whose rows
 // stream (row + gradient accumulator in registers), Tile = the matrix whose tile sits in shared
-// memory.  Work distribution and tile loading are those of pool_pred_kernel.
+// memory.  Work distribution (home tile + global per-tile counters) and tile loading are those of
+// pool_pred_kernel.
 template <typename T, int NVEC, bool GRAD, bool FLUSH_TMA>
 __global__ void __launch_bounds__(tiled_threads<T, NVEC>(), 1)
 tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
                   const uint32_t* __restrict__ rowid, const uint8_t* __restrict__ seglen,
                   const int2* __restrict__ binfo, const int64_t* __restrict__ tile_bstart,
-                  int n_tiles, int64_t n_bundles, int tile_rows, int tile_side_rows,
+                  uint32_t* tile_ctr, int n_tiles, int64_t n_bundles, int tile_rows, int tile_side_rows,
                   const T* __restrict__ Own, const T* __restrict__ Tile, T inv_sigma,
                   T mean_offset, T* __restrict__ dOwn, double* __restrict__ sq_err) {
   using V = typename Vec<T>::type;
@@ -100,7 +101,7 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
   constexpr int THREADS = tiled_threads<T, NVEC>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_v;
-  __shared__ unsigned int s_ctr;
+  __shared__ int s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t stage = smem_u32(smem_raw) + warp * runs_stage_bytes<NVEC>();
   unsigned char* tile_ptr = smem_raw + tiled_stage_total<T, NVEC>();
@@ -110,10 +111,6 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
 
   const int64_t total = runs_cost(binfo, n_bundles, TILED_BUNDLE_COST);
   const int64_t b_lo = runs_split(binfo, n_bundles, TILED_BUNDLE_COST, total * blockIdx.x / gridDim.x);
-  const int64_t b_hi = blockIdx.x + 1 == gridDim.x
-                           ? n_bundles
-                           : runs_split(binfo, n_bundles, TILED_BUNDLE_COST,
-                                        total * (blockIdx.x + 1) / gridDim.x);
   if (threadIdx.x == 0) mbar_init(&bar_v, 1);
   // the row behind the tile: what padding entries read (their residual is masked by the length)
   for (int t = threadIdx.x; t < (int)(ROW_BYTES / sizeof(T)); t += THREADS)
@@ -130,18 +127,20 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
   double local_sq = 0;
   uint32_t phase_v = 0;
 
-  for (int64_t c = b_lo; c < b_hi;) {
-    while (t_cur + 1 < n_tiles && tile_bstart[t_cur + 1] <= c) ++t_cur;
-    const int64_t seg_end = min(b_hi, tile_bstart[t_cur + 1]);
-    __syncthreads();                                  // previous tile and counter are done with
+  for (int hop = 0; hop < n_tiles;) {
+    const int r_hop = runs_next_tile(tile_ctr, tile_bstart, n_tiles, t_cur + hop, n_tiles - hop, &s_next);
+    if (r_hop < 0) break;
+    hop += r_hop;
+    const int t_now = (t_cur + hop) % n_tiles;
+    ++hop;
+    const int64_t c = tile_bstart[t_now], seg_end = tile_bstart[t_now + 1];
     if (threadIdx.x == 0) {
-      s_ctr = 0;
-      const int rows = min(tile_rows, tile_side_rows - t_cur * tile_rows);
+      const int rows = min(tile_rows, tile_side_rows - t_now * tile_rows);
       const uint32_t bytes = (uint32_t)rows * ROW_BYTES;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bar_v, bytes);
       const unsigned char* src =
-          reinterpret_cast<const unsigned char*>(Tile) + (int64_t)t_cur * tile_rows * ROW_BYTES;
+          reinterpret_cast<const unsigned char*>(Tile) + (int64_t)t_now * tile_rows * ROW_BYTES;
       for (uint32_t o = 0; o < bytes; o += 32768u)
         tma_load_1d(tile_ptr + o, src + o, min(bytes - o, 32768u), &bar_v);
     }
@@ -149,9 +148,9 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
     mbar_wait(&bar_v, phase_v);
     phase_v ^= 1;
 
-    auto grab = [&]() -> int64_t {
+    auto grab = [&]() -> int64_t {                    // the tile's global counter: shared by all CTAs on it
       unsigned int g = 0;
-      if (lane == 0) g = atomicAdd(&s_ctr, 1u);
+      if (lane == 0) g = atomicAdd(tile_ctr + t_now, 1u);
       return c + (int64_t)__shfl_sync(0xffffffffu, g, 0);
     };
     int64_t b = grab();
@@ -210,7 +209,6 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
       local_sq += (double)sq;
       b = nb; info = ninfo; rid = nrid; mylen = nlen;
     }
-    c = seg_end;
   }
   if (sq_err) {
     const double s = block_sum(local_sq);
@@ -256,6 +254,7 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
   // red / tma overrides.
   const char* fl = getenv("AMF_TILED_FLUSH");
   const bool tma_flush = fl ? !strcmp(fl, "tma") : sizeof(T) == 8;
+  AMF_CUDA(cudaMemsetAsync(r->tile_ctr, 0, 4 * (size_t)r->n_tiles, s));   // bundles handed out: none yet
   if (GRAD) AMF_DBG_RANGE(0, dOwn, (size_t)(side == 0 ? h->n_users : h->n_items) * nvec * 16, s);
 #define TILED(NVEC_)                                                                              \
   do {                                                                                            \
@@ -265,8 +264,8 @@ static int launch_tiled(const amf_ratings* h, int side, int nvec, const T* Own, 
     auto kern = tma_flush ? tiled_side_kernel<T, NVEC_, GRAD, GRAD> : tiled_side_kernel<T, NVEC_, GRAD, false>; \
     AMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, tiled_threads<T, NVEC_>(), smem, s>>>(                                           \
-        r->idx, (const T*)r->val, r->rowid, r->seglen, r->binfo, r->tile_bstart, r->n_tiles,      \
-        r->n_bundles, r->tile_rows, tile_side_rows, Own, Tile, inv_sigma, mean_offset, dOwn,      \
+        r->idx, (const T*)r->val, r->rowid, r->seglen, r->binfo, r->tile_bstart, r->tile_ctr,     \
+        r->n_tiles, r->n_bundles, r->tile_rows, tile_side_rows, Own, Tile, inv_sigma, mean_offset, dOwn,      \
         sq_err);                                                                                  \
   } while (0)
   switch (nvec) {

@@ -88,6 +88,8 @@ PROTOTYPES = {
                                         C.c_uint64, _P, _I32, _I32, _P],
     "amf_gibbs_half_sweep_batched": [_P, _INT, _INT, _INT, _INT, _P, _P, _P, _F64, _F64, _P, _P, _P, _P,
                                      C.c_uint64, C.c_uint64, _P, _P],
+    "amf_gibbs_chain_device": [_P, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _F64, _F64, C.c_uint64,
+                               C.c_uint64, _P, _P, _P],
     "amf_gibbs_hyper_device": [_P, _INT, _INT, _I64, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P],
     "amf_philox_normal": [_INT, C.c_uint64, C.c_uint64, _I64, _INT, _P, _P],
     "amf_gibbs_status": [_P, C.POINTER(_INT), _P],

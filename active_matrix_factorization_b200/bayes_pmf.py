@@ -284,6 +284,7 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
     # where the d x d Normal-Wishart draws of the fast-mode chain are made: 'device'
     # (amf_gibbs_hyper_device: nothing of a sample touches the host) or 'host' (numpy, global stream)
     hyper_mode = 'device'
+    device_chunk = 64         # samples per amf_gibbs_chain_device call of the fast-mode chain (at most 256 MB)
 
     def samples_device(self, num_gibbs=2, fit_first=False, seed=None, hyper=None):
         '''Fast-mode chain (bayes_pmf.py:227-302 in law): yields (user_sample, item_sample) as
@@ -340,8 +341,25 @@ class BayesianPMF(ProbabilisticMatrixFactorization):
             c = t64 - mean
             return mean, (c.T @ c) / (t.shape[0] - 1)
 
+        # samples are produced `chunk` at a time by ONE library call (amf_gibbs_chain_device): the
+        # host does not take part in a sample at all; the failure flag is read once per chunk
+        chunk = max(1, int(self.device_chunk))      # 1: drive every kernel group from here instead
+        if chunk > 1:
+            chunk = max(2, min(chunk, (256 << 20) // max(1, (n + m) * d * (4 if name == 'f32' else 8))))
+        while hyper == 'device' and chunk > 1:
+            us = torch.empty((chunk, n, d), dtype=tdt, device=users_t.device)
+            vs = torch.empty((chunk, m, d), dtype=tdt, device=users_t.device)
+            N.check(lib.amf_gibbs_chain_device(
+                rat.handle, D.code(name), d, chunk, int(num_gibbs), D.ptr(users_t), D.ptr(items_t),
+                D.ptr(priors[0]), D.ptr(priors[1]), float(self.beta), float(self._mean_offset()), seed,
+                stream_id, D.ptr(us), D.ptr(vs), D.stream_ptr()))
+            stream_id += chunk * (2 + 2 * int(num_gibbs))
+            self._check_gibbs(rat)
+            users_t, items_t = us[chunk - 1], vs[chunk - 1]
+            for k in range(chunk):
+                yield us[k], vs[k]
         while True:
-            if hyper == 'device':
+            if hyper == 'device':      # device_chunk = 1: the same chain, one library call per kernel group
                 hyper_t = torch.empty(2 * (d + dd), dtype=tdt, device=users_t.device)
                 for side, feats in ((0, users_t), (1, items_t)):
                     o = side * (d + dd)

@@ -284,6 +284,10 @@ int runs_build(amf_runs* out, int64_t n, const int32_t* own_d, const int32_t* ot
                const void* val_d, int val_size, int32_t own_rows, int32_t other_rows, int tile_rows,
                bool want_orig, cudaStream_t s);
 void runs_free(amf_runs* r);
+// gibbs_hyper.cu: one Normal-Wishart draw (mu, alpha) from the factor rows `feats` (amf_gibbs_hyper_device)
+int gibbs_hyper_draw(const amf_ratings* h, int dtype, int d, int64_t rows, const void* feats,
+                     const double* prior, unsigned long long seed, unsigned long long stream_id,
+                     void* mu, void* alpha, cudaStream_t s);
 }  // namespace amf
 
 #define AMF_SUB 32

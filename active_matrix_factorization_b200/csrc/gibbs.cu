@@ -1031,6 +1031,71 @@ int amf_gibbs_half_sweep_batched(const amf_ratings_t* h, int side, int dtype, in
                               true, seed, stream_id, gb);
 }
 
+int amf_gibbs_chain_device(const amf_ratings_t* h, int dtype, int d, int n_samples, int num_gibbs,
+                           const void* users_d, const void* items_d, const double* prior_u_d,
+                           const double* prior_v_d, double beta, double mean_offset, uint64_t seed,
+                           uint64_t stream_id0, void* out_users_d, void* out_items_d, void* stream) {
+  AMF_REQUIRE(h && users_d && items_d && prior_u_d && prior_v_d && out_users_d && out_items_d,
+              "amf_gibbs_chain_device: NULL argument");
+  AMF_REQUIRE(dtype == h->dtype, "amf_gibbs_chain_device: dtype does not match the rating list");
+  AMF_REQUIRE(d >= 1 && d <= 32, "amf_gibbs_chain_device: d must be in [1, 32]");
+  AMF_REQUIRE(n_samples >= 0 && num_gibbs >= 1, "amf_gibbs_chain_device: bad counts");
+  AMF_REQUIRE(h->n_users >= 2 && h->n_items >= 2, "amf_gibbs_chain_device: needs at least two rows per side");
+  if (n_samples == 0) return AMF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    int rc = ratings_compact(const_cast<amf_ratings*>(h), s);
+    if (rc != AMF_OK) return rc;
+  }
+  const size_t es = dtype == AMF_F32 ? 4 : 8;
+  const size_t bu = (size_t)h->n_users * d * es, bv = (size_t)h->n_items * d * es;
+  const size_t bh = (size_t)(d + d * d) * es;           // one side's (mu, alpha)
+  // scratch: both sides' hyper-parameters, and the rows of the rounds that are not kept
+  unsigned char* scratch = nullptr;
+  AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), 2 * bh + bu + bv, s));
+  unsigned char* hyper = scratch;
+  unsigned char* tmp_u = scratch + 2 * bh;
+  unsigned char* tmp_v = tmp_u + bu;
+  const unsigned char* cur_u = static_cast<const unsigned char*>(users_d);
+  const unsigned char* cur_v = static_cast<const unsigned char*>(items_d);
+  uint64_t sid = stream_id0;
+  int rc = AMF_OK;
+  auto half = [&](int side, const unsigned char* other, unsigned char* out) -> int {
+    const unsigned char* mu = hyper + side * bh;
+    const unsigned char* alpha = mu + (size_t)d * es;
+    const uint64_t id = sid++;
+    if (dtype == AMF_F32)
+      return gibbs_launch<float>(h, side, d, (const float*)other, (const float*)alpha, (const float*)mu,
+                                 beta, mean_offset, nullptr, (float*)out, 0, -1, s, true, seed, id);
+    return gibbs_launch<double>(h, side, d, (const double*)other, (const double*)alpha,
+                                (const double*)mu, beta, mean_offset, nullptr, (double*)out, 0, -1, s,
+                                true, seed, id);
+  };
+  for (int smp = 0; smp < n_samples && rc == AMF_OK; ++smp) {
+    // the same counters the host-driven loop of samples_device() uses: draw for draw equal to it
+    rc = gibbs_hyper_draw(h, dtype, d, h->n_users, cur_u, prior_u_d, seed, (1ull << 40) + sid, hyper,
+                          hyper + (size_t)d * es, s);
+    ++sid;
+    if (rc == AMF_OK)
+      rc = gibbs_hyper_draw(h, dtype, d, h->n_items, cur_v, prior_v_d, seed, (1ull << 40) + sid,
+                            hyper + bh, hyper + bh + (size_t)d * es, s);
+    ++sid;
+    unsigned char* keep_u = static_cast<unsigned char*>(out_users_d) + (size_t)smp * bu;
+    unsigned char* keep_v = static_cast<unsigned char*>(out_items_d) + (size_t)smp * bv;
+    for (int r = 0; r < num_gibbs && rc == AMF_OK; ++r) {
+      const bool last = r == num_gibbs - 1;
+      unsigned char* nu = last ? keep_u : tmp_u;
+      unsigned char* nv = last ? keep_v : tmp_v;
+      rc = half(0, cur_v, nu);
+      cur_u = nu;
+      if (rc == AMF_OK) rc = half(1, cur_u, nv);
+      cur_v = nv;
+    }
+  }
+  cudaFreeAsync(scratch, s);
+  return rc;
+}
+
 int amf_philox_normal(int dtype, uint64_t seed, uint64_t stream_id, int64_t rows, int d,
                       void* out_d, void* stream) {
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_philox_normal: bad dtype");

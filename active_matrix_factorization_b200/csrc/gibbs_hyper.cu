@@ -66,20 +66,36 @@ __device__ double philox_chi2(double k, unsigned long long seed, unsigned long l
   return 2.0 * dd;                                     // unreachable in practice (acceptance > 95 %)
 }
 
-// one warp, lane = row / column; d <= 32; all algebra in fp64
+// 128 threads draw the random numbers of the Bartlett factor (a Philox normal costs a few hundred
+// fp64 instructions: spread over the CTA they take one round instead of d), then warp 0 does the
+// algebra with lane = row / column; d <= 32; everything in fp64
 template <typename T>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 hyper_draw_kernel(const T* __restrict__ x, int64_t rows, int d, const double* __restrict__ work,
                   const double* __restrict__ prior, unsigned long long seed,
                   unsigned long long stream, T* __restrict__ mu_out, T* __restrict__ alpha_out,
                   int* __restrict__ fail) {
   __shared__ double L[32][33], B[32][33], X[32][33];
-  __shared__ double tvec[32], xbar[32];
-  const int lane = threadIdx.x;
+  __shared__ double tvec[32], xbar[32], zvec[32];
   const double n = (double)rows;
   const double* winv0 = prior;
   const double* mu0 = prior + d * d;
   const double b0 = prior[d * d + d], dof = floor(prior[d * d + d + 1] + n);
+  // Bartlett factor and the normals of mu: entry (i, j) of B by thread i * d + j (strided)
+  for (int e = threadIdx.x; e < d * d + d; e += blockDim.x) {
+    if (e < d * d) {
+      const int i = e / d, j = e % d;
+      double v = 0.0;
+      if (j < i) v = philox_normal(seed, stream, (uint32_t)i, (uint32_t)j);
+      else if (j == i) v = sqrt(philox_chi2(dof - i, seed, stream, (uint32_t)i));
+      B[i][j] = v;
+    } else {
+      zvec[e - d * d] = philox_normal(seed, stream, (uint32_t)(e - d * d), 32u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   // mean, covariance, posterior scale matrix
   double sh = 0, xb = 0;
   if (lane < d) {
@@ -117,13 +133,6 @@ hyper_draw_kernel(const T* __restrict__ x, int64_t rows, int d, const double* __
     }
     __syncwarp();
   }
-  // Bartlett factor
-  if (lane < d) {
-    for (int j = 0; j < d; ++j)
-      B[lane][j] = j < lane ? philox_normal(seed, stream, (uint32_t)lane, (uint32_t)j) : 0.0;
-    B[lane][lane] = sqrt(philox_chi2(dof - lane, seed, stream, (uint32_t)lane));
-  }
-  __syncwarp();
   // X = L^-T B: lane = column of X, back substitution with the upper triangular L'
   if (lane < d) {
     for (int i = d - 1; i >= 0; --i) {
@@ -142,8 +151,7 @@ hyper_draw_kernel(const T* __restrict__ x, int64_t rows, int d, const double* __
     }
   }
   // mu = mu* + L (B^-T z) / sqrt(b0 + n)
-  const double z = lane < d ? philox_normal(seed, stream, (uint32_t)lane, 32u) : 0.0;
-  tvec[lane] = z;
+  tvec[lane] = lane < d ? zvec[lane] : 0.0;
   __syncwarp();
   if (lane == 0) {
     for (int i = d - 1; i >= 0; --i) {                 // B' t = z, B' upper triangular
@@ -174,12 +182,24 @@ int hyper_launch(const amf_ratings* h, int d, int64_t rows, const T* x, const do
   hyper_moments_kernel<T><<<grid, 256, sizeof(double) * HYPER_SLAB * d, s>>>(x, rows, d, work);
   AMF_LAUNCH_CHECK();
   int* fail = reinterpret_cast<int*>(h->sums_d + 6);   // the handle's sticky Gibbs failure flag
-  hyper_draw_kernel<T><<<1, 32, 0, s>>>(x, rows, d, work, prior, seed, stream_id, mu, alpha, fail);
+  hyper_draw_kernel<T><<<1, 128, 0, s>>>(x, rows, d, work, prior, seed, stream_id, mu, alpha, fail);
   AMF_LAUNCH_CHECK();
   return AMF_OK;
 }
 
 }  // namespace
+
+// typed entry for the chain driver of gibbs.cu
+int gibbs_hyper_draw(const amf_ratings* h, int dtype, int d, int64_t rows, const void* feats,
+                     const double* prior, unsigned long long seed, unsigned long long stream_id,
+                     void* mu, void* alpha, cudaStream_t s) {
+  if (dtype == AMF_F32)
+    return hyper_launch<float>(h, d, rows, (const float*)feats, prior, seed, stream_id, (float*)mu,
+                               (float*)alpha, s);
+  return hyper_launch<double>(h, d, rows, (const double*)feats, prior, seed, stream_id, (double*)mu,
+                              (double*)alpha, s);
+}
+
 }  // namespace amf
 
 using namespace amf;
@@ -194,12 +214,8 @@ int amf_gibbs_hyper_device(const amf_ratings_t* h, int dtype, int d, int64_t row
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_gibbs_hyper_device: bad dtype");
   AMF_REQUIRE(d >= 1 && d <= 32, "amf_gibbs_hyper_device: d must be in [1, 32]");
   AMF_REQUIRE(rows >= 2, "amf_gibbs_hyper_device: the covariance needs at least two rows");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == AMF_F32)
-    return hyper_launch<float>(h, d, rows, (const float*)feats_d, prior_d, seed, stream_id,
-                               (float*)mu_out_d, (float*)alpha_out_d, s);
-  return hyper_launch<double>(h, d, rows, (const double*)feats_d, prior_d, seed, stream_id,
-                              (double*)mu_out_d, (double*)alpha_out_d, s);
+  return gibbs_hyper_draw(h, dtype, d, rows, feats_d, prior_d, seed, stream_id, mu_out_d,
+                          alpha_out_d, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

@@ -318,6 +318,18 @@ int amf_gibbs_half_sweep_device_rng(const amf_ratings_t* h, int side, int dtype,
 int amf_gibbs_hyper_device(const amf_ratings_t* h, int dtype, int d, int64_t rows,
                            const void* feats_d, const double* prior_d, uint64_t seed,
                            uint64_t stream_id, void* mu_out_d, void* alpha_out_d, void* stream);
+/* n_samples consecutive samples of the fast-mode chain (BayesianPMF.samples, bayes_pmf.py:227-302,
+ * in law) enqueued by ONE call: per sample the Normal-Wishart draws of both sides
+ * (amf_gibbs_hyper_device) and num_gibbs rounds of the two half-sweeps
+ * (amf_gibbs_half_sweep_device_rng); nothing is read back, the host does not take part.  The chain
+ * starts from users_d (n, d) / items_d (m, d); sample s is written to out_users_d[s] (n, d) and
+ * out_items_d[s] (m, d) (the last one is the state to continue from).  Counters: hyper draws use
+ * (1 << 40) + id, half-sweeps id, with id running from stream_id0 by 2 + 2 num_gibbs per sample --
+ * the sequence a host loop over the two entry points above makes, so both give the same chain. */
+int amf_gibbs_chain_device(const amf_ratings_t* h, int dtype, int d, int n_samples, int num_gibbs,
+                           const void* users_d, const void* items_d, const double* prior_u_d,
+                           const double* prior_v_d, double beta, double mean_offset, uint64_t seed,
+                           uint64_t stream_id0, void* out_users_d, void* out_items_d, void* stream);
 /* `count` chains over the SAME rating list in one launch, chain p with one extra rating
  * (ex_row_d[p] = its row on the side being sampled, ex_col_d[p] = the row of `other` it pairs
  * with, ex_val_d[p] = its value; all NULL: none) -- the per-candidate, per-value models of the

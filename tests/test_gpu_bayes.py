@@ -351,6 +351,27 @@ def test_device_hyperparameter_draws_follow_the_normal_wishart_posterior(Bm, dty
     assert np.linalg.eigvalsh(alphas).min() > 0
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_chain_driver_equals_the_host_driven_loop(Bm, golden, dtype, monkeypatch):
+    """amf_gibbs_chain_device (16 samples per call) and the same chain driven kernel group by
+    kernel group from Python use the same Philox counters: equal draw for draw"""
+    monkeypatch.setenv("AMF_B200_DTYPE", dtype)
+    g = golden("gibbs_15x12_d3")
+    chains = []
+    for chunk in (16, 1, 5):
+        b = Bm.BayesianPMF(g["ratings"], 3, subtract_mean=True)
+        b.compute_dtype = dtype
+        b.users, b.items = g["users"].copy(), g["items"].copy()
+        b.device_seed, b.device_chunk = 9, chunk
+        chains.append([(u.cpu().numpy().copy(), v.cpu().numpy().copy())
+                       for u, v in islice(b.samples_device(num_gibbs=2), 21)])
+    for other in chains[1:]:
+        for (u0, v0), (u1, v1) in zip(chains[0], other):
+            np.testing.assert_array_equal(u0, u1)
+            np.testing.assert_array_equal(v0, v1)
+    assert np.isfinite(chains[0][-1][0]).all()
+
+
 def test_fast_chain_with_host_hyperparameters_still_available(Bm, golden):
     g = golden("gibbs_15x12_d3")
     b = Bm.BayesianPMF(g["ratings"], 3, subtract_mean=True)

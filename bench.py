@@ -598,7 +598,7 @@ def run_ours(a):
                                    if a.grad_shard == "ratings" else
                                    "candidates sharded per GPU, ratings and U rows sharded by user range (%d users per GPU), "
                                    "NCCL all-reduce of dV/sums + all-gather of winners" % n),
-                   "l2": "inputs larger than L2 (rating list %.0f MB per side, packed candidate pool %.0f MB per GPU)" % (nnz * 8 / 1e6, ncand * 4 / 1e6),
+                   "l2": "inputs larger than the 126 MB L2: the kernels stream >= %.0f MB of rating entries per side (6 bytes each, bundled-runs layout) and >= %.0f MB of candidate indices per GPU (2 bytes each) every step" % (nnz * 6 / 1e6, ncand * 2 / 1e6),
                    "rating_layout": "tiled" if tiled_grad else "rows",
                    "value_is": "candidates / scoring-phase time; ms_per_step covers gradient + scoring"},
         "phases": {

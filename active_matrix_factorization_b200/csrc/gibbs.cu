@@ -504,7 +504,12 @@ struct GibbsBatch {
 };
 
 template <typename T, bool TC, bool FAST>
-__global__ void __launch_bounds__(GIBBS_THREADS, 3)   // <= 168 registers: 12 warps per SM
+#ifndef AMF_GIBBS_MINBLOCKS
+#define AMF_GIBBS_MINBLOCKS 4     // 128 registers, 16 warps per SM.  Measured at C5 scale, fast / parity
+                                  // half-sweep of the user side: 3 (168 regs) 7.60 / 12.65 ms, 4 6.80 / 12.19 ms
+                                  // (despite ~0.9 KB of spills), 5 10.2 / 15.2 ms, 6 13.1 / 19.4 ms
+#endif
+__global__ void __launch_bounds__(GIBBS_THREADS, AMF_GIBBS_MINBLOCKS)
 gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const T* __restrict__ val, int row_begin, int rows, int d,
                        const T* __restrict__ other, const T* __restrict__ alpha,

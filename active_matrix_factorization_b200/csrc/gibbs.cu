@@ -503,13 +503,12 @@ struct GibbsBatch {
   const double* offsets;      // mean offset of chain p (NULL: the common one)
 };
 
-template <typename T, bool TC, bool FAST>
-#ifndef AMF_GIBBS_MINBLOCKS
-#define AMF_GIBBS_MINBLOCKS 4     // 128 registers, 16 warps per SM.  Measured at C5 scale, fast / parity
-                                  // half-sweep of the user side: 3 (168 regs) 7.60 / 12.65 ms, 4 6.80 / 12.19 ms
-                                  // (despite ~0.9 KB of spills), 5 10.2 / 15.2 ms, 6 13.1 / 19.4 ms
-#endif
-__global__ void __launch_bounds__(GIBBS_THREADS, AMF_GIBBS_MINBLOCKS)
+// MINB = resident CTAs per SM the register budget is set for: 3 (168 registers, no spills) is the
+// faster code for one wave of rows (C4: 2625 rows, 0.108 against 0.132 ms per sweep), 4 (128
+// registers, ~0.9 KB of spills, 16 warps per SM) wins when the rows fill the GPU many times over
+// (C5 user side, fast / parity: 6.80 / 12.19 against 7.60 / 12.65 ms; 5 and 6 are far slower).
+template <typename T, bool TC, bool FAST, int MINB>
+__global__ void __launch_bounds__(GIBBS_THREADS, MINB)
 gibbs_rows_warp_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const T* __restrict__ val, int row_begin, int rows, int d,
                        const T* __restrict__ other, const T* __restrict__ alpha,
@@ -890,20 +889,25 @@ static int gibbs_launch(const amf_ratings* h, int side, int d, const T* other, c
     const int64_t nwarp_rows = ((int64_t)span * (gb.count > 1 ? gb.count : 1) + GIBBS_THREADS / 32 - 1) /
                                (GIBBS_THREADS / 32);
     const int grid_w = (int)(nwarp_rows < (int64_t)num_sms() * 8 ? nwarp_rows : (int64_t)num_sms() * 8);
-#define GIBBS_WARP(TC_, FAST_)                                                                   \
+#define GIBBS_WARP_B(TC_, FAST_, MINB_)                                                          \
   do {                                                                                           \
-    AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_, FAST_>,                         \
+    AMF_CUDA(cudaFuncSetAttribute(gibbs_rows_warp_kernel<T, TC_, FAST_, MINB_>,                  \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));    \
-    gibbs_rows_warp_kernel<T, TC_, FAST_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(                 \
+    gibbs_rows_warp_kernel<T, TC_, FAST_, MINB_><<<grid_w, GIBBS_THREADS, smem_w, s>>>(          \
         h->ptr[side], h->idx[side], (const T*)h->val[side], row_begin, rows, d, other, alpha, mu, \
         beta, mean_offset, z, out, fail, a_doubles, warp_doubles, seed, stream_id, gb);          \
   } while (0)
+    // many waves of rows: the 16-warp build; otherwise the spill-free one
+    const bool many = nwarp_rows > (int64_t)num_sms() * 3 * 8;
+#define GIBBS_WARP(TC_, FAST_)                                                                   \
+  do { if (many) GIBBS_WARP_B(TC_, FAST_, 4); else GIBBS_WARP_B(TC_, FAST_, 3); } while (0)
     if constexpr (sizeof(T) == 4) {
       if (tc) { if (fast) GIBBS_WARP(true, true); else GIBBS_WARP(true, false); }
       else { if (fast) GIBBS_WARP(false, true); else GIBBS_WARP(false, false); }
     } else {
       if (fast) GIBBS_WARP(false, true); else GIBBS_WARP(false, false);
     }
+#undef GIBBS_WARP_B
 #undef GIBBS_WARP
     AMF_LAUNCH_CHECK();
     return AMF_OK;

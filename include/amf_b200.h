@@ -82,9 +82,10 @@ int amf_ratings_append(amf_ratings_t* h, int64_t n_new, const int32_t* i_d, cons
 int amf_ratings_compact(amf_ratings_t* h, void* stream);
 
 /* Which copy of the list amf_pmf_loss_grad runs on.  AUTO: the tiled copy (item / user tiles of
- * the factor matrices resident in shared memory, built on first use, +8 or +12 bytes per rating
- * and side) when nnz >= 2^20 and the padded factor row is 64, 128 or 256 bytes, else the
- * row-sorted lists; ROWS / TILED force one (TILED fails with AMF_ERR_UNSUPPORTED if it cannot). */
+ * the factor matrices resident in shared memory; the "bundled runs" layout: one lane per (row, tile)
+ * run segment, 16-bit row inside the tile + the rating = 6 or 10 bytes per rating and side plus
+ * ~20 % padding, built on first use) when nnz >= 2^20 and the padded factor row is 64, 128 or 256
+ * bytes, else the row-sorted lists; ROWS / TILED force one (TILED fails with AMF_ERR_UNSUPPORTED if it cannot). */
 #define AMF_LAYOUT_AUTO 0
 #define AMF_LAYOUT_ROWS 1
 #define AMF_LAYOUT_TILED 2

@@ -169,86 +169,6 @@ __device__ __forceinline__ void flush_rows_tma(unsigned char* __restrict__ table
   }
 }
 
-// ---- the same with a staging buffer for all 32 rows of a bundle (32 * NVEC * 16 bytes per warp) ----
-// The row fetch is split in two so that it can be software-pipelined: load_rows_raw issues the
-// coalesced global loads (NVEC lanes per row) into registers -- for the NEXT bundle, while the
-// current one is being worked on -- and rows_from_raw turns them into "one whole row per lane"
-// through the staging buffer at the bundle boundary: no global latency at the start of a bundle.
-template <typename V, int NVEC>
-__device__ __forceinline__ void load_rows_raw(const unsigned char* __restrict__ table, uint32_t rid,
-                                              int lane, V (&raw)[NVEC]) {
-  constexpr uint32_t ROW_BYTES = NVEC * 16;
-  constexpr int RPI = 32 / NVEC;                          // rows per load instruction
-  const uint32_t rr = rid == RUNS_NONE ? 0u : rid;
-  const int sub = lane / NVEC, ch = lane % NVEC;
-#pragma unroll
-  for (int k = 0; k < NVEC; ++k) {
-    const uint32_t src = __shfl_sync(0xffffffffu, rr, k * RPI + sub);
-    raw[k] = ldg_v(table + (uint64_t)src * ROW_BYTES + ch * 16, V());
-  }
-}
-template <typename V, int NVEC>
-__device__ __forceinline__ void rows_from_raw(const V (&raw)[NVEC], uint32_t stage, int lane,
-                                              V (&a)[NVEC]) {
-  constexpr uint32_t ROW_BYTES = NVEC * 16;
-  constexpr int RPI = 32 / NVEC;
-  const int sub = lane / NVEC, ch = lane % NVEC;
-#pragma unroll
-  for (int k = 0; k < NVEC; ++k) sts_v(stage + (k * RPI + sub) * ROW_BYTES + ch * 16, raw[k]);
-  __syncwarp();
-  lds_row<V, NVEC>((stage + lane * ROW_BYTES) | runs_lane_rot<NVEC>(lane), a);
-  __syncwarp();
-}
-// the lanes' accumulated rows into their slots of the staging buffer (natural slice order)
-template <typename V, int NVEC>
-__device__ __forceinline__ void stage_rows(uint32_t stage, int lane, const V (&acc)[NVEC]) {
-  constexpr uint32_t ROW_BYTES = NVEC * 16;
-  const uint32_t base = (stage + lane * ROW_BYTES) | runs_lane_rot<NVEC>(lane);
-#pragma unroll
-  for (int t = 0; t < NVEC; ++t) sts_v(base ^ (uint32_t)(t << 4), acc[t]);
-}
-// flush of a whole bundle with coalesced vector REDs
-template <typename T, typename V, int NVEC>
-__device__ __forceinline__ void flush_rows_full(unsigned char* __restrict__ table, uint32_t rid,
-                                                uint32_t stage, int lane, const V (&acc)[NVEC]) {
-  constexpr uint32_t ROW_BYTES = NVEC * 16;
-  constexpr int RPI = 32 / NVEC;
-  const int sub = lane / NVEC, ch = lane % NVEC;
-  stage_rows<V, NVEC>(stage, lane, acc);
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < NVEC; ++k) {
-    const uint32_t dst = __shfl_sync(0xffffffffu, rid, k * RPI + sub);
-    if (dst != RUNS_NONE) {
-      const V v = lds_v(stage + (k * RPI + sub) * ROW_BYTES + ch * 16, V());
-      red_add_v(reinterpret_cast<T*>(table + (uint64_t)dst * ROW_BYTES + ch * 16), v);
-    }
-  }
-  __syncwarp();
-}
-// flush of a whole bundle through the TMA: one bulk reduction per lane, NOT waited for here --
-// the caller calls bulk_reads_done() before it writes the staging buffer again (a bundle later)
-template <typename T, typename V, int NVEC>
-__device__ __forceinline__ void flush_rows_full_tma(unsigned char* __restrict__ table, uint32_t rid,
-                                                    uint32_t stage, int lane, const V (&acc)[NVEC]) {
-  constexpr uint32_t ROW_BYTES = NVEC * 16;
-  stage_rows<V, NVEC>(stage, lane, acc);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (rid != RUNS_NONE) {
-    AMF_DBG_WRITE(table + (uint64_t)rid * ROW_BYTES, ROW_BYTES);
-    bulk_red_add(reinterpret_cast<T*>(table + (uint64_t)rid * ROW_BYTES), stage + lane * ROW_BYTES,
-                 ROW_BYTES);
-  }
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_reads_done() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  __syncwarp();
-}
-__device__ __forceinline__ void bulk_all_done() {
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 // first bundle whose cost prefix reaches `target`; cost(b) = 4 * first_group(b) + c0 * b
 // (entries streamed + a fixed price per bundle for the row fetch / flush)
 __device__ __forceinline__ int64_t runs_cost(const int2* __restrict__ binfo, int64_t b, int64_t c0) {

@@ -210,6 +210,8 @@ tiled_side_kernel(const uint16_t* __restrict__ idx, const T* __restrict__ rv,
       b = nb; info = ninfo; rid = nrid; mylen = nlen;
     }
   }
+  // bulk reductions still in flight complete before the CTA retires
+  if (GRAD && FLUSH_TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (sq_err) {
     const double s = block_sum(local_sq);
     if (threadIdx.x == 0) atomicAdd(sq_err, s);

@@ -627,6 +627,17 @@ def run_ours(a):
         "clocks": clocks,
         "selected": {"value": float(bv), "index": bi, "check": selection_check},
     }
+    # the resource that binds both kernels: one random factor row per candidate
+    # (and per rating and pass) through the SM's 128 B/clk load-store data pipe, on `sms` SMs
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    mhz = float(clocks["sm_mhz"]) if clocks and clocks.get("sm_mhz") else 1965.0
+    row_clk = d * es / 128.0
+    floor_score = ncand * row_clk / (sms * mhz * 1e3)
+    floor_grad = 2 * nnz * row_clk / (sms * mhz * 1e3)
+    line["binding_roof"] = {"resource": "SM load/store data pipe, 128 B/clk/SM: one %d-byte row per candidate, and per rating and pass" % (d * es),
+                            "sms": sms, "sm_mhz": mhz,
+                            "scoring_floor_ms": floor_score, "scoring_frac": floor_score / scorek_ms,
+                            "gradient_floor_ms": floor_grad, "gradient_frac": floor_grad / side_ms}
     if per_rank is not None:
         line["per_rank"] = per_rank
     if strong is not None:

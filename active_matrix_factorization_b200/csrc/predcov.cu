@@ -110,13 +110,17 @@ extern "C" {
 int amf_pred_covs(int32_t n, int32_t m, int d, int count, const double* mean_d,
                   const double* cov_d, double* out_d, void* stream) {
   AMF_REQUIRE(mean_d && cov_d && out_d, "amf_pred_covs: NULL argument");
-  AMF_REQUIRE(n > 0 && m > 0 && d >= 1 && count >= 0 && count <= 65535, "amf_pred_covs: bad sizes");
-  if (count == 0) return AMF_OK;
-  const int64_t nm2 = (int64_t)n * m * n * m;
+  AMF_REQUIRE(n > 0 && m > 0 && d >= 1 && count >= 0, "amf_pred_covs: bad sizes");
+  const int64_t nm2 = (int64_t)n * m * n * m, kdim = (int64_t)(n + m) * d;
   const int64_t blocks = (nm2 + 255) / 256;
-  const dim3 grid((unsigned)(blocks < 1024 ? blocks : 1024), (unsigned)count);
-  pred_covs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, d, mean_d, cov_d, out_d);
-  AMF_LAUNCH_CHECK();
+  for (int done = 0; done < count; done += 65535) {      // gridDim.y holds at most 65535 problems
+    const int now = count - done < 65535 ? count - done : 65535;
+    const dim3 grid((unsigned)(blocks < 1024 ? blocks : 1024), (unsigned)now);
+    pred_covs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, d, mean_d + done * kdim,
+                                                           cov_d + done * kdim * kdim,
+                                                           out_d + done * nm2);
+    AMF_LAUNCH_CHECK();
+  }
   return AMF_OK;
 }
 

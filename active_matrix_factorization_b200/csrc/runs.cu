@@ -15,21 +15,26 @@ int bits_for(uint64_t x) {
   return b;
 }
 
-// device temporaries freed on every exit path
+// device temporaries freed on every exit path.  Stream-ordered allocations from the device's
+// default pool (its release threshold is raised by acquire_partials, scoring.cu): rebuilding a pool
+// of 100M candidates needs ~3 GB of them, and cudaMalloc / cudaFree of that size cost more than
+// the sorts when the device memory is fragmented.
 struct Scratch {
+  cudaStream_t s;
   void* p[24];
   int n = 0;
+  explicit Scratch(cudaStream_t stream) : s(stream) {}
   template <typename T> cudaError_t get(T** out, size_t count) {
     *out = nullptr;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(out), (count ? count : 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(out), (count ? count : 1) * sizeof(T), s);
     if (e == cudaSuccess) p[n++] = *out;
     return e;
   }
   void drop(void* q) {
     for (int t = 0; t < n; ++t)
-      if (p[t] == q) { cudaFree(q); p[t] = p[--n]; return; }
+      if (p[t] == q) { cudaFreeAsync(q, s); p[t] = p[--n]; return; }
   }
-  ~Scratch() { for (int t = 0; t < n; ++t) cudaFree(p[t]); }
+  ~Scratch() { for (int t = 0; t < n; ++t) cudaFreeAsync(p[t], s); }
 };
 
 __global__ void runs_keys_kernel(const int32_t* __restrict__ own, const int32_t* __restrict__ other,
@@ -181,7 +186,7 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
   const int tbits = bits_for((uint64_t)nt + 1);
   AMF_REQUIRE(tbits <= 24, "bundled runs: too many tiles");
   const int grid = num_sms() * 8;
-  Scratch sc;
+  Scratch sc(s);
   int rc = AMF_OK;
   int64_t nseg = 0, n_bundles = 0, n_groups = 0;
   void* tmp = nullptr;
@@ -219,11 +224,11 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     RUNS_CUDA(cudaGetLastError());
     RUNS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, vals, perm, n, 0,
                                               ibits + jbits + tbits, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, vals, perm, n, 0,
                                               ibits + jbits + tbits, s));
     RUNS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(tmp); tmp = nullptr;
+    cudaFreeAsync(tmp, s); tmp = nullptr;
     sc.drop(keys); sc.drop(vals);
 
     // runs -> segments
@@ -233,14 +238,14 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     RUNS_CUDA(cudaGetLastError());
     tmp_bytes = 0;
     RUNS_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, head, seg_incl, cub::Max(), n, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceScan::InclusiveScan(tmp, tmp_bytes, head, seg_incl, cub::Max(), n, s));
     runs_seghead_kernel<<<grid, 256, 0, s>>>(seg_incl, n, head);
     RUNS_CUDA(cudaGetLastError());
     RUNS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(tmp); tmp = nullptr; tmp_bytes = 0;
+    cudaFreeAsync(tmp, s); tmp = nullptr; tmp_bytes = 0;
     RUNS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, head, seg_incl, n, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, seg_incl, n, s));
     {
       uint32_t last = 0;
@@ -248,7 +253,7 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
       RUNS_CUDA(cudaStreamSynchronize(s));
       nseg = last;
     }
-    cudaFree(tmp); tmp = nullptr;
+    cudaFreeAsync(tmp, s); tmp = nullptr;
     sc.drop(head);
     RUNS_CUDA(sc.get(&seg_first, (size_t)nseg));
     RUNS_CUDA(sc.get(&key2, (size_t)nseg));
@@ -263,11 +268,11 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     tmp_bytes = 0;
     RUNS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key2, key2_s, segv, sseg, nseg, 0,
                                               7 + tbits, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key2, key2_s, segv, sseg, nseg, 0,
                                               7 + tbits, s));
     RUNS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(tmp); tmp = nullptr;
+    cudaFreeAsync(tmp, s); tmp = nullptr;
 
     // segments -> bundles
     RUNS_CUDA(sc.get(&seg_start, (size_t)(nt + 1)));
@@ -278,11 +283,11 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     RUNS_CUDA(cudaGetLastError());
     tmp_bytes = 0;
     RUNS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nb, r->tile_bstart, nt + 1, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nb, r->tile_bstart, nt + 1, s));
     RUNS_CUDA(cudaMemcpyAsync(&n_bundles, r->tile_bstart + nt, 8, cudaMemcpyDeviceToHost, s));
     RUNS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(tmp); tmp = nullptr;
+    cudaFreeAsync(tmp, s); tmp = nullptr;
     r->n_bundles = n_bundles;
     RUNS_CUDA(cudaMalloc(&r->rowid, 4 * (size_t)n_bundles * 32));
     RUNS_CUDA(cudaMalloc(&r->seglen, (size_t)n_bundles * 32));
@@ -299,11 +304,11 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
     RUNS_CUDA(cudaGetLastError());
     tmp_bytes = 0;
     RUNS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, bundle_g, gstart, n_bundles + 1, s));
-    RUNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    RUNS_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
     RUNS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, bundle_g, gstart, n_bundles + 1, s));
     RUNS_CUDA(cudaMemcpyAsync(&n_groups, gstart + n_bundles, 8, cudaMemcpyDeviceToHost, s));
     RUNS_CUDA(cudaStreamSynchronize(s));
-    cudaFree(tmp); tmp = nullptr;
+    cudaFreeAsync(tmp, s); tmp = nullptr;
     if (n_groups >= (1ll << 24)) {
       set_error("bundled runs: %lld groups of entries exceed the 32-bit slot index", (long long)n_groups);
       rc = AMF_ERR_UNSUPPORTED;
@@ -342,7 +347,7 @@ int runs_build(amf_runs* r, int64_t n, const int32_t* own_d, const int32_t* othe
   }
 done:
 #undef RUNS_CUDA
-  cudaFree(tmp);
+  if (tmp) cudaFreeAsync(tmp, s);
   if (rc != AMF_OK) runs_free(r);
   return rc;
 }

@@ -123,6 +123,8 @@ PROTOTYPES = {
     "amf_mn_score_candidates": [_INT, _INT, _I64, _P, _P, _I32, _I32, _INT, _P, _P, _P, _F64, _P,
                                 _INT, _I64, _P, _P],
     "amf_blocks_half_sweep": [_P, _INT, _INT, _P, _P, _F64, _F64, _F64, _P, _P, _P, _P, _P, _P, _P],
+    "amf_blocks_fit": [_P, _INT, _F64, _F64, _F64, _F64, _INT, _INT, _F64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                       _P, C.POINTER(_INT), _P],
     "amf_blocks_sums": [_I64, _INT, _P, _P, _P, _P],
     "amf_blocks_lookahead": [C.POINTER(BlocksView), _INT, _INT, _I64, _P, _P, _INT, _P, _INT, _P,
                              _P, _P, _P, _P, _INT, _I64, _P, _P, _P],

@@ -269,6 +269,20 @@ class ActivePMF(ProbabilisticMatrixFactorization):
         return float(batch.kl_divergence()[0])
 
     def fit_normal(self):
+        if self._in_blocks():
+            # no KL is asked for: the whole coordinate descent is one library call (amf_blocks_fit),
+            # same sweeps and stopping rule as fit_normal_kls
+            if self.mean is None or self.cov is None:
+                raise ValueError("run initialize_approx first")
+            post = self._new_block_posterior()
+            n, d = self.num_users, self.latent_d
+            try:
+                post.fit(self._rating_handle(), self.mean[:n * d].reshape(n, d),
+                         self.mean[n * d:].reshape(-1, d), sweeps=self.blocks_max_sweeps,
+                         tol=self.blocks_tol)
+            finally:
+                self._adopt(post)
+            return
         for _kl in self.fit_normal_kls():
             pass
 

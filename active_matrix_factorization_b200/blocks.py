@@ -129,10 +129,31 @@ class BlockPosterior(object):
             D.ptr(getattr(self, "logdet_" + me)), D.ptr(self._fail), D.stream_ptr()))
         self._invalidate()
 
-    def fit(self, rat, users, items, **kw):
-        """fit_sweeps run to the end"""
-        for _ in self.fit_sweeps(rat, users, items, **kw):
-            pass
+    def fit(self, rat, users, items, sweeps=500, tol=1e-10, cov_term=True, update_mean=True,
+            kl_of=None):
+        """fit_sweeps run to the end.  Without a per-sweep callback the whole loop is one library
+        call (amf_blocks_fit): same sweeps, same stopping rule, no Python per sweep."""
+        if kl_of is not None or not update_mean:
+            for _ in self.fit_sweeps(rat, users, items, sweeps=sweeps, tol=tol, cov_term=cov_term,
+                                     update_mean=update_mean, kl_of=kl_of):
+                pass
+            return self
+        import ctypes as C
+        lib = N.require_device()
+        self.mean_u.copy_(_f64(users))
+        self.mean_v.copy_(_f64(items))
+        self.cov_u.zero_()
+        self.cov_v.zero_()
+        done = C.c_int(0)
+        N.check(lib.amf_blocks_fit(
+            rat.handle, self.d, self.sigma_u_sq, self.sigma_v_sq, self.sigma_sq, self.mean_offset,
+            1 if cov_term else 0, int(sweeps), float(tol),
+            D.ptr(self.mean_u), D.ptr(self.cov_u), D.ptr(self.prec_u), D.ptr(self.h_u), D.ptr(self.logdet_u),
+            D.ptr(self.mean_v), D.ptr(self.cov_v), D.ptr(self.prec_v), D.ptr(self.h_v), D.ptr(self.logdet_v),
+            D.ptr(self._fail), C.byref(done), D.stream_ptr()))
+        self.sweeps_done = int(done.value)
+        self._invalidate()
+        self._check()
         return self
 
     def fit_sweeps(self, rat, users, items, sweeps=500, tol=1e-10, cov_term=True,

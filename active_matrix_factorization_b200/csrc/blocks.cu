@@ -418,6 +418,71 @@ int amf_blocks_half_sweep(const amf_ratings_t* hc, int side, int d, const double
   return AMF_OK;
 }
 
+// largest |a - b| over n doubles, written to *out (single CTA: the tables of a posterior are small)
+__global__ void __launch_bounds__(1024)
+blocks_maxdiff_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                      const double* __restrict__ a2, const double* __restrict__ b2, int64_t n2,
+                      const int* __restrict__ fail, double* __restrict__ out) {
+  __shared__ double part[32];
+  double m = 0;
+  for (int64_t t = threadIdx.x; t < n; t += blockDim.x) m = fmax(m, fabs(a[t] - b[t]));
+  for (int64_t t = threadIdx.x; t < n2; t += blockDim.x) m = fmax(m, fabs(a2[t] - b2[t]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) { out[0] = m; out[1] = fail && *fail ? 1.0 : 0.0; }
+  }
+}
+
+int amf_blocks_fit(const amf_ratings_t* hc, int d, double sigma_u_sq, double sigma_v_sq,
+                   double sigma_sq, double mean_offset, int use_cov_term, int max_sweeps, double tol,
+                   double* mean_u_d, double* cov_u_d, double* prec_u_d, double* h_u_d,
+                   double* logdet_u_d, double* mean_v_d, double* cov_v_d, double* prec_v_d,
+                   double* h_v_d, double* logdet_v_d, int* fail_d, int* sweeps_done, void* stream) {
+  AMF_REQUIRE(hc && mean_u_d && cov_u_d && prec_u_d && h_u_d && logdet_u_d && mean_v_d && cov_v_d &&
+                  prec_v_d && h_v_d && logdet_v_d && fail_d && sweeps_done,
+              "amf_blocks_fit: NULL argument");
+  AMF_REQUIRE(max_sweeps >= 0 && d >= 1 && d <= 32, "amf_blocks_fit: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nu = (int64_t)hc->n_users * d, nv = (int64_t)hc->n_items * d;
+  double* old = nullptr;                    // previous means of both sides + {move, failed}
+  AMF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&old), sizeof(double) * (size_t)(nu + nv + 2), s));
+  double* state_h = nullptr;
+  if (cudaMallocHost(reinterpret_cast<void**>(&state_h), 2 * sizeof(double)) != cudaSuccess) {
+    cudaFreeAsync(old, s);
+    set_error("amf_blocks_fit: no pinned host memory");
+    return AMF_ERR_CUDA;
+  }
+  int rc = AMF_OK, done = 0;
+  for (int sw = 0; sw < max_sweeps && rc == AMF_OK; ++sw) {
+    cudaMemcpyAsync(old, mean_u_d, sizeof(double) * (size_t)nu, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(old + nu, mean_v_d, sizeof(double) * (size_t)nv, cudaMemcpyDeviceToDevice, s);
+    rc = amf_blocks_half_sweep(hc, 0, d, mean_v_d, use_cov_term ? cov_v_d : nullptr, sigma_u_sq,
+                               sigma_sq, mean_offset, prec_u_d, h_u_d, cov_u_d, mean_u_d, logdet_u_d,
+                               fail_d, stream);
+    if (rc == AMF_OK)
+      rc = amf_blocks_half_sweep(hc, 1, d, mean_u_d, use_cov_term ? cov_u_d : nullptr, sigma_v_sq,
+                                 sigma_sq, mean_offset, prec_v_d, h_v_d, cov_v_d, mean_v_d,
+                                 logdet_v_d, fail_d, stream);
+    if (rc != AMF_OK) break;
+    blocks_maxdiff_kernel<<<1, 1024, 0, s>>>(mean_u_d, old, nu, mean_v_d, old + nu, nv, fail_d,
+                                             old + nu + nv);
+    cudaMemcpyAsync(state_h, old + nu + nv, 2 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { rc = AMF_ERR_CUDA; set_error("amf_blocks_fit: sweep failed"); break; }
+    done = sw + 1;
+    if (state_h[1] != 0.0 || state_h[0] < tol) break;   // not positive definite (caller reads fail_d) / converged
+  }
+  *sweeps_done = done;
+  cudaFreeHost(state_h);
+  cudaFreeAsync(old, s);
+  return rc;
+}
+
 int amf_blocks_sums(int64_t rows, int d, const double* mean_d, const double* cov_d,
                     double* out_d, void* stream) {
   AMF_REQUIRE(rows >= 0 && d >= 1 && mean_d && cov_d && out_d, "amf_blocks_sums: bad arguments");

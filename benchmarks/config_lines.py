@@ -107,6 +107,10 @@ def c2_drugbank(hbm_peak):
     a.initialize_approx()
     sweeps = len(list(a.fit_normal_kls()))
     fit_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    a.initialize_approx()
+    a.fit_normal()                      # one library call (amf_blocks_fit), no KL per sweep
+    fit_fast_s = time.perf_counter() - t0
     ii, jj = unknown_cells(R, n, m)
     pool = np.column_stack((ii, jj)).astype(np.int32)
     post = a._block_posterior()
@@ -116,7 +120,9 @@ def c2_drugbank(hbm_peak):
     sd = torch.ones_like(mu)
     vals, bounds = np.array([-1., 1.]), a.rating_bounds
     out = {"config": "C2 drugbank 94x425, 500 known, rank 5, scalable mode (k = 2595 never formed)",
-           "candidates": len(ii), "values": 2, "block_fit": {"sweeps": sweeps, "seconds": fit_s}}
+           "candidates": len(ii), "values": 2,
+           "block_fit": {"sweeps": sweeps, "seconds": fit_s, "fit_normal_seconds": fit_fast_s,
+                         "note": "seconds: fit_normal_kls (KL evaluated and yielded after every sweep); fit_normal_seconds: fit_normal(), one library call"}}
     for what, code in (("uv_entropy", N.LOOK_ENTROPY), ("total_variance", N.LOOK_TOTAL_VARIANCE)):
         ms = cuda_ms(lambda: post.lookahead(code, ci, cj, vals, N.WEIGHTS_DISCRETE, bounds, mu, sd))
         out[what] = {"kernel_ms": ms, "cand_per_s": len(ii) / (ms * 1e-3),
@@ -155,7 +161,12 @@ def c3_movielens(hbm_peak):
     t0 = time.perf_counter()
     a.initialize_approx()
     sweeps = len(list(a.fit_normal_kls()))
-    out["block_fit"] = {"sweeps": sweeps, "seconds": time.perf_counter() - t0}
+    out["block_fit"] = {"sweeps": sweeps, "seconds": time.perf_counter() - t0,
+                        "note": "fit_normal_kls: the KL is evaluated and yielded after every sweep"}
+    t0 = time.perf_counter()
+    a.initialize_approx()
+    a.fit_normal()
+    out["block_fit"]["fit_normal_seconds"] = time.perf_counter() - t0   # one library call, no KL per sweep
     ii, jj = unknown_cells(R, n, m)
     nc = len(ii)
     out["candidates"] = nc

@@ -438,6 +438,18 @@ int amf_blocks_half_sweep(const amf_ratings_t* h, int side, int d, const double*
                           double mean_offset, double* prec_d, double* h_d, double* cov_d,
                           double* mean_d, double* logdet_d, int* fail_d, void* stream);
 
+/* fit_normal on the block family (active_pmf.py:251-288 restricted to blocks): full sweeps (all
+ * user rows given the items' posterior, then all item columns) until no mean moves by more than
+ * `tol` or max_sweeps are done -- the loop of amf_blocks_half_sweep calls, with the largest move of
+ * a mean and the failure flag read once per sweep, run by the library.  The means must hold the
+ * starting point; use_cov_term = 0 drops the B_j / A_i terms.  *sweeps_done = sweeps run; *fail_d
+ * (device) is left set if a precision was not positive definite. */
+int amf_blocks_fit(const amf_ratings_t* h, int d, double sigma_u_sq, double sigma_v_sq,
+                   double sigma_sq, double mean_offset, int use_cov_term, int max_sweeps, double tol,
+                   double* mean_u_d, double* cov_u_d, double* prec_u_d, double* h_u_d,
+                   double* logdet_u_d, double* mean_v_d, double* cov_v_d, double* prec_v_d,
+                   double* h_v_d, double* logdet_v_d, int* fail_d, int* sweeps_done, void* stream);
+
 /* out_d[0 : d*d] = sum_i cov_i, out_d[d*d : 2 d*d] = sum_i mean_i mean_i^T over one side: the
  * d x d sums that _total_variance (active_pmf.py:605-606) is a bilinear form of. */
 int amf_blocks_sums(int64_t rows, int d, const double* mean_d, const double* cov_d, double* out_d,

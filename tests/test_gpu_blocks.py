@@ -46,6 +46,25 @@ def _fit_device(K, R, n, m, d, U, V, s2=1., su=10., sv=10., **kw):
     return rat, post
 
 
+def test_one_call_fit_equals_the_python_driven_sweeps(K):
+    """amf_blocks_fit (the whole coordinate descent in one library call) against fit_sweeps driven
+    sweep by sweep from Python: same number of sweeps, identical tables"""
+    n, m, d = 40, 55, 4
+    R, U, V = _problem(7, n, m, d, 600)
+    rat, _ = _fit_device(K, R, n, m, d, U, V, .7, 6., 11., sweeps=1, cov_term=False, update_mean=False)
+    a = K.blocks.BlockPosterior(n, m, d, .7, 6., 11.)
+    steps = len(list(a.fit_sweeps(rat, U, V, sweeps=200, tol=1e-9)))
+    b = K.blocks.BlockPosterior(n, m, d, .7, 6., 11.)
+    b.fit(rat, U, V, sweeps=200, tol=1e-9)
+    assert b.sweeps_done == steps and 2 < steps < 200
+    ha, hb = a.to_host(), b.to_host()
+    for name in ("mean_u", "mean_v", "A", "B", "Lu", "Lv", "hu", "hv", "logdet_u", "logdet_v"):
+        np.testing.assert_array_equal(getattr(ha, name), getattr(hb, name))
+    c = K.blocks.BlockPosterior(n, m, d, .7, 6., 11.)
+    c.fit(rat, U, V, sweeps=3, tol=0.0)              # the sweep limit stops it
+    assert c.sweeps_done == 3
+
+
 @pytest.mark.parametrize("n,m,d,nnz", [(6, 7, 2, 14), (12, 20, 5, 80), (30, 40, 10, 400),
                                         (20, 25, 16, 300), (10, 12, 32, 100), (9, 5, 1, 20)])
 def test_fit_matches_oracle(K, n, m, d, nnz):

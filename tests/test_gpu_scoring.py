@@ -65,6 +65,7 @@ def test_pred_large_random(S, dtype, tol):
                                                   (64, 50, 5, 3000, 64 * 1024),
                                                   (200, 1500, 30, 20_000, 16 * 1024),
                                                   (20, 300, 7, 5000, 64 * 1024),     # runs longer than a segment
+                                                  (50, 9000, 32, 30_000, 512),      # 2250 tiles: more than a CTA has threads
                                                   (300, 9000, 32, 400_000, 64 * 1024),
                                                   (30, 20, 2, 600, 1024)])
 def test_tiled_pool_matches_flat_and_oracle(S, n, m, d, nc, tile_bytes, dtype, tol):

@@ -110,6 +110,30 @@ def test_tiled_ragged(env, dtype, tol, monkeypatch):
     np.testing.assert_allclose(gv[empty_items], -V[empty_items] / HYP["sigma_v_sq"], rtol=tol)
 
 
+def test_tiled_more_tiles_than_threads(env, monkeypatch):
+    """200,000 items in 128-row tiles = 1563 item tiles, more than the CTA's 384 threads: the
+    search for the next tile with work left takes several rounds; result equal to the row-sorted
+    kernels and the oracle"""
+    N, D, torch = env
+    monkeypatch.setenv("AMF_TILED_KB", "16")
+    rng = np.random.RandomState(3)
+    n, m, d, nnz = 300, 200_000, 32, 100_000
+    ii = rng.randint(0, n, nnz).astype(np.int32)
+    jj = rng.randint(0, m, nnz).astype(np.int32)
+    r = rng.normal(3, 1, nnz)
+    U, V = rng.normal(0, .5, (n, d)), rng.normal(0, .5, (m, d))
+    rat = D.Ratings(n, m, ii, jj, r, "f32")
+    ld = D.padded_ld(d, "f32")
+    rat.set_layout("rows")
+    ll_r, gu_r, gv_r = loss_grad(env, rat, U, V, d, ld, "f32", HYP)
+    rat.set_layout("tiled")
+    ll_t, gu_t, gv_t = loss_grad(env, rat, U, V, d, ld, "f32", HYP)
+    assert ll_t == pytest.approx(ll_r, rel=2e-5)
+    assert rel_err(gu_t, gu_r) < 2e-5 and rel_err(gv_t, gv_r) < 2e-5
+    R = np.column_stack((ii, jj, r))
+    assert ll_t == pytest.approx(O.log_likelihood(R, U, V, **HYP), rel=2e-5)
+
+
 def test_tiled_auto_threshold_and_model_api(env):
     """AUTO switches to the tiled copy from 2^20 ratings; the drop-in class sees the same
     objective and gradient either way (f32, 1e-5)"""

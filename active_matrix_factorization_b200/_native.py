@@ -107,6 +107,10 @@ PROTOTYPES = {
     "amf_ratings_append": [_P, _I64, _P, _P, _P, _P],
     "amf_ratings_compact": [_P, _P],
     "amf_best_reduce": [_P, _INT, _INT, _P, _P],
+    "amf_peer_create": [C.POINTER(_P), _INT, _INT, _P],
+    "amf_peer_connect": [_P, _P],
+    "amf_peer_best_reduce": [_P, _P, _INT, _P, _P],
+    "amf_peer_destroy": [_P],
     "amf_pred_covs": [_I32, _I32, _INT, _INT, _P, _P, _P, _P],
     "amf_slogdet_batched": [_INT, _INT, _P, _P, _P, _P],
     "amf_predicted_matrix": [_INT, _I32, _I32, _INT, _INT, _P, _P, _F64, _P, _P],

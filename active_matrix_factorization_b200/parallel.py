@@ -11,7 +11,9 @@
 The collectives go through torch.distributed so the same code runs under NCCL and gloo.
 """
 import math
+import os
 
+import numpy as np
 import torch
 
 try:
@@ -116,6 +118,58 @@ def gather_winner(best, world, group=None):
     return rec
 
 
+class PeerWinnerExchange:
+    """The winner all-gather + reduction as ONE kernel per rank over NVLink peer memory
+    (csrc/peer.cu): every rank stores its 16-byte record into every peer's mailbox, raises a flag
+    there, waits for all flags in its own and reduces.  One process per GPU on one node; mailboxes
+    are opened in the peers through CUDA IPC.  `create` returns None when that is not possible
+    (the caller then keeps the NCCL all-gather)."""
+
+    def __init__(self, handle, world):
+        self._h, self.world = handle, world
+
+    @classmethod
+    def create(cls, world, rank, group=None):
+        import ctypes as C
+        from . import _native as N
+        if world <= 1 or world > 32 or os.environ.get("AMF_PEER_EXCHANGE", "1") == "0":
+            return None
+        lib = N.require_device()
+        h = C.c_void_p()
+        mine = (C.c_ubyte * 64)()
+        ok = lib.amf_peer_create(C.byref(h), world, rank, mine) == 0
+        # every rank takes part in the handle exchange whether or not its own setup worked
+        send = torch.tensor(list(bytes(mine)) + [1 if ok else 0], dtype=torch.uint8, device='cuda')
+        allh = torch.empty((world, 65), dtype=torch.uint8, device='cuda')
+        dist.all_gather_into_tensor(allh, send.view(1, 65), group=group)
+        allh = allh.cpu().numpy()
+        good = ok and bool(allh[:, 64].all())
+        if good:
+            buf = np.ascontiguousarray(allh[:, :64]).tobytes()
+            good = lib.amf_peer_connect(h, buf) == 0
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks or none
+        if int(flag.item()) != 1:
+            if ok:
+                lib.amf_peer_destroy(h)
+            return None
+        return cls(h, world)
+
+    def reduce(self, best, maximize=True):
+        """best: this rank's amf_best_t (2 int64 words) -> the winner over all ranks, in place"""
+        from . import _native as N
+        from . import device as D
+        N.check(N.load().amf_peer_best_reduce(self._h, D.ptr(best), 1 if maximize else 0, D.ptr(best),
+                                              D.stream_ptr()))
+
+    def close(self):
+        if self._h:
+            from . import _native as N
+            torch.cuda.synchronize()
+            N.load().amf_peer_destroy(self._h)
+            self._h = None
+
+
 def winner_from_records(rec, maximize=True):
     vals = rec[:, 0].contiguous().view(torch.float64)
     return reduce_winners(vals, rec[:, 1].contiguous(), maximize)
@@ -189,6 +243,10 @@ class ShardedStep:
         self.index_base = 0
         self._rec = None
         self.pool = None          # optional scoring.Pool (tiled layout) for the pred criterion
+        # winners of the shards: one kernel over NVLink peer memory when the ranks can map each
+        # other's mailboxes (PeerWinnerExchange), else a 16-byte NCCL all-gather + a reduction launch
+        self.peer = None
+        self._peer_tried = False
         # kernels launched by one step: 2 prior + 2 side passes; scoring + winner reduction
         # (+ the reduction of the gathered winners on multi-GPU runs)
         self.launches_per_step = 6 + (1 if world > 1 else 0)
@@ -254,6 +312,13 @@ class ShardedStep:
                 C.byref(view) if view is not None else None, float(cutoff), None,
                 1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
         if self.world > 1:
+            if not self._peer_tried:
+                self._peer_tried = True
+                self.peer = PeerWinnerExchange.create(self.world, self.rank)
+            if self.peer is not None:
+                # one launch: records exchanged with remote stores over NVLink, same tie-break
+                self.peer.reduce(best, maximize)
+                return
             # 16-byte all-gather of the per-rank winners, then one launch applies the same
             # tie-break on every rank; no host sync inside the step
             rec = gather_winner(best, self.world)

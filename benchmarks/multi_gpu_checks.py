@@ -96,6 +96,43 @@ def main():
     np.testing.assert_allclose(pv[g["sub"]], g["b_pred_var_sub"], rtol=1e-9)
     res["pred_variance"] = {"max_rel_vs_fixture": float(np.abs(pv[g["sub"]] / g["b_pred_var_sub"] - 1).max())}
     out["sharded_criteria_c2"] = res
+
+    # ---- winner exchange over NVLink peer memory against the NCCL all-gather + amf_best_reduce ----
+    if world > 1:
+        from active_matrix_factorization_b200 import _native as N, device as D
+        lib = N.require_device()
+        peer = P.PeerWinnerExchange.create(world, rank)
+        ex = {"available": peer is not None}
+        if peer is not None:
+            rng = np.random.RandomState(1234)              # the same table of records on every rank
+            trials = 200
+            vals = rng.normal(size=(trials, world))
+            vals[::7] = np.round(vals[::7])                  # ties: the lowest index must win
+            idxs = rng.randint(0, 10**9, size=(trials, world)).astype(np.int64)
+            idxs[::11, 0] = -1                               # a rank without a candidate
+            vals[5, :] = np.nan                              # NaN never wins
+            t_peer = t_nccl = 0.0
+            for mx in (1, 0):
+                for t in range(trials):
+                    mine = torch.tensor([np.float64(vals[t, rank]).view(np.int64), idxs[t, rank]],
+                                        dtype=torch.int64, device="cuda")
+                    ref = mine.clone()
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    e0.record()
+                    peer.reduce(mine, bool(mx))
+                    e1.record()
+                    rec = P.gather_winner(ref, world)
+                    N.check(lib.amf_best_reduce(D.ptr(rec), world, mx, D.ptr(ref), D.stream_ptr()))
+                    e2.record()
+                    torch.cuda.synchronize()
+                    t_peer += e0.elapsed_time(e1)
+                    t_nccl += e1.elapsed_time(e2)
+                    a_, b_ = mine.cpu().numpy(), ref.cpu().numpy()
+                    assert a_[1] == b_[1] and (a_[0] == b_[0] or a_[1] < 0), (t, mx, a_, b_)
+            ex.update({"trials": 2 * trials, "equal_to_nccl_path": True,
+                       "peer_kernel_us": 1e3 * t_peer / (2 * trials), "nccl_path_us": 1e3 * t_nccl / (2 * trials)})
+            peer.close()
+        out["peer_winner_exchange"] = ex
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -227,6 +227,22 @@ int amf_sq_error_dense(int dtype, int32_t n, int32_t m, int d, int ld, const voi
                        const void* V_d, double offset, const double* real_d,
                        const unsigned char* mask_d, double* sums_d, void* stream);
 
+/* Winner exchange of a sharded pool over NVLink peer memory (one process per GPU, one node): the
+ * all-gather of the per-GPU winners + amf_best_reduce as ONE kernel per rank -- remote stores of the
+ * 16-byte record into every peer's mailbox, a release flag, an acquire wait for all peers' flags,
+ * the reduction (`chooser` over the Pool.map chunks, active_pmf.py:765-770, on several GPUs).
+ *   amf_peer_create   allocates this rank's mailbox and returns its 64-byte CUDA IPC handle;
+ *   amf_peer_connect  takes the handles of all ranks (world x 64 bytes, rank order) and maps them
+ *                     (AMF_ERR_UNSUPPORTED if a peer cannot be mapped: keep the NCCL path);
+ *   amf_peer_best_reduce  mine_d -> out_d (may alias); a collective: every rank calls it the same
+ *                     number of times in the same order; a peer that never arrives traps after ~1 s. */
+typedef struct amf_peer amf_peer_t;
+int amf_peer_create(amf_peer_t** out, int world, int rank, unsigned char* ipc_handle_out);
+int amf_peer_connect(amf_peer_t* p, const unsigned char* all_handles);
+int amf_peer_best_reduce(amf_peer_t* p, const amf_best_t* mine_d, int maximize, amf_best_t* out_d,
+                         void* stream);
+int amf_peer_destroy(amf_peer_t* p);
+
 /* Candidate pool handle: the pool bucketed once by item tile (tile_rows items) in the "bundled
  * runs" layout: the candidates one user has inside one tile are a run, one lane of the scoring
  * kernel owns a run segment (<= 64 candidates) with the whole user row in registers, and 32

@@ -148,3 +148,13 @@ def test_shard_bounds_and_reduce():
     assert P.reduce_winners(v, i, False) == (1.0, 5)
     v, idx = P.reduce_winners(torch.tensor([float('nan')], dtype=torch.float64), torch.tensor([-1]))
     assert idx == -1 and np.isnan(v)
+
+
+def test_peer_winner_exchange_is_off_for_one_rank_and_by_request(monkeypatch):
+    """the NVLink peer-memory exchange needs several ranks; world = 1, more than 32 ranks or
+    AMF_PEER_EXCHANGE=0 keep the plain path (no device, no process group touched)"""
+    from active_matrix_factorization_b200 import parallel as P
+    assert P.PeerWinnerExchange.create(1, 0) is None
+    assert P.PeerWinnerExchange.create(64, 3) is None
+    monkeypatch.setenv("AMF_PEER_EXCHANGE", "0")
+    assert P.PeerWinnerExchange.create(2, 0) is None

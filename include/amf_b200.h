@@ -266,7 +266,9 @@ int64_t amf_pool_size(const amf_pool_t* h);
  * active loop queries one candidate per step and keeps scoring the rest. */
 int amf_pool_remove(amf_pool_t* h, int64_t n, const int64_t* idx_d, void* stream);
 /* AMF_CRIT_PRED over the pool: scores_d (T[ncand], caller's order) may be NULL; best_d as in
- * amf_score_candidates (index = position in the caller's order + index_base, lowest wins ties). */
+ * amf_score_candidates (index = position in the caller's order + index_base, lowest wins ties).
+ * The pool holds the work counters and the score scratch of the launch: calls on one pool must be
+ * stream-ordered (one at a time); distinct pools may be scored concurrently. */
 int amf_pool_score_pred(const amf_pool_t* h, int dtype, int d, int ld, const void* U_d,
                         const void* V_d, void* scores_d, int maximize, int64_t index_base,
                         amf_best_t* best_d, void* stream);

@@ -121,6 +121,7 @@ PROTOTYPES = {
     "amf_pool_size": [_P],
     "amf_pool_remove": [_P, _I64, _P, _P],
     "amf_pool_score_pred": [_P, _INT, _INT, _INT, _P, _P, _P, _INT, _I64, _P, _P],
+    "amf_pool_score_pred_peer": [_P, _INT, _INT, _INT, _P, _P, _P, _INT, _I64, _P, _P, _P],
     "amf_mn_workspace_doubles": [_I32, _I32, _INT],
     "amf_mn_batched": [_INT, _INT, _I64, _P, _P, _P, _P, _P, _P, C.POINTER(NormalFitParams),
                        _P, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P],

@@ -6,68 +6,17 @@
 // call, no host synchronisation.  Mailboxes are plain cudaMalloc buffers opened in the peer
 // processes through CUDA IPC (one process per GPU, one node); epochs alternate between two slots so
 // that a fast rank two steps ahead cannot overwrite a record a slow rank is still reading.
-#include "common.cuh"
-
-struct amf_peer {
-  int world, rank;
-  unsigned char* local;        // this rank's mailbox (device memory, exported)
-  unsigned char** peers_h;     // mailbox of every rank as mapped here (peers_h[rank] == local)
-  unsigned char** peers_d;     // the same table on the device
-  unsigned int epoch;
-  bool connected;
-};
+#include "peer.cuh"
 
 namespace amf {
 namespace {
-
-constexpr int PEER_MAX = 32;
-// mailbox: Best recs[2][PEER_MAX], then unsigned flags[2][PEER_MAX]
-constexpr size_t PEER_RECS = 2 * PEER_MAX * sizeof(Best);
-constexpr size_t PEER_BYTES = PEER_RECS + 2 * PEER_MAX * sizeof(unsigned int);
-
-__device__ __forceinline__ void st_sys_v2(void* p, unsigned long long a, unsigned long long b) {
-  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 template <bool MAX>
 __global__ void __launch_bounds__(32)
 peer_best_kernel(unsigned char* const* __restrict__ peers, int world, int rank, unsigned int epoch,
                  const Best* __restrict__ mine, amf_best_t* __restrict__ out) {
   const int lane = threadIdx.x;
-  const int slot = (int)(epoch & 1u);
-  const Best me = *mine;
-  if (lane < world) {                                   // my record into peer `lane`'s mailbox
-    unsigned char* box = peers[lane];
-    Best* recs = reinterpret_cast<Best*>(box) + slot * PEER_MAX;
-    unsigned int* flags = reinterpret_cast<unsigned int*>(box + PEER_RECS) + slot * PEER_MAX;
-    st_sys_v2(&recs[rank], (unsigned long long)__double_as_longlong(me.v), (unsigned long long)me.i);
-    st_release_sys(&flags[rank], epoch);
-  }
-  Best b{0.0, -1};
-  if (lane < world) {                                   // ... and peer `lane`'s record out of mine
-    const unsigned char* box = peers[rank];
-    const Best* recs = reinterpret_cast<const Best*>(box) + slot * PEER_MAX;
-    const unsigned int* flags = reinterpret_cast<const unsigned int*>(box + PEER_RECS) + slot * PEER_MAX;
-    unsigned int spins = 0;
-    while (ld_acquire_sys(&flags[lane]) != epoch) {
-      __nanosleep(40);
-      if (++spins > (1u << 25)) {                       // > 1 s: a peer never arrived
-        printf("amf peer exchange: rank %d timed out waiting for rank %d (epoch %u)\n", rank, lane, epoch);
-        __trap();
-      }
-    }
-    b = recs[lane];
-    if (b.v != b.v) b.i = -1;                           // NaN never wins (amf_best_reduce)
-  }
-  b = warp_best<MAX>(b);
+  const Best b = peer_exchange_warp<MAX>(peers, world, rank, epoch, *mine, lane);
   if (lane == 0) { out->value = b.i < 0 ? 0.0 : b.v; out->index = b.i; }
 }
 

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 #include "runs.cuh"
 
 struct amf_pool {
@@ -22,6 +23,7 @@ struct amf_pool {
   amf_runs runs;         // own side = users, tile side = items; orig/pos_of kept
   void* tmp_scores;      // scratch for scores in slot order
   size_t tmp_bytes;
+  unsigned int* ticket;  // CTAs of the running launch that have finished (fused winner exchange)
 };
 
 namespace amf {
@@ -74,6 +76,15 @@ __device__ __forceinline__ void st_scores4(double* p, const double (&v)[4]) {
   __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v[2], v[3]));
 }
 
+// what the scoring kernel needs to finish with the cross-GPU winner exchange (peers == NULL: off)
+struct PoolPeer {
+  unsigned char* const* peers;
+  int world, rank;
+  unsigned int epoch;
+  unsigned int* ticket;
+  amf_best_t* out;
+};
+
 // PRED over a pool in the bundled-runs layout.  One CTA per SM; it starts at the item tile an
 // equal-cost split puts it on, brings the tile into shared memory by TMA, and its warps take
 // bundles of that tile from the tile's global counter until the tile is dry, then it moves to
@@ -87,7 +98,7 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
                  const uint32_t* __restrict__ rowid, const int2* __restrict__ binfo,
                  const int64_t* __restrict__ tile_bstart, uint32_t* tile_ctr, int n_tiles, int64_t n_bundles,
                  int tile_rows, int n_items, const T* __restrict__ U, const T* __restrict__ Vm,
-                 T* __restrict__ scores, int64_t index_base, Best* __restrict__ part) {
+                 T* __restrict__ scores, int64_t index_base, Best* __restrict__ part, PoolPeer pp) {
   using V = typename Vec<T>::type;
   constexpr uint32_t ROW_BYTES = NVEC * 16;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -222,6 +233,35 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
   Best best{(double)best_v, best_o < 0 ? -1 : best_o + index_base};
   best = block_best<MAX>(best);
   if (threadIdx.x == 0) part[blockIdx.x] = best;
+  if (pp.peers == nullptr) return;                    // the host launches the final reduction
+  // Fused tail (sharded pools): the LAST CTA to finish reduces the partial winners of this GPU and
+  // exchanges the result with the other GPUs over NVLink peer memory (peer.cuh) -- scoring, local
+  // arg-best and the cross-GPU "all-gather + chooser" are ONE kernel, no collective call follows.
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(pp.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Best mine{0.0, -1};
+  for (unsigned int t = threadIdx.x; t < gridDim.x; t += THREADS) {
+    const volatile Best* q = part + t;
+    const Best o{q->v, q->i};
+    if (better<MAX>(o.v, o.i, mine.v, mine.i)) mine = o;
+  }
+  mine = block_best<MAX>(mine);                       // valid in thread 0
+  if (threadIdx.x < 32) {
+    mine.v = __shfl_sync(0xffffffffu, mine.v, 0);
+    mine.i = __shfl_sync(0xffffffffu, mine.i, 0);
+    const Best all = peer_exchange_warp<MAX>(pp.peers, pp.world, pp.rank, pp.epoch, mine, (int)threadIdx.x);
+    if (threadIdx.x == 0) {
+      pp.out->value = all.i < 0 ? 0.0 : all.v;
+      pp.out->index = all.i;
+      *pp.ticket = 0;                                 // ready for the next launch on this pool
+    }
+  }
 }
 
 template <typename T>
@@ -246,7 +286,7 @@ static int pool_threads_narrow() {
 
 template <typename T, bool MAX>
 static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* scores_tmp,
-                     int64_t index_base, Best* part, int grid, cudaStream_t s) {
+                     int64_t index_base, Best* part, int grid, cudaStream_t s, PoolPeer pp) {
   constexpr int N = Vec<T>::N;
   const int nvec = ld / N;
   const amf_runs* r = &h->runs;
@@ -260,7 +300,7 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     pool_pred_kernel<T, NVEC_, MAX, THREADS_><<<grid, THREADS_, smem, s>>>(                     \
         r->idx, r->orig, r->rowid, r->binfo, r->tile_bstart, r->tile_ctr, r->n_tiles, r->n_bundles,          \
-        r->tile_rows, h->n_items, U, V, scores_tmp, index_base, part);                          \
+        r->tile_rows, h->n_items, U, V, scores_tmp, index_base, part, pp);                      \
   } while (0)
 #define POOL(NVEC_) POOL_T(NVEC_, POOL_THREADS_NARROW)
   const int narrow = pool_threads_narrow();
@@ -308,6 +348,7 @@ int amf_pool_destroy(amf_pool_t* h) {
   if (!h) return AMF_OK;
   runs_free(&h->runs);
   cudaFree(h->tmp_scores);
+  cudaFree(h->ticket);
   delete h;
   return AMF_OK;
 }
@@ -326,6 +367,12 @@ int amf_pool_create(amf_pool_t** out, int64_t ncand, const int32_t* ci_d, const 
   const int rc = runs_build(&h->runs, ncand, ci_d, cj_d, nullptr, 0, n_users, n_items,
                             tile_rows < n_items ? tile_rows : n_items, true, s);
   if (rc != AMF_OK) { delete h; return rc; }
+  if (cudaMalloc(&h->ticket, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->ticket, 0, sizeof(unsigned int)) != cudaSuccess) {
+    set_error("amf_pool_create: %s", cudaGetErrorString(cudaGetLastError()));
+    amf_pool_destroy(h);
+    return AMF_ERR_CUDA;
+  }
   *out = h;
   return AMF_OK;
 }
@@ -352,10 +399,11 @@ int amf_pool_remove(amf_pool_t* h, int64_t n, const int64_t* idx_d, void* stream
   return AMF_OK;
 }
 
-int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,
-                        const void* V_d, void* scores_d, int maximize, int64_t index_base,
-                        amf_best_t* best_d, void* stream) {
+static int pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,
+                           const void* V_d, void* scores_d, int maximize, int64_t index_base,
+                           amf_peer_t* peer, amf_best_t* best_d, void* stream) {
   AMF_REQUIRE(hc && U_d && V_d && best_d, "amf_pool_score_pred: NULL argument");
+  AMF_REQUIRE(!peer || peer->connected, "amf_pool_score_pred_peer: amf_peer_connect has not been called");
   AMF_REQUIRE(dtype == AMF_F32 || dtype == AMF_F64, "amf_pool_score_pred: bad dtype");
   amf_pool* h = const_cast<amf_pool*>(hc);
   cudaStream_t s = (cudaStream_t)stream;
@@ -384,12 +432,15 @@ int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const vo
   int64_t grid64 = (int64_t)num_sms();
   if (grid64 > r->n_bundles) grid64 = r->n_bundles > 0 ? r->n_bundles : 1;
   const int grid = (int)grid64;
+  PoolPeer pp{nullptr, 1, 0, 0u, nullptr, nullptr};
+  if (peer)       // a collective: every rank calls in the same order, so the epochs agree
+    pp = PoolPeer{peer->peers_d, peer->world, peer->rank, ++peer->epoch, h->ticket, best_d};
   if (dtype == AMF_F32)
-    rc = maximize ? pool_pred<float, true>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s)
-                  : pool_pred<float, false>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s);
+    rc = maximize ? pool_pred<float, true>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s, pp)
+                  : pool_pred<float, false>(h, ld, (const float*)U_d, (const float*)V_d, (float*)tmp_scores, index_base, part, grid, s, pp);
   else
-    rc = maximize ? pool_pred<double, true>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s)
-                  : pool_pred<double, false>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s);
+    rc = maximize ? pool_pred<double, true>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s, pp)
+                  : pool_pred<double, false>(h, ld, (const double*)U_d, (const double*)V_d, (double*)tmp_scores, index_base, part, grid, s, pp);
   if (rc != AMF_OK) return rc;
   if (tmp_scores) {
     const int g2 = num_sms() * 8;
@@ -397,8 +448,22 @@ int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const vo
     else unpermute_kernel<double><<<g2, 256, 0, s>>>((const double*)tmp_scores, r->orig, r->npos, (double*)scores_d);
     AMF_LAUNCH_CHECK();
   }
+  if (peer) return AMF_OK;                 // the scoring kernel's last CTA wrote best_d; the guard frees the partials
   guard.armed = false;                     // launch_best_final frees the partials
   return launch_best_final(part, grid, maximize != 0, best_d, s);
+}
+
+int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,
+                        const void* V_d, void* scores_d, int maximize, int64_t index_base,
+                        amf_best_t* best_d, void* stream) {
+  return pool_score_pred(hc, dtype, d, ld, U_d, V_d, scores_d, maximize, index_base, nullptr, best_d, stream);
+}
+
+int amf_pool_score_pred_peer(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,
+                             const void* V_d, void* scores_d, int maximize, int64_t index_base,
+                             amf_peer_t* peer, amf_best_t* best_d, void* stream) {
+  AMF_REQUIRE(peer, "amf_pool_score_pred_peer: NULL peer");
+  return pool_score_pred(hc, dtype, d, ld, U_d, V_d, scores_d, maximize, index_base, peer, best_d, stream);
 }
 
 #pragma GCC visibility pop

@@ -249,7 +249,7 @@ class ShardedStep:
         self._peer_tried = False
         # kernels launched by one step: 2 prior + 2 side passes; scoring + winner reduction
         # (+ the reduction of the gathered winners on multi-GPU runs)
-        self.launches_per_step = 6 + (1 if world > 1 else 0)
+        self.launches_per_step = 6 + (1 if world > 1 else 0)   # (5 with the fused winner exchange)
 
     def set_candidate_offset(self, ncand_local):
         """global index = offset of this rank's shard + local index"""
@@ -303,8 +303,15 @@ class ShardedStep:
             self.set_candidate_offset(int(ci.numel()))
             self._rec = True
         lib = N.require_device()
+        if self.world > 1 and not self._peer_tried:
+            self._peer_tried = True
+            self.peer = PeerWinnerExchange.create(self.world, self.rank)
         if self.pool is not None and criterion == N.CRIT_PRED:
-            self.pool.score_pred(U, V, False, maximize, self.index_base, best)
+            # with a peer exchange the scoring kernel itself ends with the cross-GPU winner
+            self.pool.score_pred(U, V, False, maximize, self.index_base, best, peer=self.peer)
+            if self.peer is not None:
+                self.launches_per_step = 5     # 2 prior + 2 side passes + the scoring kernel
+                return
         else:
             N.check(lib.amf_score_candidates(
                 criterion, D.code(self.name), int(ci.numel()), D.ptr(ci), D.ptr(cj), self.d,
@@ -312,9 +319,6 @@ class ShardedStep:
                 C.byref(view) if view is not None else None, float(cutoff), None,
                 1 if maximize else 0, self.index_base, D.ptr(best), D.stream_ptr()))
         if self.world > 1:
-            if not self._peer_tried:
-                self._peer_tried = True
-                self.peer = PeerWinnerExchange.create(self.world, self.rank)
             if self.peer is not None:
                 # one launch: records exchanged with remote stores over NVLink, same tie-break
                 self.peer.reduce(best, maximize)

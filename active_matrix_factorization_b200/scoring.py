@@ -178,15 +178,21 @@ class Pool:
         N.check(lib.amf_pool_create(C.byref(self._h), self.ncand, D.ptr(ci), D.ptr(cj),
                                     self.n_users, self.n_items, self.tile_rows, D.stream_ptr()))
 
-    def score_pred(self, U, V, want_scores=False, maximize=True, index_base=0, best=None):
+    def score_pred(self, U, V, want_scores=False, maximize=True, index_base=0, best=None, peer=None):
         """U, V: device tensors padded to (rows, self.ld) -- see pad().  Returns (scores tensor
-        or None, best record tensor)."""
+        or None, best record tensor).  peer = a connected parallel.PeerWinnerExchange: the winner
+        over all ranks' shards, exchanged inside the scoring kernel (a collective call)."""
         lib = N.require_device()
         assert U.shape[1] == self.ld and V.shape[1] == self.ld, "use Pool.pad() for the factors"
         scores = torch.empty(self.ncand, dtype=D.torch_dtype(self.name), device=U.device) \
             if want_scores else None
         if best is None:
             best = torch.empty(2, dtype=torch.int64, device=U.device)
+        if peer is not None:
+            N.check(lib.amf_pool_score_pred_peer(self._h, D.code(self.name), self.d, U.shape[1], D.ptr(U),
+                                                 D.ptr(V), D.ptr(scores), 1 if maximize else 0,
+                                                 int(index_base), peer._h, D.ptr(best), D.stream_ptr()))
+            return scores, best
         N.check(lib.amf_pool_score_pred(self._h, D.code(self.name), self.d, U.shape[1], D.ptr(U),
                                         D.ptr(V), D.ptr(scores), 1 if maximize else 0,
                                         int(index_base), D.ptr(best), D.stream_ptr()))

@@ -526,9 +526,8 @@ def run_ours(a):
         sl_best = torch.zeros(2, dtype=torch.int64, device=U.device)
 
         def strong_step():
-            sl_pool.score_pred(U, V, False, True, lo, sl_best)
+            sl_pool.score_pred(U, V, False, True, lo, sl_best, peer=step.peer)
             if step.peer is not None:
-                step.peer.reduce(sl_best, True)
                 return
             rec = P.gather_winner(sl_best, world)
             N.check(lib.amf_best_reduce(D.ptr(rec), world, 1, D.ptr(sl_best), D.stream_ptr()))
@@ -642,7 +641,7 @@ def run_ours(a):
                             "scoring_floor_ms": floor_score, "scoring_frac": floor_score / scorek_ms,
                             "gradient_floor_ms": floor_grad, "gradient_frac": floor_grad / side_ms}
     if world > 1:
-        line["selection_collective"] = ("one kernel per rank over NVLink peer memory (CUDA IPC mailboxes, csrc/peer.cu)"
+        line["selection_collective"] = ("fused into the scoring kernel: its last CTA exchanges the winners over NVLink peer memory (CUDA IPC mailboxes, csrc/peer.cuh)"
                                         if step.peer is not None else "NCCL all-gather of 16-byte records + amf_best_reduce")
     if per_rank is not None:
         line["per_rank"] = per_rank

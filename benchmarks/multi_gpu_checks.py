@@ -129,6 +129,28 @@ def main():
                     t_nccl += e1.elapsed_time(e2)
                     a_, b_ = mine.cpu().numpy(), ref.cpu().numpy()
                     assert a_[1] == b_[1] and (a_[0] == b_[0] or a_[1] < 0), (t, mx, a_, b_)
+            # the exchange fused into the pool scoring kernel (amf_pool_score_pred_peer): every rank
+            # scores its own random shard; the winner over all shards must equal the NCCL path's
+            from active_matrix_factorization_b200 import scoring as S
+            rs = np.random.RandomState(100 + rank)
+            nu, ni, dd, nc = 500, 3000, 32, 200_000
+            Uh = np.random.RandomState(7).normal(size=(nu, dd))
+            Vh = np.random.RandomState(8).normal(size=(ni, dd))
+            ii, jj = rs.randint(0, nu, nc), rs.randint(0, ni, nc)
+            for name in ("f32", "f64"):
+                pool = S.Pool(ii, jj, nu, ni, name, dd, tile_bytes=64 * 1024)
+                Ut, Vt = pool.pad(Uh), pool.pad(Vh)
+                for mx in (True, False):
+                    for rep in range(3):
+                        _, fused = pool.score_pred(Ut, Vt, maximize=mx, index_base=rank * nc, peer=peer)
+                        _, local = pool.score_pred(Ut, Vt, maximize=mx, index_base=rank * nc)
+                        rec = P.gather_winner(local, world)
+                        ref = torch.empty(2, dtype=torch.int64, device="cuda")
+                        N.check(lib.amf_best_reduce(D.ptr(rec), world, 1 if mx else 0, D.ptr(ref), D.stream_ptr()))
+                        torch.cuda.synchronize()
+                        assert (fused.cpu().numpy() == ref.cpu().numpy()).all(), (name, mx, fused, ref)
+                pool.close()
+            ex["fused_into_pool_kernel_equal_to_nccl_path"] = True
             ex.update({"trials": 2 * trials, "equal_to_nccl_path": True,
                        "peer_kernel_us": 1e3 * t_peer / (2 * trials), "nccl_path_us": 1e3 * t_nccl / (2 * trials)})
             peer.close()

@@ -273,6 +273,15 @@ int amf_pool_score_pred(const amf_pool_t* h, int dtype, int d, int ld, const voi
                         const void* V_d, void* scores_d, int maximize, int64_t index_base,
                         amf_best_t* best_d, void* stream);
 
+/* The same with the cross-GPU winner exchange fused into the scoring kernel (sharded pools, one
+ * process per GPU): the last CTA to finish reduces this GPU's partial winners and exchanges the
+ * record with the other GPUs over NVLink peer memory (amf_peer_*), so that best_d holds the winner
+ * over ALL shards when the kernel ends -- scoring, arg-best and the "all-gather + chooser" of
+ * active_pmf.py:765-770 in ONE launch.  A collective: every rank calls it in the same order. */
+int amf_pool_score_pred_peer(const amf_pool_t* h, int dtype, int d, int ld, const void* U_d,
+                             const void* V_d, void* scores_d, int maximize, int64_t index_base,
+                             amf_peer_t* peer, amf_best_t* best_d, void* stream);
+
 /* End-to-end host variant of AMF_CRIT_PRED: host candidate arrays and factors in, scores
  * (may be NULL) and winner out; synchronises. */
 int amf_score_pred_host(int dtype, int64_t ncand, const int32_t* ci_h, const int32_t* cj_h,

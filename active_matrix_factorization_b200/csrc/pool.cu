@@ -233,10 +233,9 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
   Best best{(double)best_v, best_o < 0 ? -1 : best_o + index_base};
   best = block_best<MAX>(best);
   if (threadIdx.x == 0) part[blockIdx.x] = best;
-  if (pp.peers == nullptr) return;                    // the host launches the final reduction
-  // Fused tail (sharded pools): the LAST CTA to finish reduces the partial winners of this GPU and
-  // exchanges the result with the other GPUs over NVLink peer memory (peer.cuh) -- scoring, local
-  // arg-best and the cross-GPU "all-gather + chooser" are ONE kernel, no collective call follows.
+  // Fused tail: the LAST CTA to finish reduces the partial winners of this GPU and, for a sharded
+  // pool, exchanges the result with the other GPUs over NVLink peer memory (peer.cuh) -- scoring,
+  // arg-best and the cross-GPU "all-gather + chooser" are ONE kernel, nothing is launched after it.
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -255,7 +254,10 @@ pool_pred_kernel(const uint16_t* __restrict__ idx, const uint32_t* __restrict__ 
   if (threadIdx.x < 32) {
     mine.v = __shfl_sync(0xffffffffu, mine.v, 0);
     mine.i = __shfl_sync(0xffffffffu, mine.i, 0);
-    const Best all = peer_exchange_warp<MAX>(pp.peers, pp.world, pp.rank, pp.epoch, mine, (int)threadIdx.x);
+    Best all = mine;
+    if (all.v != all.v) all.i = -1;                   // NaN never wins
+    if (pp.peers)
+      all = peer_exchange_warp<MAX>(pp.peers, pp.world, pp.rank, pp.epoch, mine, (int)threadIdx.x);
     if (threadIdx.x == 0) {
       pp.out->value = all.i < 0 ? 0.0 : all.v;
       pp.out->index = all.i;
@@ -432,7 +434,7 @@ static int pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const
   int64_t grid64 = (int64_t)num_sms();
   if (grid64 > r->n_bundles) grid64 = r->n_bundles > 0 ? r->n_bundles : 1;
   const int grid = (int)grid64;
-  PoolPeer pp{nullptr, 1, 0, 0u, nullptr, nullptr};
+  PoolPeer pp{nullptr, 1, 0, 0u, h->ticket, best_d};
   if (peer)       // a collective: every rank calls in the same order, so the epochs agree
     pp = PoolPeer{peer->peers_d, peer->world, peer->rank, ++peer->epoch, h->ticket, best_d};
   if (dtype == AMF_F32)
@@ -448,9 +450,7 @@ static int pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const
     else unpermute_kernel<double><<<g2, 256, 0, s>>>((const double*)tmp_scores, r->orig, r->npos, (double*)scores_d);
     AMF_LAUNCH_CHECK();
   }
-  if (peer) return AMF_OK;                 // the scoring kernel's last CTA wrote best_d; the guard frees the partials
-  guard.armed = false;                     // launch_best_final frees the partials
-  return launch_best_final(part, grid, maximize != 0, best_d, s);
+  return AMF_OK;                           // the scoring kernel's last CTA wrote best_d; the guard frees the partials
 }
 
 int amf_pool_score_pred(const amf_pool_t* hc, int dtype, int d, int ld, const void* U_d,

@@ -309,8 +309,10 @@ class ShardedStep:
         if self.pool is not None and criterion == N.CRIT_PRED:
             # with a peer exchange the scoring kernel itself ends with the cross-GPU winner
             self.pool.score_pred(U, V, False, maximize, self.index_base, best, peer=self.peer)
+            # 2 prior + 2 side passes + the scoring kernel (which ends with the winner reduction and,
+            # with a peer exchange, the cross-GPU winner); + 1 for the NCCL fallback's reduction
+            self.launches_per_step = 5 if (self.world == 1 or self.peer is not None) else 6
             if self.peer is not None:
-                self.launches_per_step = 5     # 2 prior + 2 side passes + the scoring kernel
                 return
         else:
             N.check(lib.amf_score_candidates(

@@ -283,7 +283,7 @@ template <int NVEC, int THREADS> static size_t pool_smem(int tile_rows) {
 static int pool_threads_narrow() {
   const char* e = getenv("AMF_POOL_THREADS");
   const int t = e ? atoi(e) : POOL_THREADS_NARROW;
-  return (t == 256 || t == 384 || t == 640 || t == 768) ? t : POOL_THREADS_NARROW;
+  return (t == 256 || t == 384 || t == 448 || t == 576 || t == 640 || t == 768) ? t : POOL_THREADS_NARROW;
 }
 
 template <typename T, bool MAX>
@@ -312,7 +312,8 @@ static int pool_pred(const amf_pool* h, int ld, const T* U, const T* V, T* score
     case 4: POOL(4); break;
     case 8:
       if (narrow == 768) POOL_T(8, 768); else if (narrow == 640) POOL_T(8, 640);
-      else if (narrow == 384) POOL_T(8, 384); else if (narrow == 256) POOL_T(8, 256); else POOL(8);
+      else if (narrow == 384) POOL_T(8, 384); else if (narrow == 256) POOL_T(8, 256);
+      else if (narrow == 448) POOL_T(8, 448); else if (narrow == 576) POOL_T(8, 576); else POOL(8);
       break;
     case 16: POOL_T(16, POOL_THREADS_WIDE); break;
     default:

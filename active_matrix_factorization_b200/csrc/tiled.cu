@@ -25,7 +25,8 @@ constexpr int64_t TILED_BUNDLE_COST = 10;   // row fetch + flush of a bundle, in
 constexpr size_t TILED_SMEM_BUDGET = 227 * 1024 - 1024;
 
 #ifndef AMF_TILED_THREADS
-#define AMF_TILED_THREADS 384                        // measured best of 256 / 384 / 512 (benchmarks/variant_lib.sh)
+#define AMF_TILED_THREADS 448                        // measured at C5 (benchmarks/variant_lib.sh): 256 1.094, 320 1.016,
+                                                     // 352 0.971, 384 0.943, 416 1.003, 448 0.925, 480 0.993, 512 0.952 ms
 #endif
 template <typename T, int NVEC> constexpr int tiled_threads() {
   return NVEC * 12 > 96 ? 256 : AMF_TILED_THREADS;   // three rows of registers per lane (own, accumulator, tile row)
